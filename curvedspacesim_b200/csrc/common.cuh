@@ -1,0 +1,89 @@
+// Shared device-side definitions for the geodesic MD hot path (sm_100a, fp64).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace css {
+
+// ---- mesh in HBM (L2-resident at 1 M faces: 16 MB vertices + 16 MB corners + 16 MB adjacency) ----
+// vertices : double4 {x,y,z,0}   one 32-byte sector per gather
+// corners  : int4 {c0,c1,c2,0}   reference corner order
+// adjacency: int4 {a0,a1,a2,kk}  a_k = face across the edge opposite corner k (-1 border);
+//                                kk packs the index of that edge inside the neighbour, 2 bits per k
+struct MeshDev {
+    int nV, nF;
+    const double4* vert;
+    const int4* corner;
+    const int4* adj;
+    const unsigned char* saddle; // per-vertex: interior angle sum >= 2 pi  (pseudo-source candidate)
+};
+
+struct CellGrid {
+    double mn[3], cs[3];
+    int n[3];
+    double range2;
+};
+
+struct ForceParams {
+    int kind;
+    double a, sigma; // harmonic: k, sigma ; gaussian: alpha, sigma
+};
+
+struct d3 {
+    double x, y, z;
+};
+
+// ---- exactly-rounded arithmetic (never contracted into FMA) --------------------------------------
+// Used wherever a branch or an index decision must be bit-identical to the CPU oracle: cell binning,
+// candidate selection, patch membership, the whole walker.
+__device__ __forceinline__ double xmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double xadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double xsub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double xdiv(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ double xsqrt(double a) { return __dsqrt_rn(a); }
+
+__device__ __forceinline__ d3 xsub3(const d3& a, const d3& b) { return d3{xsub(a.x, b.x), xsub(a.y, b.y), xsub(a.z, b.z)}; }
+__device__ __forceinline__ d3 xadd3(const d3& a, const d3& b) { return d3{xadd(a.x, b.x), xadd(a.y, b.y), xadd(a.z, b.z)}; }
+__device__ __forceinline__ d3 xscale(double s, const d3& a) { return d3{xmul(s, a.x), xmul(s, a.y), xmul(s, a.z)}; }
+__device__ __forceinline__ d3 xdivs(const d3& a, double s) { return d3{xdiv(a.x, s), xdiv(a.y, s), xdiv(a.z, s)}; }
+__device__ __forceinline__ double xdot(const d3& a, const d3& b) { return xadd(xadd(xmul(a.x, b.x), xmul(a.y, b.y)), xmul(a.z, b.z)); }
+__device__ __forceinline__ d3 xcross(const d3& a, const d3& b)
+{
+    return d3{xsub(xmul(a.y, b.z), xmul(a.z, b.y)), xsub(xmul(a.z, b.x), xmul(a.x, b.z)), xsub(xmul(a.x, b.y), xmul(a.y, b.x))};
+}
+__device__ __forceinline__ double xsqlen(const d3& a) { return xdot(a, a); }
+__device__ __forceinline__ double xnorm(const d3& a) { return xsqrt(xsqlen(a)); }
+
+__device__ __forceinline__ d3 ldvert(const MeshDev& m, int v)
+{
+    const double2* p = reinterpret_cast<const double2*>(m.vert + v);
+    double2 a = __ldg(p);
+    double2 b = __ldg(p + 1);
+    return d3{a.x, a.y, b.x};
+}
+
+// (b0 p0 + b1 p1 + b2 p2) / (b0 + b1 + b2)   [PMP::construct_point, SURVEY.md §8(c)-C3]
+__device__ __forceinline__ d3 xpoint(const d3& p0, const d3& p1, const d3& p2, double b0, double b1, double b2)
+{
+    double s = xadd(xadd(b0, b1), b2);
+    return d3{xdiv(xadd(xadd(xmul(b0, p0.x), xmul(b1, p1.x)), xmul(b2, p2.x)), s),
+              xdiv(xadd(xadd(xmul(b0, p0.y), xmul(b1, p1.y)), xmul(b2, p2.y)), s),
+              xdiv(xadd(xadd(xmul(b0, p0.z), xmul(b1, p1.z)), xmul(b2, p2.z)), s)};
+}
+
+__device__ __forceinline__ int cellCoord(const CellGrid& g, double x, int d)
+{
+    int c = (int)floor(xdiv(xsub(x, g.mn[d]), g.cs[d]));
+    return max(0, min(g.n[d] - 1, c));
+}
+
+// walker flag bits / counters (mirrors include/css_api.h)
+enum { WALK_VERTEX = 1, WALK_NOHIT = 2, WALK_ITERCAP = 4, WALK_NAN = 8, WALK_BORDER = 16 };
+enum {
+    C_WALK_VERTEX = 0, C_WALK_NOHIT, C_WALK_ITERCAP, C_WALK_NAN, C_WALK_BORDER, C_DISCONNECTED, C_TIES, C_CROSSINGS, C_WINDOWS,
+    C_PSEUDO, C_PATCH_FACES, C_PATCH_VERTS, C_QUERIES, C_SOURCES, C_TIER_RETRY, C_OVERFLOW, C_KERNELS, C_KMAX_OVERFLOW,
+    NUM_COUNTERS = 24
+};
+#define CSS_WALK_MAX_CROSSINGS 100000
+
+} // namespace css

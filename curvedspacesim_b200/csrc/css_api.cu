@@ -1,0 +1,1118 @@
+// C ABI of the B200-native geodesic MD hot path (see include/css_api.h for the reference interfaces
+// each entry point replaces).  Host side: owns device memory, one stream, the tiered launch of the
+// geodesic kernel and (optionally) one NCCL communicator.  No CPU fallback exists: every entry point
+// that computes launches CUDA kernels and fails with CSS_ECUDA when no device is usable.
+#include "../../include/css_api.h"
+#include "kernels.h"
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <nccl.h>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+using namespace css;
+
+struct css_ctx {
+    int device = 0;
+    cudaStream_t st = nullptr;
+    std::string err;
+    // mesh
+    int nV = 0, nF = 0;
+    double4* d_vert = nullptr;
+    int4* d_corner = nullptr;
+    int4* d_adj = nullptr;
+    unsigned char* d_saddle = nullptr;
+    double bbmin[3] = {0, 0, 0}, bbmax[3] = {0, 0, 0}, area = 0;
+    double cellMin[3] = {0, 0, 0}, cellMax[3] = {0, 0, 0};
+    bool submeshing = false;
+    double maxDist = 0;
+    bool useCellList = true, wantEnd = false;
+    // particles
+    int nLocal = 0, nTotal = 0, minIdx = 0, capLocal = 0, capTotal = 0;
+    int* d_face = nullptr;
+    double *d_bary = nullptr, *d_eucl = nullptr, *d_vel = nullptr, *d_frc = nullptr, *d_disp = nullptr;
+    int* d_walkFlags = nullptr;
+    // cell list
+    CellGrid grid{};
+    double gridRange = -1;
+    int nCells = 0, capCells = 0;
+    int *d_cellOf = nullptr, *d_cellCount = nullptr, *d_cellStart = nullptr, *d_blockSums = nullptr, *d_fill = nullptr, *d_tmpItems = nullptr,
+        *d_items = nullptr;
+    // neighbours (fixed stride kmax)
+    int kmax = 32, capNbr = 0;
+    bool nbrHasEnd = false;
+    int* d_nbrCount = nullptr;
+    int* d_nbrIdx = nullptr;
+    double *d_nbrDist = nullptr, *d_nbrTs = nullptr, *d_nbrTe = nullptr;
+    bool nbrValid = false;
+    // geodesic tiers
+    int *d_work = nullptr, *d_retry[3] = {nullptr, nullptr, nullptr};
+    int capRetry = 0;
+    char* d_gws = nullptr;
+    size_t gwsBytes = 0;
+    GeoCaps capsT0{96, 64, 64, 16, 256, 256}, capsT1{768, 448, 1024, 128, 2048, 1024}, capsT2{0, 0, 0, 0, 0, 0};
+    int t2Warps = 32;
+    int numSMs = 148;
+    // reductions / scratch
+    double *d_partial = nullptr, *d_red = nullptr;
+    unsigned long long* d_counters = nullptr;
+    unsigned long long hostKernels = 0;
+    // updaters
+    struct {
+        double dt, dt2, dt4, dt8, T, tau;
+        int M = 0;
+        std::vector<double> bx, by, bz, bw;
+        double KE = 0, scale = 1;
+    } nh;
+    struct FireState {
+        double dt = 0.001, alpha = 0.99;
+        int maximumIterations = 1000, nMin = 4, nSinceNegativePower = 0, iterations = 0;
+        double alphaStart = 0.99, deltaTMax = 0.1, deltaTInc = 1.1, deltaTMin = 1e-5, deltaTDec = 0.95, alphaDec = 0.9, forceCutoff = 1e-12,
+               alphaMin = 0.0;
+        double forceMax = 0;
+    } fire;
+    // comm
+    ncclComm_t comm = nullptr;
+    int rank = 0, nranks = 1;
+    int* d_sendI = nullptr;
+    double* d_sendD = nullptr;
+    int* d_recvI = nullptr;
+    double* d_recvD = nullptr;
+    int capComm = 0;
+    double* d_redBuf = nullptr;
+    // timing
+    bool timing = false;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    float msGeo = 0, msWalk = 0, msCell = 0;
+};
+
+static int fail(css_ctx* c, int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    return code;
+}
+#define CU(call)                                                                                                         \
+    do {                                                                                                                 \
+        cudaError_t e_ = (call);                                                                                         \
+        if (e_ != cudaSuccess) return fail(ctx, CSS_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+#define NC(call)                                                                                                         \
+    do {                                                                                                                 \
+        ncclResult_t e_ = (call);                                                                                        \
+        if (e_ != ncclSuccess) return fail(ctx, CSS_ENCCL, "%s failed: %s", #call, ncclGetErrorString(e_));              \
+    } while (0)
+#define BIND() CU(cudaSetDevice(ctx->device))
+
+template <class T> static cudaError_t regrow(T*& p, size_t n)
+{
+    if (p) cudaFree(p);
+    p = nullptr;
+    return cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T));
+}
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+int css_create(css_ctx** out, int device)
+{
+    if (!out) return CSS_EINVAL;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0 || device < 0 || device >= n) return CSS_ECUDA;
+    css_ctx* ctx = new css_ctx();
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return CSS_ECUDA;
+    }
+    cudaDeviceGetAttribute(&ctx->numSMs, cudaDevAttrMultiProcessorCount, device);
+    cudaMalloc(&ctx->d_counters, NUM_COUNTERS * sizeof(unsigned long long));
+    cudaMemset(ctx->d_counters, 0, NUM_COUNTERS * sizeof(unsigned long long));
+    cudaMalloc(&ctx->d_work, 16 * sizeof(int));
+    cudaMalloc(&ctx->d_partial, REDUCE_MAX_BLOCKS * 5 * sizeof(double));
+    cudaMalloc(&ctx->d_red, 8 * sizeof(double));
+    for (auto& e : ctx->ev) cudaEventCreate(&e);
+    *out = ctx;
+    return CSS_OK;
+}
+
+int css_destroy(css_ctx* ctx)
+{
+    if (!ctx) return CSS_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->st);
+    if (ctx->comm) ncclCommDestroy(ctx->comm);
+    void* ptrs[] = {ctx->d_vert,   ctx->d_corner,    ctx->d_adj,     ctx->d_saddle,  ctx->d_face,     ctx->d_bary,    ctx->d_eucl,
+                    ctx->d_vel,    ctx->d_frc,       ctx->d_disp,    ctx->d_walkFlags, ctx->d_cellOf, ctx->d_cellCount, ctx->d_cellStart,
+                    ctx->d_blockSums, ctx->d_fill,   ctx->d_tmpItems, ctx->d_items,  ctx->d_nbrCount, ctx->d_nbrIdx,  ctx->d_nbrDist,
+                    ctx->d_nbrTs,  ctx->d_nbrTe,     ctx->d_work,    ctx->d_retry[0], ctx->d_retry[1], ctx->d_retry[2], ctx->d_gws,
+                    ctx->d_partial, ctx->d_red,      ctx->d_counters, ctx->d_sendI,  ctx->d_sendD,    ctx->d_recvI,   ctx->d_recvD,
+                    ctx->d_redBuf};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    for (auto& e : ctx->ev)
+        if (e) cudaEventDestroy(e);
+    cudaStreamDestroy(ctx->st);
+    delete ctx;
+    return CSS_OK;
+}
+
+const char* css_last_error(css_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+// ------------------------------------------------------------------------------------------ mesh
+int css_set_mesh(css_ctx* ctx, int nV, const double* xyz, int nF, const int32_t* corners)
+{
+    if (!ctx || nV <= 0 || nF <= 0 || !xyz || !corners) return fail(ctx, CSS_EINVAL, "css_set_mesh: bad arguments");
+    BIND();
+    for (int i = 0; i < 3 * nF; ++i)
+        if (corners[i] < 0 || corners[i] >= nV) return fail(ctx, CSS_EMESH, "Invalid input file."); // triangulatedMeshSpace.cpp:55
+    // directed-edge map -> adjacency (what CGAL::Surface_mesh connectivity provides to the reference)
+    std::unordered_map<uint64_t, int> half;
+    half.reserve((size_t)nF * 6);
+    auto key = [](int a, int b) { return ((uint64_t)(uint32_t)a << 32) | (uint32_t)b; };
+    for (int f = 0; f < nF; ++f)
+        for (int k = 0; k < 3; ++k) {
+            int a = corners[3 * f + (k + 1) % 3], b = corners[3 * f + (k + 2) % 3];
+            if (a == b || !half.emplace(key(a, b), 3 * f + k).second)
+                return fail(ctx, CSS_EMESH, "mesh is not a consistently oriented manifold triangle mesh (face %d)", f);
+        }
+    std::vector<int4> hc(nF), ha(nF);
+    for (int f = 0; f < nF; ++f) {
+        int a3[3], kk = 0;
+        for (int k = 0; k < 3; ++k) {
+            int a = corners[3 * f + (k + 1) % 3], b = corners[3 * f + (k + 2) % 3];
+            auto it = half.find(key(b, a));
+            if (it == half.end()) a3[k] = -1;
+            else {
+                a3[k] = it->second / 3;
+                kk |= (it->second % 3) << (2 * k);
+            }
+        }
+        hc[f] = make_int4(corners[3 * f], corners[3 * f + 1], corners[3 * f + 2], 0);
+        ha[f] = make_int4(a3[0], a3[1], a3[2], kk);
+    }
+    // bounding box seeded with the origin (triangulatedMeshSpace::updateMeshSpanAndTree :9-30), area, angle sums
+    std::vector<double4> hv(nV);
+    for (int d = 0; d < 3; ++d) ctx->bbmin[d] = ctx->bbmax[d] = 0;
+    for (int i = 0; i < nV; ++i) {
+        hv[i] = make_double4(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], 0);
+        for (int d = 0; d < 3; ++d) {
+            ctx->bbmin[d] = std::min(ctx->bbmin[d], xyz[3 * i + d]);
+            ctx->bbmax[d] = std::max(ctx->bbmax[d], xyz[3 * i + d]);
+        }
+    }
+    std::vector<double> ang(nV, 0.0);
+    double area = 0;
+    for (int f = 0; f < nF; ++f) {
+        for (int k = 0; k < 3; ++k) {
+            const double* p = xyz + 3 * corners[3 * f + k];
+            const double* q = xyz + 3 * corners[3 * f + (k + 1) % 3];
+            const double* r = xyz + 3 * corners[3 * f + (k + 2) % 3];
+            double a[3] = {q[0] - p[0], q[1] - p[1], q[2] - p[2]}, b[3] = {r[0] - p[0], r[1] - p[1], r[2] - p[2]};
+            double cr[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+            double cn = std::sqrt(cr[0] * cr[0] + cr[1] * cr[1] + cr[2] * cr[2]);
+            ang[corners[3 * f + k]] += std::atan2(cn, a[0] * b[0] + a[1] * b[1] + a[2] * b[2]);
+            if (k == 0) area += cn / 2.0;
+        }
+    }
+    ctx->area = area;
+    std::vector<unsigned char> sad(nV);
+    for (int i = 0; i < nV; ++i) sad[i] = ang[i] >= 2.0 * M_PI - 1e-9;
+    for (int d = 0; d < 3; ++d) ctx->cellMin[d] = ctx->bbmin[d], ctx->cellMax[d] = ctx->bbmax[d];
+    ctx->gridRange = -1;
+    CU(regrow(ctx->d_vert, nV));
+    CU(regrow(ctx->d_corner, nF));
+    CU(regrow(ctx->d_adj, nF));
+    CU(regrow(ctx->d_saddle, nV));
+    CU(cudaMemcpy(ctx->d_vert, hv.data(), sizeof(double4) * nV, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ctx->d_corner, hc.data(), sizeof(int4) * nF, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ctx->d_adj, ha.data(), sizeof(int4) * nF, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ctx->d_saddle, sad.data(), nV, cudaMemcpyHostToDevice));
+    ctx->nV = nV;
+    ctx->nF = nF;
+    ctx->nbrValid = false;
+    // last-resort tier: the whole mesh fits (local ids are 16 bit)
+    int mf = std::min(nF, 65534), mv = std::min(nV, 65534);
+    auto p2 = [](int x) {
+        int p = 1;
+        while (p < x) p <<= 1;
+        return p;
+    };
+    ctx->capsT2 = GeoCaps{mf, mv, p2(std::min(4 * mf + 64, 1 << 20)), 256, p2(2 * mf + 128), p2(2 * mv + 256)};
+    return CSS_OK;
+}
+
+int css_mesh_info(css_ctx* ctx, double bbmin[3], double bbmax[3], double* area)
+{
+    if (!ctx || !ctx->nF) return fail(ctx, CSS_ESTATE, "mesh not set");
+    for (int d = 0; d < 3; ++d) {
+        if (bbmin) bbmin[d] = ctx->bbmin[d];
+        if (bbmax) bbmax[d] = ctx->bbmax[d];
+    }
+    if (area) *area = ctx->area;
+    return CSS_OK;
+}
+
+int css_set_submeshing(css_ctx* ctx, int enabled, double maxDist)
+{
+    if (!ctx) return CSS_EINVAL;
+    ctx->submeshing = enabled != 0;
+    ctx->maxDist = maxDist;
+    ctx->nbrValid = false;
+    return CSS_OK;
+}
+int css_set_cell_domain(css_ctx* ctx, const double mn[3], const double mx[3])
+{
+    if (!ctx || !mn || !mx) return CSS_EINVAL;
+    for (int d = 0; d < 3; ++d) ctx->cellMin[d] = mn[d], ctx->cellMax[d] = mx[d];
+    ctx->gridRange = -1;
+    return CSS_OK;
+}
+int css_set_options(css_ctx* ctx, int useCellList, int wantEndTangents)
+{
+    if (!ctx) return CSS_EINVAL;
+    ctx->useCellList = useCellList != 0;
+    ctx->wantEnd = wantEndTangents != 0;
+    ctx->nbrValid = false;
+    return CSS_OK;
+}
+
+static MeshDev meshDev(css_ctx* c) { return MeshDev{c->nV, c->nF, c->d_vert, c->d_corner, c->d_adj, c->d_saddle}; }
+
+// ------------------------------------------------------------------------------- per-call parity
+int css_euclidean(css_ctx* ctx, int n, const int32_t* face, const double* bary, double* xyz)
+{
+    if (!ctx || !ctx->nF) return fail(ctx, CSS_ESTATE, "mesh not set");
+    if (n <= 0) return CSS_OK;
+    BIND();
+    for (int i = 0; i < n; ++i)
+        if (face[i] < 0 || face[i] >= ctx->nF) return fail(ctx, CSS_EINVAL, "css_euclidean: face index %d out of range", face[i]);
+    int* df = nullptr;
+    double *db = nullptr, *dx = nullptr;
+    CU(cudaMalloc(&df, sizeof(int) * n));
+    CU(cudaMalloc(&db, sizeof(double) * 3 * n));
+    CU(cudaMalloc(&dx, sizeof(double) * 3 * n));
+    CU(cudaMemcpyAsync(df, face, sizeof(int) * n, cudaMemcpyHostToDevice, ctx->st));
+    CU(cudaMemcpyAsync(db, bary, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, ctx->st));
+    launchEuclidCell(ctx->st, meshDev(ctx), ctx->grid, n, df, db, dx, nullptr, nullptr);
+    ctx->hostKernels++;
+    CU(cudaMemcpyAsync(xyz, dx, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    cudaFree(df), cudaFree(db), cudaFree(dx);
+    return CSS_OK;
+}
+
+int css_transport(css_ctx* ctx, int n, int32_t* face, double* bary, double* disp, int nVec, double* vecs, int32_t* flags)
+{
+    if (!ctx || !ctx->nF) return fail(ctx, CSS_ESTATE, "mesh not set");
+    if (n <= 0) return CSS_OK;
+    BIND();
+    for (int i = 0; i < n; ++i)
+        if (face[i] < 0 || face[i] >= ctx->nF) return fail(ctx, CSS_EINVAL, "css_transport: face index %d out of range", face[i]);
+    int *df = nullptr, *dfl = nullptr;
+    double *db = nullptr, *dd = nullptr, *dv = nullptr;
+    CU(cudaMalloc(&df, sizeof(int) * n));
+    CU(cudaMalloc(&dfl, sizeof(int) * n));
+    CU(cudaMalloc(&db, sizeof(double) * 3 * n));
+    CU(cudaMalloc(&dd, sizeof(double) * 3 * n));
+    CU(cudaMalloc(&dv, sizeof(double) * 3 * (size_t)n * std::max(nVec, 1)));
+    CU(cudaMemcpyAsync(df, face, sizeof(int) * n, cudaMemcpyHostToDevice, ctx->st));
+    CU(cudaMemcpyAsync(db, bary, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, ctx->st));
+    CU(cudaMemcpyAsync(dd, disp, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, ctx->st));
+    if (nVec > 0) CU(cudaMemcpyAsync(dv, vecs, sizeof(double) * 3 * (size_t)n * nVec, cudaMemcpyHostToDevice, ctx->st));
+    launchTransportGeneric(ctx->st, meshDev(ctx), n, df, db, dd, nVec, dv, dfl);
+    ctx->hostKernels++;
+    CU(cudaMemcpyAsync(face, df, sizeof(int) * n, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaMemcpyAsync(bary, db, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaMemcpyAsync(disp, dd, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, ctx->st));
+    if (nVec > 0) CU(cudaMemcpyAsync(vecs, dv, sizeof(double) * 3 * (size_t)n * nVec, cudaMemcpyDeviceToHost, ctx->st));
+    if (flags) CU(cudaMemcpyAsync(flags, dfl, sizeof(int) * n, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    cudaFree(df), cudaFree(dfl), cudaFree(db), cudaFree(dd), cudaFree(dv);
+    return CSS_OK;
+}
+
+// ------------------------------------------------------------------------------------- geodesics
+static int ensureTierBuffers(css_ctx* ctx, int nSrc)
+{
+    if (nSrc > ctx->capRetry) {
+        for (int t = 0; t < 3; ++t) CU(regrow(ctx->d_retry[t], nSrc));
+        ctx->capRetry = nSrc;
+    }
+    return CSS_OK;
+}
+
+// runs the tiered geodesic kernel for a prepared GeoArgs (srcList/work fields are filled here)
+static int runGeodesicTiers(css_ctx* ctx, GeoArgs a, int nSrc)
+{
+    int rc = ensureTierBuffers(ctx, std::max(nSrc, 1));
+    if (rc) return rc;
+    CU(cudaMemsetAsync(ctx->d_work, 0, 16 * sizeof(int), ctx->st)); // [0..2] work counters, [4..6] retry counts
+    // tier 0: shared memory, several warps per block
+    {
+        a.caps = ctx->capsT0;
+        a.srcList = nullptr, a.srcCount = nullptr;
+        a.workCounter = ctx->d_work + 0;
+        a.retryList = ctx->d_retry[0], a.retryCount = ctx->d_work + 4;
+        a.gws = nullptr, a.lastTier = 0;
+        size_t ws = geoWorkspaceBytes(a.caps);
+        int wpb = 4;
+        int bps = std::max(1, std::min(3, (int)(geodesicMaxSmemPerBlock() / (ws * wpb))));
+        int blocks = std::min(ctx->numSMs * bps, std::max(1, (nSrc + wpb - 1) / wpb));
+        launchGeodesic(ctx->st, a, wpb, blocks);
+        ctx->hostKernels++;
+    }
+    // tier 1: shared memory, one warp per block, large capacities
+    {
+        a.caps = ctx->capsT1;
+        a.srcList = ctx->d_retry[0], a.srcCount = ctx->d_work + 4;
+        a.workCounter = ctx->d_work + 1;
+        a.retryList = ctx->d_retry[1], a.retryCount = ctx->d_work + 5;
+        a.gws = nullptr, a.lastTier = 0;
+        launchGeodesic(ctx->st, a, 1, std::min(ctx->numSMs, std::max(1, nSrc)));
+        ctx->hostKernels++;
+    }
+    // tier 2: global-memory workspace sized for the whole mesh
+    {
+        a.caps = ctx->capsT2;
+        if (a.xK >= 0) a.caps.kt = std::max(a.caps.kt, a.xK);
+        else if (!ctx->useCellList) a.caps.kt = std::max(a.caps.kt, a.nTotal);
+        size_t ws = geoWorkspaceBytes(a.caps);
+        int warps = ctx->t2Warps;
+        if (ws * warps > ctx->gwsBytes) {
+            CU(cudaStreamSynchronize(ctx->st));
+            if (ctx->d_gws) cudaFree(ctx->d_gws);
+            ctx->d_gws = nullptr;
+            CU(cudaMalloc(&ctx->d_gws, ws * warps));
+            ctx->gwsBytes = ws * warps;
+        }
+        a.srcList = ctx->d_retry[1], a.srcCount = ctx->d_work + 5;
+        a.workCounter = ctx->d_work + 2;
+        a.retryList = ctx->d_retry[2], a.retryCount = ctx->d_work + 6;
+        a.gws = ctx->d_gws, a.lastTier = 1;
+        launchGeodesic(ctx->st, a, 1, warps);
+        ctx->hostKernels++;
+    }
+    return CSS_OK;
+}
+
+int css_distance(css_ctx* ctx, int srcFace, const double srcBary[3], int K, const int32_t* tgtFace, const double* tgtBary,
+                 double threshold, double* dist, double* startTan, double* endTan)
+{
+    if (!ctx || !ctx->nF) return fail(ctx, CSS_ESTATE, "mesh not set");
+    if (K < 0 || srcFace < 0 || srcFace >= ctx->nF) return fail(ctx, CSS_EINVAL, "css_distance: bad source");
+    if (K == 0) return CSS_OK;
+    BIND();
+    for (int i = 0; i < K; ++i)
+        if (tgtFace[i] < 0 || tgtFace[i] >= ctx->nF) return fail(ctx, CSS_EINVAL, "css_distance: target face out of range");
+    int* df = nullptr;
+    double *db = nullptr, *dd = nullptr, *dts = nullptr, *dte = nullptr;
+    CU(cudaMalloc(&df, sizeof(int) * K));
+    CU(cudaMalloc(&db, sizeof(double) * 3 * K));
+    CU(cudaMalloc(&dd, sizeof(double) * K));
+    CU(cudaMalloc(&dts, sizeof(double) * 3 * K));
+    CU(cudaMalloc(&dte, sizeof(double) * 3 * K));
+    CU(cudaMemcpyAsync(df, tgtFace, sizeof(int) * K, cudaMemcpyHostToDevice, ctx->st));
+    CU(cudaMemcpyAsync(db, tgtBary, sizeof(double) * 3 * K, cudaMemcpyHostToDevice, ctx->st));
+    GeoArgs a{};
+    a.m = meshDev(ctx);
+    a.nTotal = 0, a.nLocal = 1, a.minIdx = 0;
+    a.submeshing = ctx->submeshing, a.maxDist = ctx->maxDist;
+    a.xK = K, a.xSrcFace = srcFace;
+    a.xSrcBary[0] = srcBary[0], a.xSrcBary[1] = srcBary[1], a.xSrcBary[2] = srcBary[2];
+    a.xThreshold = threshold;
+    a.xTgtFace = df, a.xTgtBary = db;
+    a.kmax = K;
+    a.nbrDist = dd, a.nbrTs = dts, a.nbrTe = dte;
+    a.counters = ctx->d_counters;
+    unsigned long long before = 0, after = 0;
+    CU(cudaMemcpyAsync(&before, ctx->d_counters + C_OVERFLOW, sizeof before, cudaMemcpyDeviceToHost, ctx->st));
+    int rc = runGeodesicTiers(ctx, a, 1);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(&after, ctx->d_counters + C_OVERFLOW, sizeof after, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaMemcpyAsync(dist, dd, sizeof(double) * K, cudaMemcpyDeviceToHost, ctx->st));
+    if (startTan) CU(cudaMemcpyAsync(startTan, dts, sizeof(double) * 3 * K, cudaMemcpyDeviceToHost, ctx->st));
+    if (endTan) CU(cudaMemcpyAsync(endTan, dte, sizeof(double) * 3 * K, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    cudaFree(df), cudaFree(db), cudaFree(dd), cudaFree(dts), cudaFree(dte);
+    if (after != before) return fail(ctx, CSS_ECAPACITY, "css_distance: patch/window capacity exceeded on every tier");
+    return CSS_OK;
+}
+
+// ------------------------------------------------------------------------------------- model state
+static int ensureParticles(css_ctx* ctx, int nLocal, int nTotal)
+{
+    if (nTotal > ctx->capTotal) {
+        CU(regrow(ctx->d_face, nTotal));
+        CU(regrow(ctx->d_bary, 3 * (size_t)nTotal));
+        CU(regrow(ctx->d_eucl, 3 * (size_t)nTotal));
+        CU(regrow(ctx->d_cellOf, nTotal));
+        CU(regrow(ctx->d_tmpItems, nTotal));
+        CU(regrow(ctx->d_items, nTotal));
+        ctx->capTotal = nTotal;
+    }
+    if (nLocal > ctx->capLocal) {
+        CU(regrow(ctx->d_vel, 3 * (size_t)nLocal));
+        CU(regrow(ctx->d_frc, 3 * (size_t)nLocal));
+        CU(regrow(ctx->d_disp, 3 * (size_t)nLocal));
+        CU(regrow(ctx->d_walkFlags, nLocal));
+        ctx->capLocal = nLocal;
+        ctx->capNbr = 0;
+    }
+    return CSS_OK;
+}
+static int ensureNeighbors(css_ctx* ctx)
+{
+    size_t need = (size_t)std::max(ctx->nLocal, 1) * ctx->kmax;
+    if (need > (size_t)ctx->capNbr || (ctx->wantEnd && !ctx->nbrHasEnd)) {
+        CU(regrow(ctx->d_nbrCount, std::max(ctx->nLocal, 1)));
+        CU(regrow(ctx->d_nbrIdx, need));
+        CU(regrow(ctx->d_nbrDist, need));
+        CU(regrow(ctx->d_nbrTs, 3 * need));
+        if (ctx->wantEnd) CU(regrow(ctx->d_nbrTe, 3 * need));
+        ctx->nbrHasEnd = ctx->wantEnd;
+        ctx->capNbr = (int)need;
+    }
+    return CSS_OK;
+}
+
+int css_set_state(css_ctx* ctx, int nLocal, int nTotal, int minIdx, const int32_t* face, const double* bary, const double* vel,
+                  const double* frc)
+{
+    if (!ctx || !ctx->nF) return fail(ctx, CSS_ESTATE, "mesh not set");
+    if (nLocal < 0 || nTotal < nLocal || minIdx < 0 || minIdx + nLocal > nTotal || !face || !bary)
+        return fail(ctx, CSS_EINVAL, "css_set_state: bad sharding arguments");
+    BIND();
+    for (int i = 0; i < nTotal; ++i)
+        if (face[i] < 0 || face[i] >= ctx->nF) return fail(ctx, CSS_EINVAL, "css_set_state: face index %d out of range", face[i]);
+    int rc = ensureParticles(ctx, nLocal, nTotal);
+    if (rc) return rc;
+    ctx->nLocal = nLocal, ctx->nTotal = nTotal, ctx->minIdx = minIdx;
+    CU(cudaMemcpyAsync(ctx->d_face, face, sizeof(int) * nTotal, cudaMemcpyHostToDevice, ctx->st));
+    CU(cudaMemcpyAsync(ctx->d_bary, bary, sizeof(double) * 3 * nTotal, cudaMemcpyHostToDevice, ctx->st));
+    if (vel) CU(cudaMemcpyAsync(ctx->d_vel, vel, sizeof(double) * 3 * nLocal, cudaMemcpyHostToDevice, ctx->st));
+    else CU(cudaMemsetAsync(ctx->d_vel, 0, sizeof(double) * 3 * std::max(nLocal, 1), ctx->st));
+    if (frc) CU(cudaMemcpyAsync(ctx->d_frc, frc, sizeof(double) * 3 * nLocal, cudaMemcpyHostToDevice, ctx->st));
+    else CU(cudaMemsetAsync(ctx->d_frc, 0, sizeof(double) * 3 * std::max(nLocal, 1), ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    ctx->nbrValid = false;
+    return CSS_OK;
+}
+int css_get_state(css_ctx* ctx, int32_t* face, double* bary, double* vel, double* frc)
+{
+    if (!ctx || !ctx->nTotal) return fail(ctx, CSS_ESTATE, "state not set");
+    BIND();
+    if (face) CU(cudaMemcpyAsync(face, ctx->d_face, sizeof(int) * ctx->nTotal, cudaMemcpyDeviceToHost, ctx->st));
+    if (bary) CU(cudaMemcpyAsync(bary, ctx->d_bary, sizeof(double) * 3 * ctx->nTotal, cudaMemcpyDeviceToHost, ctx->st));
+    if (vel) CU(cudaMemcpyAsync(vel, ctx->d_vel, sizeof(double) * 3 * ctx->nLocal, cudaMemcpyDeviceToHost, ctx->st));
+    if (frc) CU(cudaMemcpyAsync(frc, ctx->d_frc, sizeof(double) * 3 * ctx->nLocal, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    return CSS_OK;
+}
+int css_set_velocities(css_ctx* ctx, const double* vel)
+{
+    if (!ctx || !ctx->nTotal || !vel) return fail(ctx, CSS_ESTATE, "state not set");
+    BIND();
+    CU(cudaMemcpyAsync(ctx->d_vel, vel, sizeof(double) * 3 * ctx->nLocal, cudaMemcpyHostToDevice, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    return CSS_OK;
+}
+int css_set_forces(css_ctx* ctx, const double* frc)
+{
+    if (!ctx || !ctx->nTotal || !frc) return fail(ctx, CSS_ESTATE, "state not set");
+    BIND();
+    CU(cudaMemcpyAsync(ctx->d_frc, frc, sizeof(double) * 3 * ctx->nLocal, cudaMemcpyHostToDevice, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    return CSS_OK;
+}
+
+// hyperRectangularCellList::setGridSize (hyperRectangularCellList.cpp:9-46)
+static int setupGrid(css_ctx* ctx, double range)
+{
+    if (range != ctx->gridRange) {
+        long total = 1;
+        for (int d = 0; d < 3; ++d) {
+            double ext = ctx->cellMax[d] - ctx->cellMin[d];
+            int n = std::max(1, (int)std::floor(ext / range));
+            ctx->grid.n[d] = n;
+            ctx->grid.cs[d] = ext / n;
+            ctx->grid.mn[d] = ctx->cellMin[d];
+            total *= n;
+        }
+        if (total > (1L << 28)) return fail(ctx, CSS_ECAPACITY, "cell grid of %ld cells is too large", total);
+        ctx->nCells = (int)total;
+        ctx->gridRange = range;
+    }
+    ctx->grid.range2 = range * range;
+    if (ctx->nCells > ctx->capCells) {
+        CU(regrow(ctx->d_cellCount, (size_t)ctx->nCells + 1));
+        CU(regrow(ctx->d_cellStart, (size_t)ctx->nCells + 1));
+        CU(regrow(ctx->d_fill, (size_t)ctx->nCells + 1));
+        CU(regrow(ctx->d_blockSums, (size_t)scanBlocks(ctx->nCells) + 1));
+        ctx->capCells = ctx->nCells;
+    }
+    return CSS_OK;
+}
+
+// findNeighbors (+ optional fused force / kick). forceMode 0: lists only.
+static int findNeighborsImpl(css_ctx* ctx, double range, int forceMode, ForceParams fp, int zero, double kick)
+{
+    if (!ctx->nTotal) return fail(ctx, CSS_ESTATE, "state not set");
+    int rc;
+    MeshDev m = meshDev(ctx);
+    if (ctx->timing) cudaEventRecord(ctx->ev[0], ctx->st);
+    if (ctx->useCellList) {
+        if ((rc = setupGrid(ctx, range))) return rc;
+        CU(cudaMemsetAsync(ctx->d_cellCount, 0, sizeof(int) * ((size_t)ctx->nCells + 1), ctx->st));
+        launchEuclidCell(ctx->st, m, ctx->grid, ctx->nTotal, ctx->d_face, ctx->d_bary, ctx->d_eucl, ctx->d_cellOf, ctx->d_cellCount);
+        launchCellBuild(ctx->st, ctx->nTotal, ctx->nCells, ctx->d_cellOf, ctx->d_cellCount, ctx->d_cellStart, ctx->d_blockSums, ctx->d_fill,
+                        ctx->d_tmpItems, ctx->d_items);
+        ctx->hostKernels += 6;
+    } else {
+        launchEuclidCell(ctx->st, m, ctx->grid, ctx->nTotal, ctx->d_face, ctx->d_bary, ctx->d_eucl, nullptr, nullptr);
+        ctx->hostKernels += 1;
+        if (ctx->nTotal - 1 > ctx->kmax) {
+            ctx->kmax = ctx->nTotal - 1;
+            ctx->capNbr = 0;
+        }
+    }
+    if (ctx->timing) cudaEventRecord(ctx->ev[1], ctx->st);
+    if ((rc = ensureNeighbors(ctx))) return rc;
+    GeoArgs a{};
+    a.m = m;
+    a.grid = ctx->grid;
+    a.nTotal = ctx->nTotal, a.nLocal = ctx->nLocal, a.minIdx = ctx->minIdx;
+    a.face = ctx->d_face, a.bary = ctx->d_bary, a.eucl = ctx->d_eucl;
+    a.cellStart = ctx->useCellList ? ctx->d_cellStart : nullptr;
+    a.cellItems = ctx->d_items;
+    a.submeshing = ctx->submeshing, a.maxDist = ctx->maxDist;
+    a.xK = -1;
+    a.kmax = ctx->kmax;
+    a.nbrCount = ctx->d_nbrCount, a.nbrIdx = ctx->d_nbrIdx, a.nbrDist = ctx->d_nbrDist, a.nbrTs = ctx->d_nbrTs;
+    a.nbrTe = ctx->wantEnd ? ctx->d_nbrTe : nullptr;
+    a.forceMode = forceMode, a.fp = fp, a.zero = zero, a.frc = ctx->d_frc, a.kick = kick, a.vel = ctx->d_vel;
+    a.counters = ctx->d_counters;
+    if ((rc = runGeodesicTiers(ctx, a, ctx->nLocal))) return rc;
+    if (ctx->timing) cudaEventRecord(ctx->ev[2], ctx->st);
+    ctx->nbrValid = true;
+    return CSS_OK;
+}
+
+// checks the capacity counters after a synchronisation point; grows kmax when the stride was too small
+static int checkCapacity(css_ctx* ctx, bool* rerun)
+{
+    unsigned long long h[NUM_COUNTERS];
+    CU(cudaMemcpyAsync(h, ctx->d_counters, sizeof h, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    if (rerun) *rerun = false;
+    if (h[C_KMAX_OVERFLOW]) {
+        CU(cudaMemsetAsync(ctx->d_counters + C_KMAX_OVERFLOW, 0, sizeof(unsigned long long), ctx->st));
+        ctx->kmax *= 2;
+        ctx->capNbr = 0;
+        if (rerun) *rerun = true;
+        else return fail(ctx, CSS_ECAPACITY, "neighbour stride exceeded during a fused step; stride doubled, rerun");
+    }
+    if (h[C_OVERFLOW]) {
+        CU(cudaMemsetAsync(ctx->d_counters + C_OVERFLOW, 0, sizeof(unsigned long long), ctx->st));
+        return fail(ctx, CSS_ECAPACITY, "%llu sources exceeded the patch/window capacity of every tier", h[C_OVERFLOW]);
+    }
+    return CSS_OK;
+}
+
+static ForceParams mkForce(int kind, const double* p, double* range)
+{
+    ForceParams f;
+    f.kind = kind;
+    f.a = p[0];
+    f.sigma = p[1];
+    *range = p[2];
+    return f;
+}
+
+int css_find_neighbors(css_ctx* ctx, double range, int64_t* totalNeighbors)
+{
+    if (!ctx) return CSS_EINVAL;
+    BIND();
+    for (int attempt = 0; attempt < 8; ++attempt) {
+        int rc = findNeighborsImpl(ctx, range, 0, ForceParams{0, 0, 0}, 0, 0.0);
+        if (rc) return rc;
+        bool rerun = false;
+        if ((rc = checkCapacity(ctx, &rerun))) return rc;
+        if (!rerun) break;
+    }
+    if (ctx->timing) {
+        cudaEventElapsedTime(&ctx->msCell, ctx->ev[0], ctx->ev[1]);
+        cudaEventElapsedTime(&ctx->msGeo, ctx->ev[1], ctx->ev[2]);
+    }
+    if (totalNeighbors) {
+        std::vector<int> cnt(std::max(ctx->nLocal, 1));
+        CU(cudaMemcpy(cnt.data(), ctx->d_nbrCount, sizeof(int) * ctx->nLocal, cudaMemcpyDeviceToHost));
+        int64_t t = 0;
+        for (int i = 0; i < ctx->nLocal; ++i) t += cnt[i];
+        *totalNeighbors = t;
+    }
+    return CSS_OK;
+}
+
+int css_get_neighbors(css_ctx* ctx, int32_t* offsets, int32_t* idx, double* dist, double* startTan, double* endTan)
+{
+    if (!ctx || !ctx->nbrValid) return fail(ctx, CSS_ESTATE, "css_get_neighbors: no neighbour lists (call css_find_neighbors)");
+    if (endTan && !ctx->nbrHasEnd) return fail(ctx, CSS_ESTATE, "end tangents were not requested (css_set_options)");
+    BIND();
+    int n = ctx->nLocal, km = ctx->kmax;
+    std::vector<int> cnt(std::max(n, 1)), hidx;
+    std::vector<double> hd, ht;
+    CU(cudaMemcpy(cnt.data(), ctx->d_nbrCount, sizeof(int) * n, cudaMemcpyDeviceToHost));
+    size_t tot = (size_t)n * km;
+    if (idx) {
+        hidx.resize(tot);
+        CU(cudaMemcpy(hidx.data(), ctx->d_nbrIdx, sizeof(int) * tot, cudaMemcpyDeviceToHost));
+    }
+    if (dist) {
+        hd.resize(tot);
+        CU(cudaMemcpy(hd.data(), ctx->d_nbrDist, sizeof(double) * tot, cudaMemcpyDeviceToHost));
+    }
+    size_t o = 0;
+    for (int i = 0; i < n; ++i) {
+        if (offsets) offsets[i] = (int)o;
+        for (int j = 0; j < cnt[i]; ++j, ++o) {
+            if (idx) idx[o] = hidx[(size_t)i * km + j];
+            if (dist) dist[o] = hd[(size_t)i * km + j];
+        }
+    }
+    if (offsets) offsets[n] = (int)o;
+    for (int pass = 0; pass < 2; ++pass) {
+        double* out = pass ? endTan : startTan;
+        if (!out) continue;
+        ht.resize(3 * tot);
+        CU(cudaMemcpy(ht.data(), pass ? ctx->d_nbrTe : ctx->d_nbrTs, sizeof(double) * 3 * tot, cudaMemcpyDeviceToHost));
+        o = 0;
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < cnt[i]; ++j, ++o)
+                for (int d = 0; d < 3; ++d) out[3 * o + d] = ht[3 * ((size_t)i * km + j) + d];
+    }
+    return CSS_OK;
+}
+
+int css_compute_forces(css_ctx* ctx, int kind, const double* params, int zero)
+{
+    if (!ctx || !params) return CSS_EINVAL;
+    BIND();
+    double range;
+    ForceParams fp = mkForce(kind, params, &range);
+    std::vector<double> saved;
+    if (!zero) { // a rerun must restart from the caller's forces
+        saved.resize(3 * (size_t)std::max(ctx->nLocal, 1));
+        CU(cudaMemcpy(saved.data(), ctx->d_frc, sizeof(double) * 3 * ctx->nLocal, cudaMemcpyDeviceToHost));
+    }
+    for (int attempt = 0; attempt < 8; ++attempt) {
+        int rc = findNeighborsImpl(ctx, range, 1, fp, zero, 0.0);
+        if (rc) return rc;
+        bool rerun = false;
+        if ((rc = checkCapacity(ctx, &rerun))) return rc;
+        if (!rerun) break;
+        if (!zero) CU(cudaMemcpy(ctx->d_frc, saved.data(), sizeof(double) * 3 * ctx->nLocal, cudaMemcpyHostToDevice));
+    }
+    if (ctx->timing) {
+        cudaEventElapsedTime(&ctx->msCell, ctx->ev[0], ctx->ev[1]);
+        cudaEventElapsedTime(&ctx->msGeo, ctx->ev[1], ctx->ev[2]);
+    }
+    return CSS_OK;
+}
+
+int css_compute_energy(css_ctx* ctx, int kind, const double* params, double* energy)
+{
+    if (!ctx || !params || !energy) return CSS_EINVAL;
+    BIND();
+    double range;
+    ForceParams fp = mkForce(kind, params, &range);
+    int rc = css_find_neighbors(ctx, range, nullptr);
+    if (rc) return rc;
+    launchEnergy(ctx->st, ctx->nLocal, ctx->kmax, ctx->d_nbrCount, ctx->d_nbrDist, fp, ctx->d_partial, ctx->d_red);
+    ctx->hostKernels += 2;
+    CU(cudaMemcpyAsync(energy, ctx->d_red, sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    return css_reduce(ctx, CSS_SUM, 1, energy);
+}
+
+static int moveImpl(css_ctx* ctx, int transportForce, int transportVelocity, int mode, double dt)
+{
+    if (ctx->timing) cudaEventRecord(ctx->ev[3], ctx->st);
+    launchWalk(ctx->st, meshDev(ctx), ctx->nLocal, ctx->minIdx, ctx->d_face, ctx->d_bary, ctx->d_disp, ctx->d_vel, ctx->d_frc, transportForce,
+               transportVelocity, mode, dt, ctx->d_walkFlags, ctx->d_counters);
+    ctx->hostKernels++;
+    if (ctx->timing) cudaEventRecord(ctx->ev[4], ctx->st);
+    ctx->nbrValid = false;
+    if (ctx->nranks > 1) return css_gather_positions(ctx);
+    return CSS_OK;
+}
+
+int css_move(css_ctx* ctx, const double* disp, int transportForce, int transportVelocity)
+{
+    if (!ctx || !ctx->nTotal) return fail(ctx, CSS_ESTATE, "state not set");
+    BIND();
+    if (disp) CU(cudaMemcpyAsync(ctx->d_disp, disp, sizeof(double) * 3 * ctx->nLocal, cudaMemcpyHostToDevice, ctx->st));
+    int rc = moveImpl(ctx, transportForce, transportVelocity, 0, 0.0);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(ctx->st));
+    if (ctx->timing) cudaEventElapsedTime(&ctx->msWalk, ctx->ev[3], ctx->ev[4]);
+    return CSS_OK;
+}
+int css_get_walk_flags(css_ctx* ctx, int32_t* flags)
+{
+    if (!ctx || !ctx->nTotal || !flags) return fail(ctx, CSS_ESTATE, "state not set");
+    BIND();
+    CU(cudaMemcpy(flags, ctx->d_walkFlags, sizeof(int) * ctx->nLocal, cudaMemcpyDeviceToHost));
+    return CSS_OK;
+}
+
+// ---------------------------------------------------------------------------------------- updaters
+int css_step_nve(css_ctx* ctx, int kind, const double* params, double dt, int nsteps)
+{
+    if (!ctx || !params) return CSS_EINVAL;
+    if (!ctx->nTotal) return fail(ctx, CSS_ESTATE, "state not set");
+    BIND();
+    double range;
+    ForceParams fp = mkForce(kind, params, &range);
+    for (int s = 0; s < nsteps; ++s) {
+        // first half step fused into the walker; second half kick fused into the geodesic/force kernel
+        int rc = moveImpl(ctx, 0, 1, 1, dt);
+        if (rc) return rc;
+        if ((rc = findNeighborsImpl(ctx, range, 1, fp, 1, 0.5 * dt))) return rc;
+    }
+    int rc = checkCapacity(ctx, nullptr);
+    if (ctx->timing && nsteps > 0) {
+        cudaEventElapsedTime(&ctx->msCell, ctx->ev[0], ctx->ev[1]);
+        cudaEventElapsedTime(&ctx->msGeo, ctx->ev[1], ctx->ev[2]);
+        cudaEventElapsedTime(&ctx->msWalk, ctx->ev[3], ctx->ev[4]);
+    }
+    return rc;
+}
+
+int css_step_gd(css_ctx* ctx, int kind, const double* params, double dt, int nsteps)
+{
+    if (!ctx || !params) return CSS_EINVAL;
+    if (!ctx->nTotal) return fail(ctx, CSS_ESTATE, "state not set");
+    BIND();
+    double range;
+    ForceParams fp = mkForce(kind, params, &range);
+    for (int s = 0; s < nsteps; ++s) {
+        int rc = findNeighborsImpl(ctx, range, 1, fp, 1, 0.0);
+        if (rc) return rc;
+        launchAxpy(ctx->st, 1, ctx->nLocal, dt, 0, ctx->d_vel, ctx->d_frc, ctx->d_disp);
+        ctx->hostKernels++;
+        if ((rc = moveImpl(ctx, 0, 0, 0, 0.0))) return rc;
+    }
+    return checkCapacity(ctx, nullptr);
+}
+
+static int reduceDevice(css_ctx* ctx, double out[5])
+{
+    launchReduce(ctx->st, ctx->nLocal, ctx->d_vel, ctx->d_frc, ctx->d_partial, ctx->d_red);
+    ctx->hostKernels += 2;
+    CU(cudaMemcpyAsync(out, ctx->d_red, 5 * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    if (ctx->nranks > 1) {
+        double s[4] = {out[0], out[1], out[2], out[4]};
+        int rc = css_reduce(ctx, CSS_SUM, 4, s);
+        if (rc) return rc;
+        out[0] = s[0], out[1] = s[1], out[2] = s[2], out[4] = s[3];
+        if ((rc = css_reduce(ctx, CSS_MAX, 1, out + 3))) return rc;
+    }
+    return CSS_OK;
+}
+
+int css_max_force(css_ctx* ctx, double* maxForce)
+{
+    if (!ctx || !ctx->nTotal || !maxForce) return fail(ctx, CSS_ESTATE, "state not set");
+    BIND();
+    double r[5];
+    int rc = reduceDevice(ctx, r);
+    if (rc) return rc;
+    *maxForce = std::sqrt(r[3]);
+    return CSS_OK;
+}
+int css_force_norm(css_ctx* ctx, double* forceNorm)
+{
+    if (!ctx || !ctx->nTotal || !forceNorm) return fail(ctx, CSS_ESTATE, "state not set");
+    BIND();
+    double r[5];
+    int rc = reduceDevice(ctx, r);
+    if (rc) return rc;
+    *forceNorm = std::sqrt(r[0]);
+    return CSS_OK;
+}
+
+// noseHooverNVT (src/updaters/noseHooverNVT.cpp); the chain is a handful of scalars and stays on the host
+int css_nvt_init(css_ctx* ctx, double dt, double T, double tau, int M)
+{
+    if (!ctx || M < 1) return CSS_EINVAL;
+    if (!ctx->nTotal) return fail(ctx, CSS_ESTATE, "state not set");
+    auto& h = ctx->nh;
+    h.dt = dt, h.dt2 = 0.5 * dt, h.dt4 = 0.25 * dt, h.dt8 = 0.125 * dt, h.T = T, h.tau = tau, h.M = M;
+    h.bx.assign(M + 1, 0), h.by.assign(M + 1, 0), h.bz.assign(M + 1, 0), h.bw.assign(M + 1, 0);
+    int Ndof = ctx->nTotal; // global particle count: the chain is replicated on every rank
+    h.bw[0] = 2.0 * (Ndof - 1) * T * tau * tau;
+    for (int i = 1; i <= M; ++i) h.bw[i] = T * tau * tau;
+    h.KE = h.bw[0];
+    h.scale = 1.0;
+    return CSS_OK;
+}
+static void propagateChain(css_ctx* ctx) // noseHooverNVT.cpp:65-110
+{
+    auto& h = ctx->nh;
+    int M = h.M;
+    double ef = 0;
+    for (int ii = M - 1; ii > 0; --ii) {
+        h.bz[ii] = (h.bw[ii - 1] * h.by[ii - 1] * h.by[ii - 1] - h.T) / h.bw[ii];
+        ef = std::exp(-h.dt8 * h.by[ii + 1]);
+        h.by[ii] *= ef;
+        h.by[ii] += h.bz[ii] * h.dt4;
+        h.by[ii] *= ef;
+    }
+    h.bz[0] = (2.0 * h.KE / h.bw[0] - 1.0);
+    ef = std::exp(-h.dt8 * h.by[1]);
+    h.by[0] *= ef;
+    h.by[0] += h.bz[0] * h.dt4;
+    h.by[0] *= ef;
+    for (int ii = 0; ii < M; ++ii) h.bx[ii] += h.dt2 * h.by[ii];
+    h.scale = std::exp(-h.dt2 * h.by[0]);
+    h.KE = h.scale * h.scale * h.KE;
+    h.bz[0] = (2.0 * h.KE / h.bw[0] - 1.0);
+    ef = std::exp(-h.dt8 * h.by[1]);
+    h.by[0] *= ef;
+    h.by[0] += h.bz[0] * h.dt4;
+    h.by[0] *= ef;
+    for (int ii = 1; ii < M; ++ii) {
+        h.bz[ii] = (h.bw[ii - 1] * h.by[ii - 1] * h.by[ii - 1] - h.T) / h.bw[ii];
+        ef = std::exp(-h.dt8 * h.by[ii + 1]);
+        h.by[ii] *= ef;
+        h.by[ii] += h.bz[ii] * h.dt4;
+        h.by[ii] *= ef;
+    }
+}
+int css_step_nvt(css_ctx* ctx, int kind, const double* params, int nsteps)
+{
+    if (!ctx || !params) return CSS_EINVAL;
+    if (!ctx->nTotal || !ctx->nh.M) return fail(ctx, CSS_ESTATE, "css_nvt_init not called");
+    BIND();
+    double range;
+    ForceParams fp = mkForce(kind, params, &range);
+    auto& h = ctx->nh;
+    for (int s = 0; s < nsteps; ++s) { // noseHooverNVT::performUpdate :42-59 and propagatePositionsVelocities :116-139
+        propagateChain(ctx);
+        launchAxpy(ctx->st, 2, ctx->nLocal, h.scale, 0, ctx->d_vel, ctx->d_frc, ctx->d_disp);
+        launchAxpy(ctx->st, 3, ctx->nLocal, h.dt2, 0, ctx->d_vel, ctx->d_frc, ctx->d_disp);
+        ctx->hostKernels += 2;
+        int rc = moveImpl(ctx, 0, 1, 0, 0.0);
+        if (rc) return rc;
+        if ((rc = findNeighborsImpl(ctx, range, 1, fp, 1, h.dt))) return rc; // v += (dt/m) f fused as the kick
+        launchAxpy(ctx->st, 3, ctx->nLocal, h.dt2, 0, ctx->d_vel, ctx->d_frc, ctx->d_disp);
+        ctx->hostKernels++;
+        double r[5];
+        if ((rc = reduceDevice(ctx, r))) return rc;
+        h.KE = r[4];
+        if ((rc = moveImpl(ctx, 0, 1, 0, 0.0))) return rc;
+        propagateChain(ctx);
+        launchAxpy(ctx->st, 2, ctx->nLocal, h.scale, 0, ctx->d_vel, ctx->d_frc, ctx->d_disp);
+        ctx->hostKernels++;
+    }
+    return checkCapacity(ctx, nullptr);
+}
+int css_nvt_state(css_ctx* ctx, double* bath, double* ke, double* scale)
+{
+    if (!ctx || !ctx->nh.M) return fail(ctx, CSS_ESTATE, "css_nvt_init not called");
+    auto& h = ctx->nh;
+    for (int i = 0; i <= h.M && bath; ++i) bath[4 * i] = h.bx[i], bath[4 * i + 1] = h.by[i], bath[4 * i + 2] = h.bz[i], bath[4 * i + 3] = h.bw[i];
+    if (ke) *ke = h.KE;
+    if (scale) *scale = h.scale;
+    return CSS_OK;
+}
+
+// fireMinimization (src/updaters/fireMinimization.{h,cpp})
+int css_fire_init(css_ctx* ctx, const double* p, double dt0, double alpha0)
+{
+    if (!ctx) return CSS_EINVAL;
+    auto& f = ctx->fire;
+    f = css_ctx::FireState();
+    f.dt = dt0, f.alpha = alpha0;
+    if (p) { // setFIREParameters ignores its deltaT argument (fireMinimization.cpp:74-90)
+        f.maximumIterations = (int)p[0];
+        f.alphaStart = p[2], f.deltaTMax = p[3], f.deltaTMin = p[4], f.deltaTInc = p[5], f.deltaTDec = p[6], f.alphaDec = p[7];
+        f.nMin = (int)p[8], f.forceCutoff = p[9], f.alphaMin = p[10];
+        f.alpha = f.alphaStart;
+    }
+    return CSS_OK;
+}
+int css_fire_minimize(css_ctx* ctx, int kind, const double* params, double* out)
+{
+    if (!ctx || !params) return CSS_EINVAL;
+    if (!ctx->nTotal) return fail(ctx, CSS_ESTATE, "state not set");
+    BIND();
+    double range;
+    ForceParams fp = mkForce(kind, params, &range);
+    auto& f = ctx->fire;
+    int rc = findNeighborsImpl(ctx, range, 1, fp, 1, 0.0);
+    if (rc) return rc;
+    double r[5];
+    if ((rc = reduceDevice(ctx, r))) return rc;
+    f.forceMax = std::sqrt(r[3]);
+    f.iterations = 0;
+    while (f.iterations < f.maximumIterations && f.forceMax > f.forceCutoff) { // minimizeByFire :3-21
+        f.iterations += 1;
+        if ((rc = moveImpl(ctx, 1, 1, 1, f.dt))) return rc;                       // first half + move, transporting [force, velocity]
+        if ((rc = findNeighborsImpl(ctx, range, 1, fp, 1, 0.5 * f.dt))) return rc; // forces + second half kick
+        if ((rc = reduceDevice(ctx, r))) return rc;                                // fireStep :36-72
+        double forceNorm = r[0], velocityNorm = r[1], power = r[2];
+        double scaling = 0.0;
+        if (forceNorm > 0) scaling = std::sqrt(velocityNorm / forceNorm);
+        launchAxpy(ctx->st, 4, ctx->nLocal, scaling, f.alpha, ctx->d_vel, ctx->d_frc, ctx->d_disp);
+        ctx->hostKernels++;
+        if (power > 0) {
+            if (f.nSinceNegativePower > f.nMin) {
+                f.dt = std::min(f.dt * f.deltaTInc, f.deltaTMax);
+                f.alpha = f.alpha * f.alphaDec;
+                f.alpha = std::max(f.alpha, f.alphaMin);
+            }
+            f.nSinceNegativePower += 1;
+        } else {
+            f.nSinceNegativePower = 0;
+            f.dt = f.dt * f.deltaTDec;
+            f.dt = std::max(f.dt, f.deltaTMin);
+            f.alpha = f.alphaStart;
+            launchAxpy(ctx->st, 5, ctx->nLocal, 0, 0, ctx->d_vel, ctx->d_frc, ctx->d_disp);
+            ctx->hostKernels++;
+        }
+        f.forceMax = std::sqrt(r[3]);
+    }
+    if (out) out[0] = f.iterations, out[1] = f.forceMax, out[2] = f.dt, out[3] = f.alpha;
+    return checkCapacity(ctx, nullptr);
+}
+
+// --------------------------------------------------------------------------------------- multi-GPU
+int css_comm_unique_id(void* id128)
+{
+    if (!id128) return CSS_EINVAL;
+    ncclUniqueId id;
+    if (ncclGetUniqueId(&id) != ncclSuccess) return CSS_ENCCL;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    std::memcpy(id128, &id, 128);
+    return CSS_OK;
+}
+int css_comm_init(css_ctx* ctx, int rank, int nranks, const void* id128)
+{
+    if (!ctx || nranks < 1 || rank < 0 || rank >= nranks) return CSS_EINVAL;
+    BIND();
+    ctx->rank = rank, ctx->nranks = nranks;
+    if (nranks == 1) return CSS_OK;
+    if (!id128) return CSS_EINVAL;
+    ncclUniqueId id;
+    std::memcpy(&id, id128, 128);
+    NC(ncclCommInitRank(&ctx->comm, nranks, id, rank));
+    CU(regrow(ctx->d_redBuf, 64 * (size_t)nranks));
+    return CSS_OK;
+}
+// mpiSimulation::synchronizeAndTransferBuffers: every rank contributes a block padded to per = ceil(N/R)
+int css_gather_positions(css_ctx* ctx)
+{
+    if (!ctx || !ctx->nTotal) return fail(ctx, CSS_ESTATE, "state not set");
+    if (ctx->nranks == 1) return CSS_OK;
+    if (!ctx->comm) return fail(ctx, CSS_ENCCL, "communicator not initialised");
+    BIND();
+    int per = (ctx->nTotal + ctx->nranks - 1) / ctx->nranks;
+    if (ctx->minIdx != ctx->rank * per) return fail(ctx, CSS_EINVAL, "sharding does not follow mpiModel::determineIndexBounds");
+    if (per > ctx->capComm) {
+        CU(regrow(ctx->d_recvI, (size_t)per * ctx->nranks));
+        CU(regrow(ctx->d_recvD, 3 * (size_t)per * ctx->nranks));
+        ctx->capComm = per;
+    }
+    // the replicated arrays are already laid out rank-block by rank-block; only the last block is short,
+    // so gather into padded scratch and copy back the first nTotal entries
+    NC(ncclGroupStart());
+    NC(ncclAllGather(ctx->d_face + ctx->minIdx, ctx->d_recvI, per, ncclInt32, ctx->comm, ctx->st));
+    NC(ncclAllGather(ctx->d_bary + 3 * (size_t)ctx->minIdx, ctx->d_recvD, 3 * (size_t)per, ncclFloat64, ctx->comm, ctx->st));
+    NC(ncclGroupEnd());
+    CU(cudaMemcpyAsync(ctx->d_face, ctx->d_recvI, sizeof(int) * ctx->nTotal, cudaMemcpyDeviceToDevice, ctx->st));
+    CU(cudaMemcpyAsync(ctx->d_bary, ctx->d_recvD, sizeof(double) * 3 * ctx->nTotal, cudaMemcpyDeviceToDevice, ctx->st));
+    return CSS_OK;
+}
+// mpiSimulation::manipulateUpdaterData: all-gather k doubles per rank, fold in rank order
+int css_reduce(css_ctx* ctx, int op, int k, double* data)
+{
+    if (!ctx || k < 0 || k > 8 || !data) return CSS_EINVAL;
+    if (ctx->nranks == 1) return CSS_OK;
+    if (!ctx->comm) return fail(ctx, CSS_ENCCL, "communicator not initialised");
+    BIND();
+    // d_red[0..8) is the send block, d_redBuf[0 .. 8*nranks) receives
+    CU(cudaMemcpyAsync(ctx->d_red, data, sizeof(double) * k, cudaMemcpyHostToDevice, ctx->st));
+    NC(ncclAllGather(ctx->d_red, ctx->d_redBuf, 8, ncclFloat64, ctx->comm, ctx->st));
+    std::vector<double> h(8 * (size_t)ctx->nranks);
+    CU(cudaMemcpyAsync(h.data(), ctx->d_redBuf, sizeof(double) * 8 * ctx->nranks, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    for (int i = 0; i < k; ++i) {
+        double acc = 0.0; // mpiSimulation.cpp:78-88 starts from 0 for both sum and max
+        for (int r = 0; r < ctx->nranks; ++r) {
+            double y = h[8 * (size_t)r + i];
+            acc = op == CSS_MAX ? std::max(acc, y) : acc + y;
+        }
+        data[i] = acc;
+    }
+    return CSS_OK;
+}
+
+// ----------------------------------------------------------------------------------- diagnostics
+int css_counters(css_ctx* ctx, uint64_t* out, int reset)
+{
+    if (!ctx || !out) return CSS_EINVAL;
+    BIND();
+    unsigned long long h[NUM_COUNTERS];
+    CU(cudaStreamSynchronize(ctx->st));
+    CU(cudaMemcpy(h, ctx->d_counters, sizeof h, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < CSS_NUM_COUNTERS; ++i) out[i] = h[i];
+    out[CSS_C_KERNELS] = ctx->hostKernels;
+    if (reset) {
+        CU(cudaMemset(ctx->d_counters, 0, sizeof h));
+        ctx->hostKernels = 0;
+    }
+    return CSS_OK;
+}
+int css_synchronize(css_ctx* ctx)
+{
+    if (!ctx) return CSS_EINVAL;
+    BIND();
+    CU(cudaStreamSynchronize(ctx->st));
+    return CSS_OK;
+}
+int css_device_positions(css_ctx* ctx, void** face_dev, void** bary_dev)
+{
+    if (!ctx || !ctx->nTotal) return fail(ctx, CSS_ESTATE, "state not set");
+    if (face_dev) *face_dev = ctx->d_face;
+    if (bary_dev) *bary_dev = ctx->d_bary;
+    return CSS_OK;
+}
+int css_set_timing(css_ctx* ctx, int enabled)
+{
+    if (!ctx) return CSS_EINVAL;
+    ctx->timing = enabled != 0;
+    return CSS_OK;
+}
+int css_last_kernel_ms(css_ctx* ctx, float* geodesic_ms, float* walk_ms, float* celllist_ms)
+{
+    if (!ctx) return CSS_EINVAL;
+    if (geodesic_ms) *geodesic_ms = ctx->msGeo;
+    if (walk_ms) *walk_ms = ctx->msWalk;
+    if (celllist_ms) *celllist_ms = ctx->msCell;
+    return CSS_OK;
+}
+
+} // extern "C"
+#pragma GCC visibility pop

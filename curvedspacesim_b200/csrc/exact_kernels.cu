@@ -1,0 +1,602 @@
+// Kernels whose branches / indices must be bit-identical to the CPU oracle.  THIS FILE IS COMPILED WITH
+// -fmad=false (no FMA contraction); division and sqrt are IEEE-rounded in fp64 on the GPU.
+//
+//   k_euclid_cell   meshPositionToEuclideanLocation (triangulatedMeshSpace.cpp:82-106) fused with the
+//                   cell binning of hyperRectangularCellList::positionToCellIndex/sort (:71-125)
+//   k_scan_*        exclusive scan of the per-cell counts
+//   k_cell_fill / k_cell_rank   deterministic (ascending particle index) cell contents
+//   k_walk          triangulatedMeshSpace::transportParticleAndVectors (:448-658), one thread per particle,
+//                   optionally fused with the velocity-Verlet first half step (velocityVerletNVE.cpp:14-21)
+//   k_axpy-type     updater arithmetic (src/updaters/*.cpp) and reductions
+#include "common.cuh"
+#include "kernels.h"
+
+namespace css {
+
+__device__ __forceinline__ d3 operator+(const d3& a, const d3& b) { return d3{a.x + b.x, a.y + b.y, a.z + b.z}; }
+__device__ __forceinline__ d3 operator-(const d3& a, const d3& b) { return d3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ d3 operator*(double s, const d3& a) { return d3{s * a.x, s * a.y, s * a.z}; }
+__device__ __forceinline__ d3 operator/(const d3& a, double s) { return d3{a.x / s, a.y / s, a.z / s}; }
+__device__ __forceinline__ double dot(const d3& a, const d3& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ d3 cross(const d3& a, const d3& b)
+{
+    return d3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+__device__ __forceinline__ double sqlen(const d3& a) { return a.x * a.x + a.y * a.y + a.z * a.z; }
+__device__ __forceinline__ double norm(const d3& a) { return sqrt(sqlen(a)); }
+
+__device__ __forceinline__ d3 ld3(const double* p, int i) { return d3{p[3 * i], p[3 * i + 1], p[3 * i + 2]}; }
+__device__ __forceinline__ void st3(double* p, int i, const d3& v)
+{
+    p[3 * i] = v.x;
+    p[3 * i + 1] = v.y;
+    p[3 * i + 2] = v.z;
+}
+
+struct Tri {
+    d3 p0, p1, p2;
+};
+__device__ __forceinline__ Tri ldtri(const MeshDev& m, int f)
+{
+    int4 c = __ldg(m.corner + f);
+    return Tri{ldvert(m, c.x), ldvert(m, c.y), ldvert(m, c.z)};
+}
+__device__ __forceinline__ d3 tpoint(const Tri& t, const double b[3])
+{
+    double s = b[0] + b[1] + b[2];
+    return d3{(b[0] * t.p0.x + b[1] * t.p1.x + b[2] * t.p2.x) / s, (b[0] * t.p0.y + b[1] * t.p1.y + b[2] * t.p2.y) / s,
+              (b[0] * t.p0.z + b[1] * t.p1.z + b[2] * t.p2.z) / s};
+}
+__device__ __forceinline__ d3 tnormal(const Tri& t)
+{
+    d3 n = cross(t.p1 - t.p0, t.p2 - t.p0);
+    return n / norm(n);
+}
+__device__ __forceinline__ void ericson(const Tri& t, const d3& x, double out[3])
+{
+    d3 v0 = t.p1 - t.p0, v1 = t.p2 - t.p0, v2 = x - t.p0;
+    double d00 = dot(v0, v0), d01 = dot(v0, v1), d11 = dot(v1, v1), d20 = dot(v2, v0), d21 = dot(v2, v1);
+    double den = d00 * d11 - d01 * d01;
+    double vv = (d11 * d20 - d01 * d21) / den;
+    double ww = (d00 * d21 - d01 * d20) / den;
+    out[0] = 1.0 - vv - ww;
+    out[1] = vv;
+    out[2] = ww;
+}
+__device__ __forceinline__ void belowZeroClamp(double b[3])
+{
+    const double tol = 1e-11;
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        b[i] = (b[i] < tol) ? tol : b[i];
+        s += b[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) b[i] = b[i] / s;
+}
+__device__ __forceinline__ void nearZeroClamp(double b[3])
+{
+    const double tol = 1e-13;
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        if (b[i] > -tol && b[i] < tol) b[i] = tol;
+        s += b[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) b[i] = b[i] / s;
+}
+__device__ __forceinline__ d3 rotateAboutAxis(const d3& p, const d3& base, const d3& a, double s, double c)
+{
+    d3 tip = base + a;
+    d3 ax = tip - base;
+    double an = sqlen(ax);
+    ax = ax / sqrt(an);
+    d3 sh = p - base;
+    double dp = ax.x * sh.x + ax.y * sh.y + ax.z * sh.z;
+    d3 r;
+    r.x = ax.x * dp * (1. - c) + sh.x * c + (ax.y * sh.z - ax.z * sh.y) * s;
+    r.y = ax.y * dp * (1. - c) + sh.y * c + (ax.z * sh.x - ax.x * sh.z) * s;
+    r.z = ax.z * dp * (1. - c) + sh.z * c + (ax.x * sh.y - ax.y * sh.x) * s;
+    return r + base;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void k_euclid_cell(MeshDev m, CellGrid g, int n, const int* __restrict__ face, const double* __restrict__ bary,
+                              double* __restrict__ eucl, int* __restrict__ cellOf, int* __restrict__ cellCount)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Tri t = ldtri(m, face[i]);
+    double b[3] = {bary[3 * i], bary[3 * i + 1], bary[3 * i + 2]};
+    d3 p = tpoint(t, b);
+    st3(eucl, i, p);
+    if (cellOf) {
+        int ix = cellCoord(g, p.x, 0), iy = cellCoord(g, p.y, 1), iz = cellCoord(g, p.z, 2);
+        int c = ix + iy * g.n[0] + iz * g.n[0] * g.n[1];
+        cellOf[i] = c;
+        atomicAdd(cellCount + c, 1);
+    }
+}
+
+// exclusive scan, 3 passes; each block handles SCAN_ITEMS consecutive counts
+#define SCAN_THREADS 1024
+#define SCAN_PER_THREAD 4
+#define SCAN_ITEMS (SCAN_THREADS * SCAN_PER_THREAD)
+__device__ __forceinline__ int blockExclusiveScan(int v, int* total)
+{
+    __shared__ int warpSums[32];
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) warpSums[w] = x;
+    __syncthreads();
+    if (w == 0) {
+        int s = warpSums[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int y = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= o) s += y;
+        }
+        warpSums[lane] = s;
+    }
+    __syncthreads();
+    int base = w ? warpSums[w - 1] : 0;
+    if (total) *total = warpSums[31];
+    __syncthreads();
+    return base + x - v;
+}
+__global__ void k_scan_local(const int* __restrict__ in, int* __restrict__ out, int* __restrict__ blockSums, int n)
+{
+    int base = blockIdx.x * SCAN_ITEMS + threadIdx.x * SCAN_PER_THREAD;
+    int v[SCAN_PER_THREAD], s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_PER_THREAD; ++k) {
+        v[k] = (base + k < n) ? in[base + k] : 0;
+        s += v[k];
+    }
+    int tot;
+    int ex = blockExclusiveScan(s, &tot);
+#pragma unroll
+    for (int k = 0; k < SCAN_PER_THREAD; ++k) {
+        if (base + k < n) out[base + k] = ex;
+        ex += v[k];
+    }
+    if (threadIdx.x == 0) blockSums[blockIdx.x] = tot;
+}
+__global__ void k_scan_blocks(int* blockSums, int nb) // single block; nb <= SCAN_ITEMS * many via loop
+{
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int start = 0; start < nb; start += SCAN_THREADS) {
+        int i = start + threadIdx.x;
+        int v = i < nb ? blockSums[i] : 0;
+        int tot;
+        int ex = blockExclusiveScan(v, &tot);
+        int c = carry;
+        if (i < nb) blockSums[i] = ex + c;
+        __syncthreads();
+        if (threadIdx.x == 0) carry = c + tot;
+        __syncthreads();
+    }
+}
+__global__ void k_scan_add(int* __restrict__ out, const int* __restrict__ blockSums, int n, int* __restrict__ fill, int total)
+{
+    int base = blockIdx.x * SCAN_ITEMS + threadIdx.x * SCAN_PER_THREAD;
+    int add = blockSums[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_PER_THREAD; ++k)
+        if (base + k < n) {
+            out[base + k] += add;
+            fill[base + k] = 0;
+        }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) out[n] = total;
+}
+__global__ void k_cell_fill(int n, const int* __restrict__ cellOf, const int* __restrict__ cellStart, int* __restrict__ fill,
+                            int* __restrict__ tmpItems)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int c = cellOf[i];
+    int s = atomicAdd(fill + c, 1);
+    tmpItems[cellStart[c] + s] = i;
+}
+// rank of particle i inside its cell = number of members with a smaller index -> ascending order, as
+// hyperRectangularCellList::sort produces by inserting particles in index order (:96-112)
+__global__ void k_cell_rank(int n, const int* __restrict__ cellOf, const int* __restrict__ cellStart, const int* __restrict__ fill,
+                            const int* __restrict__ tmpItems, int* __restrict__ items)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int c = cellOf[i];
+    int s0 = cellStart[c], cnt = fill[c];
+    int r = 0;
+    for (int s = 0; s < cnt; ++s) r += (tmpItems[s0 + s] < i);
+    items[s0 + r] = i;
+}
+
+// ------------------------------------------------------------------------------------------------
+// The walker.  One thread per particle.  mode bit0: displacement computed in-kernel as the velocity-
+// Verlet first half step (disp = dt v + dt^2/2 f ; v += dt/2 f); otherwise disp is read from `disp`.
+__device__ __forceinline__ int edgeHits(const double S[3], const double E[3], int last, int& firstK, int& lastK, double I[3])
+{
+    int nh = 0;
+    if (last != 2) {
+        double den = S[0] + S[1] - E[0] - E[1];
+        if (den != 0) {
+            double t1 = (-E[1] + E[1] * S[0] + S[1] - E[0] * S[1]) / den;
+            double t2 = (-1 + S[0] + S[1]) / den;
+            if (t1 >= 0 && t1 <= 1 && t2 >= 0 && t2 <= 1) {
+                I[0] = S[0] + t2 * (E[0] - S[0]);
+                I[1] = S[1] + t2 * (E[1] - S[1]);
+                I[2] = S[2] + t2 * (E[2] - S[2]);
+                if (!nh) firstK = 2;
+                lastK = 2;
+                nh++;
+            }
+        }
+    }
+    if (last != 0) {
+        double den = -E[0] + S[0];
+        if (den != 0) {
+            double t1 = -(E[0] - S[0] + E[1] * S[0] - E[0] * S[1]) / den;
+            double t2 = (S[0]) / den;
+            if (t1 >= 0 && t1 <= 1 && t2 >= 0 && t2 <= 1) {
+                I[0] = S[0] + t2 * (E[0] - S[0]);
+                I[1] = S[1] + t2 * (E[1] - S[1]);
+                I[2] = S[2] + t2 * (E[2] - S[2]);
+                if (!nh) firstK = 0;
+                lastK = 0;
+                nh++;
+            }
+        }
+    }
+    if (last != 1) {
+        double den = S[1] - E[1];
+        if (den != 0) {
+            double t1 = (E[0] * S[1] - E[1] * S[0]) / den;
+            double t2 = S[1] / den;
+            if (t1 >= 0 && t1 <= 1 && t2 >= 0 && t2 <= 1) {
+                I[0] = S[0] + t2 * (E[0] - S[0]);
+                I[1] = S[1] + t2 * (E[1] - S[1]);
+                I[2] = S[2] + t2 * (E[2] - S[2]);
+                if (!nh) firstK = 1;
+                lastK = 1;
+                nh++;
+            }
+        }
+    }
+    return nh;
+}
+
+template <int NT>
+__device__ __forceinline__ int walkOne(const MeshDev& m, int& face, double bary[3], d3& disp, d3 (&T)[NT > 0 ? NT : 1], int nT,
+                                       int& nCross)
+{
+    int flags = 0;
+    int f = face;
+    double S[3] = {bary[0], bary[1], bary[2]};
+    Tri tri = ldtri(m, f);
+    d3 p = tpoint(tri, S);
+    d3 n = tnormal(tri);
+    double nd = dot(n, disp);
+    if (fabs(nd) > 1e-14) disp = disp - nd * n;
+    d3 q = p + disp;
+    int last = -1;
+    double E[3];
+    nCross = 0;
+    for (;;) {
+        ericson(tri, q, E);
+        nearZeroClamp(E);
+        q = tpoint(tri, E);
+        belowZeroClamp(S);
+        p = tpoint(tri, S);
+        disp = q - p;
+        if (E[0] != E[0]) {
+            flags |= WALK_NAN;
+            break;
+        }
+        if (!(E[0] < 0 || E[1] < 0 || E[2] < 0)) break;
+        if (nCross >= CSS_WALK_MAX_CROSSINGS) {
+            flags |= WALK_ITERCAP;
+            belowZeroClamp(E);
+            break;
+        }
+        int k0 = 0, k1 = 0;
+        double I[3];
+        int nh = edgeHits(S, E, last, k0, k1, I);
+        if (nh == 0) {
+            flags |= WALK_NOHIT;
+            belowZeroClamp(E);
+            break;
+        }
+        belowZeroClamp(I);
+        d3 x = tpoint(tri, I);
+        S[0] = I[0], S[1] = I[1], S[2] = I[2];
+        p = x;
+        int k = nh >= 2 ? k1 : k0;
+        if (nh >= 2) flags |= WALK_VERTEX;
+        int4 a = __ldg(m.adj + f);
+        int g = k == 0 ? a.x : (k == 1 ? a.y : a.z);
+        if (g < 0) {
+            flags |= WALK_BORDER;
+            E[0] = S[0], E[1] = S[1], E[2] = S[2];
+            break;
+        }
+        Tri tri2 = ldtri(m, g);
+        d3 n2 = tnormal(tri2);
+        double c = dot(n, n2);
+        d3 ax = cross(n, n2);
+        double an = norm(ax);
+        if (c < 1 && an > 0) {
+            ax = ax / an;
+            q = rotateAboutAxis(q, p, ax, an, c);
+            disp = q - p;
+#pragma unroll
+            for (int i = 0; i < NT; ++i)
+                if (i < nT) {
+                    d3 tt = p + T[i];
+                    tt = rotateAboutAxis(tt, p, ax, an, c);
+                    T[i] = tt - p;
+                }
+        }
+        last = (a.w >> (2 * k)) & 3;
+        f = g;
+        tri = tri2;
+        ericson(tri, p, S);
+        n = n2;
+        nCross++;
+    }
+    face = f;
+    bary[0] = E[0], bary[1] = E[1], bary[2] = E[2];
+    return flags;
+}
+
+// particles [0,n) of this rank; global index = minIdx + i in face/bary
+__global__ void k_walk(MeshDev m, int n, int minIdx, int* __restrict__ face, double* __restrict__ bary, double* __restrict__ disp,
+                       double* __restrict__ vel, double* __restrict__ frc, int transportForce, int transportVelocity, int mode,
+                       double dt, int* __restrict__ flagsOut, unsigned long long* __restrict__ counters)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int fl = 0, nc = 0;
+    if (i < n) {
+        d3 d;
+        if (mode & 1) { // velocityVerletNVE::velocityVerletFirstHalfStep
+            d3 v = ld3(vel, i), f = ld3(frc, i);
+            d = dt * v + (0.5 * dt * dt) * f;
+            v = v + (0.5 * dt) * f;
+            st3(vel, i, v);
+        } else
+            d = ld3(disp, i);
+        d3 T[2];
+        int nT = 0;
+        if (transportForce) T[nT++] = ld3(frc, i);
+        if (transportVelocity) T[nT++] = ld3(vel, i);
+        int gi = minIdx + i;
+        int f = face[gi];
+        double b[3] = {bary[3 * gi], bary[3 * gi + 1], bary[3 * gi + 2]};
+        fl = walkOne<2>(m, f, b, d, T, nT, nc);
+        face[gi] = f;
+        bary[3 * gi] = b[0], bary[3 * gi + 1] = b[1], bary[3 * gi + 2] = b[2];
+        st3(disp, i, d);
+        nT = 0;
+        if (transportForce) st3(frc, i, T[nT++]);
+        if (transportVelocity) st3(vel, i, T[nT++]);
+        if (flagsOut) flagsOut[i] = fl;
+    }
+    // counters: warp-aggregated
+    unsigned mask = 0xffffffffu;
+    for (int b = 0; b < 5; ++b) {
+        unsigned bal = __ballot_sync(mask, (fl >> b) & 1);
+        if ((threadIdx.x & 31) == 0 && bal) atomicAdd(counters + b, (unsigned long long)__popc(bal));
+    }
+    int s = nc;
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(mask, s, o);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(counters + C_CROSSINGS, (unsigned long long)s);
+}
+
+// generic per-call transport (css_transport): arbitrary number of vectors handled NV at a time
+__global__ void k_transport_generic(MeshDev m, int n, int* __restrict__ face, double* __restrict__ bary, double* __restrict__ disp,
+                                    int nVec, double* __restrict__ vecs, int* __restrict__ flagsOut)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int f0 = face[i];
+    double b0[3] = {bary[3 * i], bary[3 * i + 1], bary[3 * i + 2]};
+    d3 d0 = ld3(disp, i);
+    int fl = 0, nc;
+    int f = f0;
+    double b[3];
+    d3 d = d0;
+    if (nVec == 0) {
+        d3 T[1];
+        b[0] = b0[0], b[1] = b0[1], b[2] = b0[2];
+        fl = walkOne<0>(m, f, b, d, T, 0, nc);
+    }
+    for (int v0 = 0; v0 < nVec; v0 += 2) { // each pass re-walks the same (deterministic) path carrying two vectors
+        d3 T[2];
+        int nT = min(2, nVec - v0);
+        for (int j = 0; j < nT; ++j) T[j] = ld3(vecs, i * nVec + v0 + j);
+        f = f0;
+        b[0] = b0[0], b[1] = b0[1], b[2] = b0[2];
+        d = d0;
+        fl = walkOne<2>(m, f, b, d, T, nT, nc);
+        for (int j = 0; j < nT; ++j) st3(vecs, i * nVec + v0 + j, T[j]);
+    }
+    face[i] = f;
+    bary[3 * i] = b[0], bary[3 * i + 1] = b[1], bary[3 * i + 2] = b[2];
+    st3(disp, i, d);
+    if (flagsOut) flagsOut[i] = fl;
+}
+
+// ---------------------------------------------------------------------------------- updater math
+// op 0: v += a*f                      (velocityVerletNVE second half: a = dt/2 ; NVT: a = dt)
+// op 1: disp = a*f                    (gradientDescent.cpp:12-14)
+// op 2: v = a*v                       (noseHooverNVT velocity rescale)
+// op 3: disp = a*v                    (noseHooverNVT half move)
+// op 4: v = (1-b)*v + (b*a)*f         (FIRE mixing, a = scaling, b = alpha)
+// op 5: v = 0
+__global__ void k_axpy(int op, int n, double a, double b, double* __restrict__ vel, const double* __restrict__ frc,
+                       double* __restrict__ disp)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (op == 0) st3(vel, i, ld3(vel, i) + a * ld3(frc, i));
+    else if (op == 1) st3(disp, i, a * ld3(frc, i));
+    else if (op == 2) st3(vel, i, a * ld3(vel, i));
+    else if (op == 3) st3(disp, i, a * ld3(vel, i));
+    else if (op == 4) st3(vel, i, (1 - b) * ld3(vel, i) + (b * a) * ld3(frc, i));
+    else if (op == 5) st3(vel, i, d3{0, 0, 0});
+}
+
+// Deterministic reductions: every block writes one partial; a single block folds them in order.
+// out[0]=sum f.f  out[1]=sum v.v  out[2]=sum f.v  out[3]=max f.f  out[4]=sum 0.5 v.v
+// NOTE the reference accumulates these serially (fireMinimization.cpp:23-34, baseUpdater.cpp:22-54);
+// a tree order differs by rounding only (documented in DESIGN.md).
+__global__ void k_reduce_partial(int n, const double* __restrict__ vel, const double* __restrict__ frc, double* __restrict__ partial)
+{
+    __shared__ double sm[5][32];
+    double ff = 0, vv = 0, fv = 0, mx = 0, ke = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        d3 v = ld3(vel, i), f = ld3(frc, i);
+        double a = dot(f, f), b = dot(v, v);
+        ff += a;
+        vv += b;
+        fv += dot(f, v);
+        mx = a > mx ? a : mx;
+        ke += 0.5 * (1.0) * b;
+    }
+    double vals[5] = {ff, vv, fv, mx, ke};
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        double x = vals[k];
+        for (int o = 16; o; o >>= 1) {
+            double y = __shfl_xor_sync(0xffffffffu, x, o);
+            x = (k == 3) ? (x > y ? x : y) : x + y;
+        }
+        if (lane == 0) sm[k][w] = x;
+    }
+    __syncthreads();
+    if (w == 0) {
+        int nw = blockDim.x >> 5;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            double x = lane < nw ? sm[k][lane] : 0.0;
+            for (int o = 16; o; o >>= 1) {
+                double y = __shfl_xor_sync(0xffffffffu, x, o);
+                x = (k == 3) ? (x > y ? x : y) : x + y;
+            }
+            if (lane == 0) partial[blockIdx.x * 5 + k] = x;
+        }
+    }
+}
+__global__ void k_reduce_final(int nb, const double* __restrict__ partial, double* __restrict__ out)
+{
+    int k = threadIdx.x;
+    if (k >= 5) return;
+    double x = 0;
+    for (int b = 0; b < nb; ++b) {
+        double y = partial[b * 5 + k];
+        x = (k == 3) ? (x > y ? x : y) : x + y;
+    }
+    out[k] = x;
+}
+
+// force::computeEnergy (baseForce.cpp:33-44): sum over particles, neighbours in list order
+__device__ __forceinline__ double pairEnergy(const ForceParams& fp, double d)
+{
+    if (fp.kind == 0) { // harmonicRepulsion.cpp:3-16
+        double ans = 0;
+        if (d < fp.sigma) ans = 0.5 * fp.a * (fp.sigma - d) * (fp.sigma - d);
+        return ans;
+    }
+    const double sqrtTwoPi = 2.50662827463100050241576528481104525300698674061;
+    double twoSigmaSquared = 2.0 * fp.sigma * fp.sigma;
+    return fp.a * exp(-d * d / twoSigmaSquared) / (sqrtTwoPi * fp.sigma);
+}
+__global__ void k_energy_partial(int n, int kmax, const int* __restrict__ nbrCount, const double* __restrict__ nbrDist, ForceParams fp,
+                                 double* __restrict__ partial)
+{
+    __shared__ double sm[32];
+    double e = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int K = nbrCount[i];
+        for (int j = 0; j < K; ++j) e += pairEnergy(fp, nbrDist[(size_t)i * kmax + j]);
+    }
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int o = 16; o; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+    if (lane == 0) sm[w] = e;
+    __syncthreads();
+    if (w == 0) {
+        double x = lane < (blockDim.x >> 5) ? sm[lane] : 0.0;
+        for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0) partial[blockIdx.x] = x;
+    }
+}
+__global__ void k_energy_final(int nb, const double* __restrict__ partial, double* __restrict__ out)
+{
+    double x = 0;
+    for (int b = 0; b < nb; ++b) x += partial[b];
+    out[0] = x;
+}
+
+// ---------------------------------------------------------------------------------- host launchers
+static inline int gridFor(int n, int b) { return (n + b - 1) / b; }
+
+void launchEuclidCell(cudaStream_t st, const MeshDev& m, const CellGrid& g, int n, const int* face, const double* bary, double* eucl,
+                      int* cellOf, int* cellCount)
+{
+    if (n > 0) k_euclid_cell<<<gridFor(n, 256), 256, 0, st>>>(m, g, n, face, bary, eucl, cellOf, cellCount);
+}
+int scanBlocks(int nCells) { return (nCells + SCAN_ITEMS - 1) / SCAN_ITEMS; }
+void launchCellBuild(cudaStream_t st, int n, int nCells, const int* cellOf, const int* cellCount, int* cellStart, int* blockSums,
+                     int* fill, int* tmpItems, int* items)
+{
+    int nb = scanBlocks(nCells);
+    k_scan_local<<<nb, SCAN_THREADS, 0, st>>>(cellCount, cellStart, blockSums, nCells);
+    k_scan_blocks<<<1, SCAN_THREADS, 0, st>>>(blockSums, nb);
+    k_scan_add<<<nb, SCAN_THREADS, 0, st>>>(cellStart, blockSums, nCells, fill, n);
+    if (n > 0) {
+        k_cell_fill<<<gridFor(n, 256), 256, 0, st>>>(n, cellOf, cellStart, fill, tmpItems);
+        k_cell_rank<<<gridFor(n, 256), 256, 0, st>>>(n, cellOf, cellStart, fill, tmpItems, items);
+    }
+}
+void launchWalk(cudaStream_t st, const MeshDev& m, int n, int minIdx, int* face, double* bary, double* disp, double* vel, double* frc,
+                int transportForce, int transportVelocity, int mode, double dt, int* flags, unsigned long long* counters)
+{
+    if (n > 0)
+        k_walk<<<gridFor(n, 128), 128, 0, st>>>(m, n, minIdx, face, bary, disp, vel, frc, transportForce, transportVelocity, mode, dt,
+                                                flags, counters);
+}
+void launchTransportGeneric(cudaStream_t st, const MeshDev& m, int n, int* face, double* bary, double* disp, int nVec, double* vecs,
+                            int* flags)
+{
+    if (n > 0) k_transport_generic<<<gridFor(n, 128), 128, 0, st>>>(m, n, face, bary, disp, nVec, vecs, flags);
+}
+void launchAxpy(cudaStream_t st, int op, int n, double a, double b, double* vel, const double* frc, double* disp)
+{
+    if (n > 0) k_axpy<<<gridFor(n, 256), 256, 0, st>>>(op, n, a, b, vel, frc, disp);
+}
+void launchReduce(cudaStream_t st, int n, const double* vel, const double* frc, double* partial, double* out)
+{
+    int nb = n > 0 ? min(REDUCE_MAX_BLOCKS, gridFor(n, 256)) : 1;
+    k_reduce_partial<<<nb, 256, 0, st>>>(n, vel, frc, partial);
+    k_reduce_final<<<1, 32, 0, st>>>(nb, partial, out);
+}
+
+void launchEnergy(cudaStream_t st, int nLocal, int kmax, const int* nbrCount, const double* nbrDist, ForceParams fp, double* partial,
+                  double* out)
+{
+    int nb = nLocal > 0 ? min(REDUCE_MAX_BLOCKS, gridFor(nLocal, 256)) : 1;
+    k_energy_partial<<<nb, 256, 0, st>>>(nLocal, kmax, nbrCount, nbrDist, fp, partial);
+    k_energy_final<<<1, 1, 0, st>>>(nb, partial, out);
+}
+
+} // namespace css
