@@ -32,6 +32,7 @@ API_SYMBOLS = [
     "css_get_walk_flags", "css_step_nve", "css_step_gd", "css_nvt_init", "css_step_nvt", "css_nvt_state", "css_fire_init",
     "css_fire_minimize", "css_max_force", "css_force_norm", "css_comm_unique_id", "css_comm_init", "css_gather_positions",
     "css_reduce", "css_counters", "css_synchronize", "css_device_positions", "css_last_kernel_ms", "css_set_timing",
+    "css_timer_record", "css_timer_elapsed_ms",
 ]
 
 _lib = None
@@ -285,3 +286,11 @@ class Context:
         g, w, c = C.c_float(), C.c_float(), C.c_float()
         self._ck(self.L.css_last_kernel_ms(self.h, C.byref(g), C.byref(w), C.byref(c)))
         return {"geodesic_ms": g.value, "walk_ms": w.value, "celllist_ms": c.value}
+
+    def timer_record(self, slot):
+        self._ck(self.L.css_timer_record(self.h, int(slot)))
+
+    def timer_elapsed_ms(self, a, b):
+        ms = C.c_float()
+        self._ck(self.L.css_timer_elapsed_ms(self.h, int(a), int(b), C.byref(ms)))
+        return ms.value

@@ -88,6 +88,7 @@ struct css_ctx {
     bool timing = false;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     float msGeo = 0, msWalk = 0, msCell = 0;
+    cudaEvent_t tev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 static int fail(css_ctx* c, int code, const char* fmt, ...)
@@ -141,6 +142,7 @@ int css_create(css_ctx** out, int device)
     cudaMalloc(&ctx->d_partial, REDUCE_MAX_BLOCKS * 5 * sizeof(double));
     cudaMalloc(&ctx->d_red, 8 * sizeof(double));
     for (auto& e : ctx->ev) cudaEventCreate(&e);
+    for (auto& e : ctx->tev) cudaEventCreate(&e);
     *out = ctx;
     return CSS_OK;
 }
@@ -160,6 +162,8 @@ int css_destroy(css_ctx* ctx)
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (auto& e : ctx->ev)
+        if (e) cudaEventDestroy(e);
+    for (auto& e : ctx->tev)
         if (e) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->st);
     delete ctx;
@@ -1111,6 +1115,22 @@ int css_last_kernel_ms(css_ctx* ctx, float* geodesic_ms, float* walk_ms, float* 
     if (geodesic_ms) *geodesic_ms = ctx->msGeo;
     if (walk_ms) *walk_ms = ctx->msWalk;
     if (celllist_ms) *celllist_ms = ctx->msCell;
+    return CSS_OK;
+}
+
+int css_timer_record(css_ctx* ctx, int slot)
+{
+    if (!ctx || slot < 0 || slot >= 8) return CSS_EINVAL;
+    BIND();
+    CU(cudaEventRecord(ctx->tev[slot], ctx->st));
+    return CSS_OK;
+}
+int css_timer_elapsed_ms(css_ctx* ctx, int slotA, int slotB, float* ms)
+{
+    if (!ctx || slotA < 0 || slotA >= 8 || slotB < 0 || slotB >= 8 || !ms) return CSS_EINVAL;
+    BIND();
+    CU(cudaEventSynchronize(ctx->tev[slotB]));
+    CU(cudaEventElapsedTime(ms, ctx->tev[slotA], ctx->tev[slotB]));
     return CSS_OK;
 }
 
