@@ -82,7 +82,9 @@ enum { WALK_VERTEX = 1, WALK_NOHIT = 2, WALK_ITERCAP = 4, WALK_NAN = 8, WALK_BOR
 enum {
     C_WALK_VERTEX = 0, C_WALK_NOHIT, C_WALK_ITERCAP, C_WALK_NAN, C_WALK_BORDER, C_DISCONNECTED, C_TIES, C_CROSSINGS, C_WINDOWS,
     C_PSEUDO, C_PATCH_FACES, C_PATCH_VERTS, C_QUERIES, C_SOURCES, C_TIER_RETRY, C_OVERFLOW, C_KERNELS, C_KMAX_OVERFLOW,
-    NUM_COUNTERS = 24
+    C_OVF_REASON /* 18..21: candidates, faces, vertices, ring */,
+    C_CLK_BATCH = 22, C_CLK_FAN = 23, C_CLK_PROP = 24, C_CLK_PATCH = 25, C_CLK_TOTAL = 26, /* summed per-warp clock64 cycles */
+    NUM_COUNTERS = 32
 };
 #define CSS_WALK_MAX_CROSSINGS 100000
 

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <nccl.h>
@@ -56,6 +57,7 @@ struct css_ctx {
     size_t gwsBytes = 0;
     GeoCaps capsT0{96, 64, 64, 16, 256, 256}, capsT1{768, 448, 1024, 128, 2048, 1024}, capsT2{0, 0, 0, 0, 0, 0};
     int t2Warps = 32;
+    int wpb0 = 4, wpb1 = 1;
     int numSMs = 148;
     // reductions / scratch
     double *d_partial = nullptr, *d_red = nullptr;
@@ -142,6 +144,17 @@ int css_create(css_ctx** out, int device)
     cudaMalloc(&ctx->d_partial, REDUCE_MAX_BLOCKS * 5 * sizeof(double));
     cudaMalloc(&ctx->d_red, 8 * sizeof(double));
     for (auto& e : ctx->ev) cudaEventCreate(&e);
+    if (const char* tune = getenv("CSS_TUNE")) { // developer tuning: t0 maxF,maxV,ring,kt,warpsPerBlock, t1 ...
+        int v[10];
+        int n = sscanf(tune, "%d,%d,%d,%d,%d,%d,%d,%d,%d,%d", v, v + 1, v + 2, v + 3, v + 4, v + 5, v + 6, v + 7, v + 8, v + 9);
+        auto p2 = [](int x) {
+            int p = 1;
+            while (p < x) p <<= 1;
+            return p;
+        };
+        if (n >= 5) ctx->capsT0 = GeoCaps{v[0], v[1], p2(v[2]), v[3], p2(2 * v[0] + 64), p2(2 * v[1] + 128)}, ctx->wpb0 = v[4];
+        if (n >= 10) ctx->capsT1 = GeoCaps{v[5], v[6], p2(v[7]), v[8], p2(2 * v[5] + 64), p2(2 * v[6] + 128)}, ctx->wpb1 = v[9];
+    }
     for (auto& e : ctx->tev) cudaEventCreate(&e);
     *out = ctx;
     return CSS_OK;
@@ -369,10 +382,10 @@ static int runGeodesicTiers(css_ctx* ctx, GeoArgs a, int nSrc)
         a.retryList = ctx->d_retry[0], a.retryCount = ctx->d_work + 4;
         a.gws = nullptr, a.lastTier = 0;
         size_t ws = geoWorkspaceBytes(a.caps);
-        int wpb = 4;
-        int bps = std::max(1, std::min(3, (int)(geodesicMaxSmemPerBlock() / (ws * wpb))));
+        int wpb = ctx->wpb0;
+        int bps = std::max(1, std::min(12 / wpb, (int)(geodesicMaxSmemPerBlock() / (ws * wpb))));
         int blocks = std::min(ctx->numSMs * bps, std::max(1, (nSrc + wpb - 1) / wpb));
-        launchGeodesic(ctx->st, a, wpb, blocks);
+        CU(launchGeodesic(ctx->st, a, wpb, blocks));
         ctx->hostKernels++;
     }
     // tier 1: shared memory, one warp per block, large capacities
@@ -382,7 +395,9 @@ static int runGeodesicTiers(css_ctx* ctx, GeoArgs a, int nSrc)
         a.workCounter = ctx->d_work + 1;
         a.retryList = ctx->d_retry[1], a.retryCount = ctx->d_work + 5;
         a.gws = nullptr, a.lastTier = 0;
-        launchGeodesic(ctx->st, a, 1, std::min(ctx->numSMs, std::max(1, nSrc)));
+        size_t ws1 = geoWorkspaceBytes(a.caps);
+        int bps1 = std::max(1, std::min(12 / ctx->wpb1, (int)(geodesicMaxSmemPerBlock() / (ws1 * ctx->wpb1))));
+        CU(launchGeodesic(ctx->st, a, ctx->wpb1, std::min(ctx->numSMs * bps1, std::max(1, nSrc))));
         ctx->hostKernels++;
     }
     // tier 2: global-memory workspace sized for the whole mesh
@@ -403,7 +418,7 @@ static int runGeodesicTiers(css_ctx* ctx, GeoArgs a, int nSrc)
         a.workCounter = ctx->d_work + 2;
         a.retryList = ctx->d_retry[2], a.retryCount = ctx->d_work + 6;
         a.gws = ctx->d_gws, a.lastTier = 1;
-        launchGeodesic(ctx->st, a, 1, warps);
+        CU(launchGeodesic(ctx->st, a, 1, warps));
         ctx->hostKernels++;
     }
     return CSS_OK;

@@ -26,7 +26,7 @@ namespace css {
 #define NONE16 0xFFFFu
 static __device__ __forceinline__ double dinf() { return __longlong_as_double(0x7ff0000000000000LL); }
 
-enum { ST_OK = 0, ST_OVERFLOW = 1 };
+enum { ST_OK = 0, ST_OVERFLOW = 1, ST_OVF_K = 1, ST_OVF_F = 2, ST_OVF_V = 3, ST_OVF_RING = 4 };
 
 struct WS { // per-warp workspace, carved from one contiguous block; arrays addressed as base + k*capacity
     double *dv, *dt, *dr, *root;     // per-vertex [7*maxV], per-target [13*kt], ring [9*ring], root frame [16]
@@ -150,11 +150,12 @@ __device__ __forceinline__ bool atomicMinD(double* addr, double v)
     return nv < old;
 }
 
+__device__ __forceinline__ double frcp(double x);
 __device__ __forceinline__ double hitParam(const v2& S, const v2& P, const v2& X, const v2& Y)
 { // ray S->P against X + mu (Y - X), clamped
     v2 d = P - S;
     double den = cross2(Y - X, d);
-    double mu = cross2(S - X, d) / den;
+    double mu = cross2(S - X, d) * frcp(den);
     if (!(mu == mu)) mu = 0.5;
     return fmin(1.0, fmax(0.0, mu));
 }
@@ -165,6 +166,40 @@ __device__ __forceinline__ double segDist(const v2& S, const v2& X0, const v2& X
     double s = L2 > 0 ? ((S.x - X0.x) * e.x + (S.y - X0.y) * e.y) / L2 : 0.0;
     s = fmin(1.0, fmax(0.0, s));
     return dist2(S, v2{X0.x + s * e.x, X0.y + s * e.y});
+}
+
+// fast (not correctly rounded, ~1 ulp) reciprocal / square root: hardware seed + Newton steps.  Used for the
+// window geometry only; every topology-fixing decision uses the exactly rounded x* helpers of common.cuh.
+__device__ __forceinline__ double frcp(double x)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(r, fma(-x, r, 1.0), r);
+    r = fma(r, fma(-x, r, 1.0), r);
+    return r;
+}
+__device__ __forceinline__ double fsqrt(double x)
+{
+    if (!(x > 0)) return 0.0;
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double hx = 0.5 * x;
+    y = y * fma(-hx * y, y, 1.5);
+    y = y * fma(-hx * y, y, 1.5);
+    double s = x * y;
+    return fma(fma(-s, s, x), 0.5 * y, s); // one correction step on the square root itself
+}
+// float-precision lengths for pruning decisions (always used with a conservative margin)
+__device__ __forceinline__ float alen2(const v2& a) { return sqrtf((float)(a.x * a.x + a.y * a.y)); }
+__device__ __forceinline__ float adist2(const v2& a, const v2& b) { return alen2(a - b); }
+__device__ __forceinline__ float asegDist(const v2& S, const v2& X0, const v2& X1)
+{
+    float ex = (float)(X1.x - X0.x), ey = (float)(X1.y - X0.y), sx = (float)(S.x - X0.x), sy = (float)(S.y - X0.y);
+    float L2 = ex * ex + ey * ey;
+    float s = L2 > 0.f ? __fdividef(sx * ex + sy * ey, L2) : 0.f;
+    s = fminf(1.f, fmaxf(0.f, s));
+    float dx = sx - s * ex, dy = sy - s * ey;
+    return sqrtf(dx * dx + dy * dy);
 }
 
 struct Child {
@@ -197,6 +232,7 @@ __device__ int processSource(const GeoArgs& a, const WS& w, int li, int lane)
 {
     const GeoCaps& cp = a.caps;
     unsigned long long* cnt = w.wcnt;
+    const long long tp0 = clock64();
     const bool explicitQ = a.xK >= 0;
     const int gi = a.minIdx + li;
     const int maskF = cp.hashF - 1, maskV = cp.hashV - 1, maskR = cp.ring - 1;
@@ -222,7 +258,7 @@ __device__ int processSource(const GeoArgs& a, const WS& w, int li, int lane)
     if (explicitQ) {
         K = a.xK;
         R = a.xThreshold;
-        if (K > cp.kt) return ST_OVERFLOW;
+        if (K > cp.kt) return ST_OVF_K;
         for (int t = lane; t < K; t += 32) w.tIdx[t] = t;
     } else if (a.cellStart) {
         const CellGrid& g = a.grid;
@@ -255,7 +291,7 @@ __device__ int processSource(const GeoArgs& a, const WS& w, int li, int lane)
         K = __shfl_sync(FULL, incl, 31);
         maxd2 = warpMax(maxd2);
         R = xsqrt(maxd2);
-        if (K > cp.kt) return ST_OVERFLOW;
+        if (K > cp.kt) return ST_OVF_K;
         int pos = incl - mine;
         for (int s = s0; s < s1; ++s) {
             int j = a.cellItems[s];
@@ -267,7 +303,7 @@ __device__ int processSource(const GeoArgs& a, const WS& w, int li, int lane)
     } else { // baseNeighborStructure::constructCandidateNeighborList: everybody else, VERYLARGEDOUBLE
         K = a.nTotal - 1;
         R = 1e20;
-        if (K > cp.kt) return ST_OVERFLOW;
+        if (K > cp.kt) return ST_OVF_K;
         for (int t = lane; t < K; t += 32) w.tIdx[t] = t < gi ? t : t + 1;
     }
     if (!explicitQ && K > a.kmax) {
@@ -361,7 +397,7 @@ __device__ int processSource(const GeoArgs& a, const WS& w, int li, int lane)
             for (;;) {
                 __syncwarp();
                 int tail = min(w.misc[0], cp.maxF);
-                if (w.misc[2]) return ST_OVERFLOW;
+                if (w.misc[2]) return ST_OVF_F;
                 if (head >= tail) break;
                 int idx = head + lane;
                 if (idx < tail) {
@@ -393,7 +429,7 @@ __device__ int processSource(const GeoArgs& a, const WS& w, int li, int lane)
         }
     }
     __syncwarp();
-    if (w.misc[2] || w.misc[0] > cp.maxF) return ST_OVERFLOW;
+    if (w.misc[2] || w.misc[0] > cp.maxF) return ST_OVF_F;
     const int nF = w.misc[0];
 
     // ---------------- 4. local indexing ----------------
@@ -416,7 +452,7 @@ __device__ int processSource(const GeoArgs& a, const WS& w, int li, int lane)
         if (w.misc[2]) break; // hash table might be full next: stop inserting
     }
     __syncwarp();
-    if (w.misc[2] || w.misc[1] > cp.maxV) return ST_OVERFLOW;
+    if (w.misc[2] || w.misc[1] > cp.maxV) return ST_OVF_V;
     const int nV = w.misc[1];
     for (int v = lane; v < nV; v += 32) {
         int gv = w.gvert[v];
@@ -540,40 +576,233 @@ __device__ int processSource(const GeoArgs& a, const WS& w, int li, int lane)
 
     double U = dinf();
     unsigned long long nWin = 0, nPs = 0;
+    long long tk0 = clock64(), clkFan = 0, clkBatch = 0;
+    if (lane == 0) atomicAdd(a.counters + C_CLK_PATCH, (unsigned long long)(tk0 - tp0));
     for (;;) {
-        // ---- (a) vertex -> target candidates, and the bound U = max_t best[t]
-        double myMax = 0;
-        for (int t = lane; t < K; t += 32) {
-            double best = w.tbest()[t];
-            if (w.tFace[t] != 0) {
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    unsigned short cv = w.tCorner[4 * t + k];
-                    double dv = w.D()[cv];
-                    if (dv < best) {
-                        d3 e{w.tpx()[t] - w.vx()[cv], w.tpy()[t] - w.vy()[cv], w.tpz()[t] - w.vz()[cv]};
-                        double L = sqrt(e.x * e.x + e.y * e.y + e.z * e.z);
-                        if (dv + L < best) {
-                            best = dv + L;
-                            w.tbest()[t] = best;
-                            w.tsx()[t] = w.dirx()[cv], w.tsy()[t] = w.diry()[cv], w.tsz()[t] = w.dirz()[cv];
-                            w.tex()[t] = e.x / L, w.tey()[t] = e.y / L, w.tez()[t] = e.z / L;
+        // ================= windows first: drain the ring =================
+        while (head != tail) {
+            long long tb0 = clock64();
+            // ---- bound U = max_t best[t] (window candidates so far)
+            {
+                double myMax = 0;
+                for (int t = lane; t < K; t += 32) myMax = fmax(myMax, w.tbest()[t]);
+                U = warpMax(myMax);
+            }
+            const double Ub = U * (1 + 1e-12);
+            int nb = min(32, tail - head);
+            bool active = lane < nb;
+            int p = (head + lane) & maskR;
+            head += nb;
+            v2 A{0, 0}, B{1, 0}, S{0, -1};
+            double t0 = 0, t1 = 1, sg = 0;
+            int meta = 0;
+            unsigned short psv = NONE16;
+            if (active) {
+                A = v2{w.rax()[p], w.ray()[p]}, B = v2{w.rbx()[p], w.rby()[p]}, S = v2{w.rsx()[p], w.rsy()[p]};
+                t0 = w.rt0()[p], t1 = w.rt1()[p], sg = w.rsg()[p], meta = w.rmeta[p], psv = w.rpsv[p];
+            }
+            __syncwarp(); // all reads of the ring slots done before anybody pushes
+            int g = meta & 0xFFFF, e = (meta >> 16) & 3;
+            v2 AB = B - A;
+            v2 P0 = lerp2(A, B, t0), P1 = lerp2(A, B, t1);
+            if (active && sg + asegDist(S, P0, P1) * (1 - 1e-5) > Ub) active = false; // bound may have tightened since the push
+            if (active) nWin++;
+            int iA = e == 2 ? 0 : e + 1, iB = e == 0 ? 2 : e - 1, iC = e;
+            unsigned short vA = 0, vB = 0, vC = 0;
+            v2 C{0, 1};
+            int kkbits = 0;
+            if (active) {
+                vA = w.fvert[4 * g + iA], vB = w.fvert[4 * g + iB], vC = w.fvert[4 * g + iC];
+                kkbits = w.fvert[4 * g + 3];
+                double PAx = w.vx()[vA], PAy = w.vy()[vA], PAz = w.vz()[vA];
+                double abx = w.vx()[vB] - PAx, aby = w.vy()[vB] - PAy, abz = w.vz()[vB] - PAz;
+                double acx = w.vx()[vC] - PAx, acy = w.vy()[vC] - PAy, acz = w.vz()[vC] - PAz;
+                double r = frcp(abx * abx + aby * aby + abz * abz);
+                double crx = aby * acz - abz * acy, cry = abz * acx - abx * acz, crz = abx * acy - aby * acx;
+                double cxn = (acx * abx + acy * aby + acz * abz) * r;
+                double cyn = fsqrt(crx * crx + cry * cry + crz * crz) * r;
+                C = v2{A.x + cxn * AB.x - cyn * AB.y, A.y + cxn * AB.y + cyn * AB.x};
+            }
+            // ---- queries: targets inside the entered face
+            for (int t = 0; t < K; ++t) {
+                bool has = active && w.tFace[t] == g;
+                if (!__any_sync(FULL, has)) continue;
+                double cand = dinf();
+                v2 dT{0, 0};
+                if (has) {
+                    double bA = iA == 0 ? w.tb0()[t] : (iA == 1 ? w.tb1()[t] : w.tb2()[t]);
+                    double bB = iB == 0 ? w.tb0()[t] : (iB == 1 ? w.tb1()[t] : w.tb2()[t]);
+                    double bC = iC == 0 ? w.tb0()[t] : (iC == 1 ? w.tb1()[t] : w.tb2()[t]);
+                    double bs = bA + bB + bC;
+                    v2 T{(bA * A.x + bB * B.x + bC * C.x) / bs, (bA * A.y + bB * B.y + bC * C.y) / bs};
+                    dT = T - S;
+                    double den = cross2(AB, dT);
+                    if (den != 0) {
+                        double mu = cross2(S - A, dT) / den;
+                        if (mu >= t0 - 1e-12 && mu <= t1 + 1e-12) cand = sg + len2(dT);
+                    }
+                }
+                double mn = warpMin(cand);
+                if (mn < w.tbest()[t]) {
+                    unsigned bal = __ballot_sync(FULL, cand == mn);
+                    if (lane == __ffs(bal) - 1) {
+                        w.tbest()[t] = cand;
+                        if (psv == NONE16) liftRoot(dT, w.tsx()[t], w.tsy()[t], w.tsz()[t]);
+                        else w.tsx()[t] = w.dirx()[psv], w.tsy()[t] = w.diry()[psv], w.tsz()[t] = w.dirz()[psv];
+                        if (a.nbrTe) { // end tangent: dT in the face's (u, u_perp) frame, lifted with the face's 3-D frame
+                            double PAx = w.vx()[vA], PAy = w.vy()[vA], PAz = w.vz()[vA];
+                            double abx = w.vx()[vB] - PAx, aby = w.vy()[vB] - PAy, abz = w.vz()[vB] - PAz;
+                            double acx = w.vx()[vC] - PAx, acy = w.vy()[vC] - PAy, acz = w.vz()[vC] - PAz;
+                            double L3 = sqrt(abx * abx + aby * aby + abz * abz);
+                            double U3x = abx / L3, U3y = aby / L3, U3z = abz / L3;
+                            double cx = acx * U3x + acy * U3y + acz * U3z;
+                            double wx = acx - cx * U3x, wy = acy - cx * U3y, wz = acz - cx * U3z;
+                            double cy = sqrt(wx * wx + wy * wy + wz * wz);
+                            double L2d = len2(AB);
+                            double ux = AB.x / L2d, uy = AB.y / L2d;
+                            double du = dT.x * ux + dT.y * uy, dw = (-dT.x * uy + dT.y * ux) / cy;
+                            double rx = du * U3x + dw * wx, ry = du * U3y + dw * wy, rz = du * U3z + dw * wz;
+                            double L = sqrt(rx * rx + ry * ry + rz * rz);
+                            w.tex()[t] = rx / L, w.tey()[t] = ry / L, w.tez()[t] = rz / L;
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            // ---- children
+            Child c0, c1;
+            c0.valid = c1.valid = 0;
+            bool improved = false;
+            double dC = 0;
+            if (active) {
+                v2 dL = P0 - S, dR = P1 - S, dCv = C - S;
+                double sideL = cross2(dL, dCv), sideR = cross2(dR, dCv);
+                double lc2 = dCv.x * dCv.x + dCv.y * dCv.y;
+                float lcf = sqrtf((float)lc2);
+                double epsL = 1e-12 * (double)(alen2(dL) * lcf), epsR = 1e-12 * (double)(alen2(dR) * lcf);
+                bool inside = !(sideL > epsL) && !(sideR < -epsR);
+                double DA = w.D()[vA], DB = w.D()[vB], DC = w.D()[vC];
+                if (inside) {
+                    dC = sg + fsqrt(lc2);
+                    if (dC < DC) {
+                        improved = atomicMinD(&w.D()[vC], dC);
+                        DC = fmin(DC, dC);
+                    }
+                }
+                // Xin-Wang filter and bound test in float with a conservative margin: a window is dropped only
+                // when it is dominated by clearly more than the rounding of the approximation
+                const float keep = 1.f - 2e-5f;
+                float fsg = (float)sg, fDA = (float)DA, fDB = (float)DB, fDC = (float)DC;
+                float fUb = Ub < 1e30 ? (float)Ub * (1.f + 2e-5f) : 3e38f;
+                if (!(sideL > epsL)) { // edge C->A of this face (opposite corner B), seen from the neighbour as A->C
+                    unsigned short g2 = w.fadj[4 * g + iB];
+                    if (g2 != NONE16) {
+                        double m0 = hitParam(S, P0, A, C);
+                        double m1 = inside ? 1.0 : hitParam(S, P1, A, C);
+                        if (m1 - m0 > 1e-13) {
+                            v2 XA = lerp2(A, C, m0), XC = lerp2(A, C, m1);
+                            float sXA = fsg + adist2(S, XA), sXC = fsg + adist2(S, XC);
+                            bool dom = (fDA + adist2(A, XC) < sXC * keep) || (fDC + adist2(C, XA) < sXA * keep) || (fDB + adist2(B, XA) < sXA * keep);
+                            if (!dom && fsg + asegDist(S, XA, XC) <= fUb) {
+                                c0.valid = 1;
+                                c0.meta = (int)g2 | (((kkbits >> (2 * iB)) & 3) << 16);
+                                c0.A = A, c0.B = C, c0.t0 = m0, c0.t1 = m1;
+                            }
+                        }
+                    }
+                }
+                if (!(sideR < -epsR)) { // edge B->C of this face (opposite corner A), seen from the neighbour as C->B
+                    unsigned short g2 = w.fadj[4 * g + iA];
+                    if (g2 != NONE16) {
+                        double m0 = inside ? 0.0 : hitParam(S, P0, C, B);
+                        double m1 = hitParam(S, P1, C, B);
+                        if (m1 - m0 > 1e-13) {
+                            v2 XC = lerp2(C, B, m0), XB = lerp2(C, B, m1);
+                            float sXC = fsg + adist2(S, XC), sXB = fsg + adist2(S, XB);
+                            bool dom = (fDB + adist2(B, XC) < sXC * keep) || (fDC + adist2(C, XB) < sXB * keep) || (fDA + adist2(A, XB) < sXB * keep);
+                            if (!dom && fsg + asegDist(S, XC, XB) <= fUb) {
+                                c1.valid = 1;
+                                c1.meta = (int)g2 | (((kkbits >> (2 * iA)) & 3) << 16);
+                                c1.A = C, c1.B = B, c1.t0 = m0, c1.t1 = m1;
+                            }
                         }
                     }
                 }
             }
-            myMax = fmax(myMax, best);
+            __syncwarp();
+            if (improved && dC == w.D()[vC]) { // winner writes the start direction carried to this vertex
+                if (psv == NONE16) liftRoot(C - S, w.dirx()[vC], w.diry()[vC], w.dirz()[vC]);
+                else w.dirx()[vC] = w.dirx()[psv], w.diry()[vC] = w.diry()[psv], w.dirz()[vC] = w.dirz()[psv];
+                w.vdirty[vC] = 1;
+            }
+            int mine = c0.valid + c1.valid;
+            int incl = warpInclusiveScan(mine, lane);
+            int tot = __shfl_sync(FULL, incl, 31);
+            if (tail + tot - head > cp.ring) return ST_OVF_RING;
+            int pos = tail + incl - mine;
+            if (c0.valid) {
+                int q = pos & maskR;
+                w.rax()[q] = c0.A.x, w.ray()[q] = c0.A.y, w.rbx()[q] = c0.B.x, w.rby()[q] = c0.B.y, w.rsx()[q] = S.x, w.rsy()[q] = S.y;
+                w.rt0()[q] = c0.t0, w.rt1()[q] = c0.t1, w.rsg()[q] = sg, w.rmeta[q] = c0.meta, w.rpsv[q] = psv;
+                pos++;
+            }
+            if (c1.valid) {
+                int q = pos & maskR;
+                w.rax()[q] = c1.A.x, w.ray()[q] = c1.A.y, w.rbx()[q] = c1.B.x, w.rby()[q] = c1.B.y, w.rsx()[q] = S.x, w.rsy()[q] = S.y;
+                w.rt0()[q] = c1.t0, w.rt1()[q] = c1.t1, w.rsg()[q] = sg, w.rmeta[q] = c1.meta, w.rpsv[q] = psv;
+            }
+            tail += tot;
+            __syncwarp();
+            clkBatch += clock64() - tb0;
         }
-        U = warpMax(myMax);
+
+        // ================= ring empty: vertex candidates, then pseudo-source fans =================
+        long long tf0 = clock64();
+        // ---- vertex -> target candidates (a path may end with a straight leg from a corner of the target's face)
+        {
+            double myMax = 0;
+            for (int t = lane; t < K; t += 32) {
+                double best = w.tbest()[t];
+                if (w.tFace[t] != 0) {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        unsigned short cv = w.tCorner[4 * t + k];
+                        double dv = w.D()[cv];
+                        if (dv < best) {
+                            d3 ee{w.tpx()[t] - w.vx()[cv], w.tpy()[t] - w.vy()[cv], w.tpz()[t] - w.vz()[cv]};
+                            double L = sqrt(ee.x * ee.x + ee.y * ee.y + ee.z * ee.z);
+                            if (dv + L < best) {
+                                best = dv + L;
+                                w.tbest()[t] = best;
+                                w.tsx()[t] = w.dirx()[cv], w.tsy()[t] = w.diry()[cv], w.tsz()[t] = w.dirz()[cv];
+                                w.tex()[t] = ee.x / L, w.tey()[t] = ee.y / L, w.tez()[t] = ee.z / L;
+                            }
+                        }
+                    }
+                }
+                myMax = fmax(myMax, best);
+            }
+            U = warpMax(myMax);
+        }
         const double Ub = U * (1 + 1e-12);
         __syncwarp();
-
-        // ---- (b) pseudo-source fans for vertices whose distance improved
+        // ---- pseudo-source fans.  A vertex v can lie on a shortest path to target t only if
+        //      D[v] + |x_v - x_t| (Euclidean lower bound of the remaining leg) beats the best path known to t.
         bool spawned = false;
         for (int v0 = 0; v0 < nV; v0 += 32) {
             int v = v0 + lane;
             bool fl = v < nV && w.vdirty[v] && w.velig[v] && w.D()[v] <= Ub;
             if (v < nV) w.vdirty[v] = 0;
+            if (fl) {
+                bool useful = false;
+                double Dv = w.D()[v], px = w.vx()[v], py = w.vy()[v], pz = w.vz()[v];
+                for (int t = 0; t < K && !useful; ++t) {
+                    double ex = w.tpx()[t] - px, ey = w.tpy()[t] - py, ez = w.tpz()[t] - pz;
+                    float lb = sqrtf((float)(ex * ex + ey * ey + ez * ez)) * (1.f - 2e-6f);
+                    useful = Dv + (double)lb < w.tbest()[t];
+                }
+                fl = useful;
+            }
             unsigned bal = __ballot_sync(FULL, fl);
             while (bal) {
                 int b = __ffs(bal) - 1;
@@ -595,26 +824,25 @@ __device__ int processSource(const GeoArgs& a, const WS& w, int li, int lane)
                         else if (c1 == pv) i = 1;
                         else if (c2 == pv) i = 2;
                         if (i >= 0) {
-                            unsigned short cc[3] = {c0, c1, c2};
-                            unsigned short vp = cc[(i + 1) % 3], vq = cc[(i + 2) % 3];
+                            unsigned short vp = i == 0 ? c1 : (i == 1 ? c2 : c0), vq = i == 0 ? c2 : (i == 1 ? c0 : c1);
                             d3 ep{w.vx()[vp] - Pv.x, w.vy()[vp] - Pv.y, w.vz()[vp] - Pv.z}, eq{w.vx()[vq] - Pv.x, w.vy()[vq] - Pv.y, w.vz()[vq] - Pv.z};
-                            double lp = sqrt(ep.x * ep.x + ep.y * ep.y + ep.z * ep.z), lq = sqrt(eq.x * eq.x + eq.y * eq.y + eq.z * eq.z);
+                            double lp = fsqrt(ep.x * ep.x + ep.y * ep.y + ep.z * ep.z), lq = fsqrt(eq.x * eq.x + eq.y * eq.y + eq.z * eq.z);
                             // edge paths
                             if (atomicMinD(&w.D()[vp], Dv + lp)) w.vdirty[vp] = 2;
                             if (atomicMinD(&w.D()[vq], Dv + lq)) w.vdirty[vq] = 2;
                             unsigned short g2 = w.fadj[4 * f + i];
                             if (g2 != NONE16) {
-                                double qx = (eq.x * ep.x + eq.y * ep.y + eq.z * ep.z) / lp;
+                                double rlp = frcp(lp);
+                                double qx = (eq.x * ep.x + eq.y * ep.y + eq.z * ep.z) * rlp;
                                 d3 cr{ep.y * eq.z - ep.z * eq.y, ep.z * eq.x - ep.x * eq.z, ep.x * eq.y - ep.y * eq.x};
-                                double qy = sqrt(cr.x * cr.x + cr.y * cr.y + cr.z * cr.z) / lp;
+                                double qy = fsqrt(cr.x * cr.x + cr.y * cr.y + cr.z * cr.z) * rlp;
                                 int kk = (w.fvert[4 * f + 3] >> (2 * i)) & 3;
                                 ch.valid = 1;
                                 ch.meta = (int)g2 | (kk << 16);
                                 ch.A = v2{qx, qy};
                                 ch.B = v2{lp, 0};
                                 ch.t0 = 0, ch.t1 = 1;
-                                // bound: nearest point of the opposite edge
-                                if (Dv + segDist(v2{0, 0}, ch.A, ch.B) > Ub) ch.valid = 0;
+                                if (Dv + asegDist(v2{0, 0}, ch.A, ch.B) * (1 - 1e-5) > Ub) ch.valid = 0;
                             }
                         }
                     }
@@ -650,173 +878,20 @@ __device__ int processSource(const GeoArgs& a, const WS& w, int li, int lane)
                 }
             }
         }
-        if (overflow) return ST_OVERFLOW;
-        if (spawned) continue; // edge-path improvements may have lowered target bounds / dirtied more vertices
-        if (head == tail) break;
-
-        // ---- (c) one batch of up to 32 windows
-        int nb = min(32, tail - head);
-        bool active = lane < nb;
-        int p = (head + lane) & maskR;
-        head += nb;
-        v2 A{0, 0}, B{1, 0}, S{0, -1};
-        double t0 = 0, t1 = 1, sg = 0;
-        int meta = 0;
-        unsigned short psv = NONE16;
-        if (active) {
-            A = v2{w.rax()[p], w.ray()[p]}, B = v2{w.rbx()[p], w.rby()[p]}, S = v2{w.rsx()[p], w.rsy()[p]};
-            t0 = w.rt0()[p], t1 = w.rt1()[p], sg = w.rsg()[p], meta = w.rmeta[p], psv = w.rpsv[p];
-        }
-        __syncwarp(); // all reads of the ring slots done before anybody pushes
-        int g = meta & 0xFFFF, e = (meta >> 16) & 3;
-        v2 AB = B - A;
-        v2 P0 = lerp2(A, B, t0), P1 = lerp2(A, B, t1);
-        if (active && sg + segDist(S, P0, P1) > Ub) active = false; // bound may have tightened since the push
-        if (active) nWin++;
-        int iA = (e + 1) % 3, iB = (e + 2) % 3, iC = e;
-        unsigned short vA = 0, vB = 0, vC = 0;
-        v2 C{0, 1};
-        double PAx = 0, PAy = 0, PAz = 0, U3x = 0, U3y = 0, U3z = 0, W3x = 0, W3y = 0, W3z = 0; // 3-D frame of the face
-        int kkbits = 0;
-        if (active) {
-            vA = w.fvert[4 * g + iA], vB = w.fvert[4 * g + iB], vC = w.fvert[4 * g + iC];
-            kkbits = w.fvert[4 * g + 3];
-            PAx = w.vx()[vA], PAy = w.vy()[vA], PAz = w.vz()[vA];
-            double abx = w.vx()[vB] - PAx, aby = w.vy()[vB] - PAy, abz = w.vz()[vB] - PAz;
-            double acx = w.vx()[vC] - PAx, acy = w.vy()[vC] - PAy, acz = w.vz()[vC] - PAz;
-            double L3 = sqrt(abx * abx + aby * aby + abz * abz);
-            U3x = abx / L3, U3y = aby / L3, U3z = abz / L3;
-            double cx = acx * U3x + acy * U3y + acz * U3z;
-            double wx = acx - cx * U3x, wy = acy - cx * U3y, wz = acz - cx * U3z;
-            double cy = sqrt(wx * wx + wy * wy + wz * wz);
-            W3x = wx / cy, W3y = wy / cy, W3z = wz / cy;
-            double L2d = len2(AB);
-            double ux = AB.x / L2d, uy = AB.y / L2d;
-            C = v2{A.x + cx * ux - cy * uy, A.y + cx * uy + cy * ux};
-        }
-        // ---- queries: targets inside the entered face
-        for (int t = 0; t < K; ++t) {
-            bool has = active && w.tFace[t] == g;
-            if (!__any_sync(FULL, has)) continue;
-            double cand = dinf();
-            v2 dT{0, 0};
-            if (has) {
-                double b[3] = {w.tb0()[t], w.tb1()[t], w.tb2()[t]};
-                double bs = b[0] + b[1] + b[2];
-                v2 T{(b[iA] * A.x + b[iB] * B.x + b[iC] * C.x) / bs, (b[iA] * A.y + b[iB] * B.y + b[iC] * C.y) / bs};
-                dT = T - S;
-                double den = cross2(AB, dT);
-                if (den != 0) {
-                    double mu = cross2(S - A, dT) / den;
-                    if (mu >= t0 - 1e-12 && mu <= t1 + 1e-12) cand = sg + len2(dT);
-                }
-            }
-            double mn = warpMin(cand);
-            if (mn < w.tbest()[t]) {
-                unsigned bal = __ballot_sync(FULL, cand == mn);
-                if (lane == __ffs(bal) - 1) {
-                    w.tbest()[t] = cand;
-                    if (psv == NONE16) liftRoot(dT, w.tsx()[t], w.tsy()[t], w.tsz()[t]);
-                    else w.tsx()[t] = w.dirx()[psv], w.tsy()[t] = w.diry()[psv], w.tsz()[t] = w.dirz()[psv];
-                    // end tangent: dT expressed in the face's (u, u_perp) frame, lifted with (U3, W3)
-                    double L2d = len2(AB);
-                    double ux = AB.x / L2d, uy = AB.y / L2d;
-                    double du = dT.x * ux + dT.y * uy, dw = -dT.x * uy + dT.y * ux;
-                    double rx = du * U3x + dw * W3x, ry = du * U3y + dw * W3y, rz = du * U3z + dw * W3z;
-                    double L = sqrt(rx * rx + ry * ry + rz * rz);
-                    w.tex()[t] = rx / L, w.tey()[t] = ry / L, w.tez()[t] = rz / L;
-                }
-            }
-            __syncwarp();
-        }
-        // ---- children
-        Child c0, c1;
-        c0.valid = c1.valid = 0;
-        bool improved = false;
-        double dC = 0;
-        if (active) {
-            v2 dL = P0 - S, dR = P1 - S, dCv = C - S;
-            double sideL = cross2(dL, dCv), sideR = cross2(dR, dCv);
-            double lc = len2(dCv);
-            double epsL = 1e-12 * len2(dL) * lc, epsR = 1e-12 * len2(dR) * lc;
-            bool inside = !(sideL > epsL) && !(sideR < -epsR);
-            double DA = w.D()[vA], DB = w.D()[vB], DC = w.D()[vC];
-            if (inside) {
-                dC = sg + lc;
-                if (dC < DC) {
-                    improved = atomicMinD(&w.D()[vC], dC);
-                    DC = fmin(DC, dC);
-                }
-            }
-            const double keep = 1 - 1e-12;
-            if (!(sideL > epsL)) { // edge C->A of this face (opposite corner B), seen from the neighbour as A->C
-                unsigned short g2 = w.fadj[4 * g + iB];
-                if (g2 != NONE16) {
-                    double m0 = hitParam(S, P0, A, C);
-                    double m1 = inside ? 1.0 : hitParam(S, P1, A, C);
-                    if (m1 - m0 > 1e-13) {
-                        v2 XA = lerp2(A, C, m0), XC = lerp2(A, C, m1);
-                        double sXA = sg + dist2(S, XA), sXC = sg + dist2(S, XC);
-                        bool dom = (DA + dist2(A, XC) < sXC * keep) || (DC + dist2(C, XA) < sXA * keep) || (DB + dist2(B, XA) < sXA * keep);
-                        if (!dom && sg + segDist(S, XA, XC) <= Ub) {
-                            c0.valid = 1;
-                            c0.meta = (int)g2 | (((kkbits >> (2 * iB)) & 3) << 16);
-                            c0.A = A, c0.B = C, c0.t0 = m0, c0.t1 = m1;
-                        }
-                    }
-                }
-            }
-            if (!(sideR < -epsR)) { // edge B->C of this face (opposite corner A), seen from the neighbour as C->B
-                unsigned short g2 = w.fadj[4 * g + iA];
-                if (g2 != NONE16) {
-                    double m0 = inside ? 0.0 : hitParam(S, P0, C, B);
-                    double m1 = hitParam(S, P1, C, B);
-                    if (m1 - m0 > 1e-13) {
-                        v2 XC = lerp2(C, B, m0), XB = lerp2(C, B, m1);
-                        double sXC = sg + dist2(S, XC), sXB = sg + dist2(S, XB);
-                        bool dom = (DB + dist2(B, XC) < sXC * keep) || (DC + dist2(C, XB) < sXB * keep) || (DA + dist2(A, XB) < sXB * keep);
-                        if (!dom && sg + segDist(S, XC, XB) <= Ub) {
-                            c1.valid = 1;
-                            c1.meta = (int)g2 | (((kkbits >> (2 * iA)) & 3) << 16);
-                            c1.A = C, c1.B = B, c1.t0 = m0, c1.t1 = m1;
-                        }
-                    }
-                }
-            }
-        }
-        __syncwarp();
-        if (improved && dC == w.D()[vC]) { // winner writes the start direction carried to this vertex
-            if (psv == NONE16) liftRoot(C - S, w.dirx()[vC], w.diry()[vC], w.dirz()[vC]);
-            else w.dirx()[vC] = w.dirx()[psv], w.diry()[vC] = w.diry()[psv], w.dirz()[vC] = w.dirz()[psv];
-            w.vdirty[vC] = 1;
-        }
-        int mine = c0.valid + c1.valid;
-        int incl = warpInclusiveScan(mine, lane);
-        int tot = __shfl_sync(FULL, incl, 31);
-        if (tail + tot - head > cp.ring) return ST_OVERFLOW;
-        int pos = tail + incl - mine;
-        if (c0.valid) {
-            int q = pos & maskR;
-            w.rax()[q] = c0.A.x, w.ray()[q] = c0.A.y, w.rbx()[q] = c0.B.x, w.rby()[q] = c0.B.y, w.rsx()[q] = S.x, w.rsy()[q] = S.y;
-            w.rt0()[q] = c0.t0, w.rt1()[q] = c0.t1, w.rsg()[q] = sg, w.rmeta[q] = c0.meta, w.rpsv[q] = psv;
-            pos++;
-        }
-        if (c1.valid) {
-            int q = pos & maskR;
-            w.rax()[q] = c1.A.x, w.ray()[q] = c1.A.y, w.rbx()[q] = c1.B.x, w.rby()[q] = c1.B.y, w.rsx()[q] = S.x, w.rsy()[q] = S.y;
-            w.rt0()[q] = c1.t0, w.rt1()[q] = c1.t1, w.rsg()[q] = sg, w.rmeta[q] = c1.meta, w.rpsv[q] = psv;
-        }
-        tail += tot;
-        __syncwarp();
+        clkFan += clock64() - tf0;
+        if (overflow) return ST_OVF_RING;
+        if (!spawned) break;
     }
     if (lane == 0) {
-        cnt[C_WINDOWS] += nWin;
         cnt[C_PSEUDO] += nPs;
+        atomicAdd(a.counters + C_CLK_BATCH, (unsigned long long)clkBatch);
+        atomicAdd(a.counters + C_CLK_FAN, (unsigned long long)clkFan);
+        atomicAdd(a.counters + C_CLK_PROP, (unsigned long long)(clock64() - tk0));
     }
     {
-        unsigned long long w0 = nWin; // lanes other than 0 also counted windows
+        unsigned long long w0 = nWin;
         for (int o = 16; o; o >>= 1) w0 += __shfl_xor_sync(FULL, w0, o);
-        if (lane == 0) cnt[C_WINDOWS] += w0 - nWin;
+        if (lane == 0) cnt[C_WINDOWS] += w0;
     }
 
     // ---------------- 6. results ----------------
@@ -885,10 +960,13 @@ __global__ void __launch_bounds__(128, 3) k_geodesic(GeoArgs a, size_t wsBytes)
         s = __shfl_sync(FULL, s, 0);
         if (s >= nSrc) break;
         int li = a.srcList ? a.srcList[s] : s;
+        long long tc0 = clock64();
         int st = processSource<GLOBAL_WS>(a, w, li, lane);
+        if (lane == 0) atomicAdd(a.counters + C_CLK_TOTAL, (unsigned long long)(clock64() - tc0));
         st = __shfl_sync(FULL, st, 0);
         __syncwarp();
         if (st != ST_OK && lane == 0) {
+            atomicAdd(a.counters + C_OVF_REASON + st - 1, 1ull);
             if (a.lastTier) {
                 cnt[C_OVERFLOW]++;
                 if (a.xK < 0) a.nbrCount[li] = 0;
@@ -905,8 +983,9 @@ __global__ void __launch_bounds__(128, 3) k_geodesic(GeoArgs a, size_t wsBytes)
 
 int geodesicMaxSmemPerBlock() { return 227 * 1024; }
 
-void launchGeodesic(cudaStream_t st, const GeoArgs& a, int warpsPerBlock, int blocks)
+cudaError_t launchGeodesic(cudaStream_t st, const GeoArgs& a, int warpsPerBlock, int blocks)
 {
+    if (warpsPerBlock * 32 > 128) return cudaErrorInvalidConfiguration; // __launch_bounds__(128, 3)
     size_t wsBytes = geoWorkspaceBytes(a.caps);
     if (a.gws) {
         k_geodesic<true><<<blocks, warpsPerBlock * 32, 0, st>>>(a, wsBytes);
@@ -915,6 +994,7 @@ void launchGeodesic(cudaStream_t st, const GeoArgs& a, int warpsPerBlock, int bl
         cudaFuncSetAttribute(k_geodesic<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)geodesicMaxSmemPerBlock());
         k_geodesic<false><<<blocks, warpsPerBlock * 32, smem, st>>>(a, wsBytes);
     }
+    return cudaGetLastError();
 }
 
 } // namespace css

@@ -55,7 +55,7 @@ struct GeoArgs {
     int lastTier;
 };
 
-void launchGeodesic(cudaStream_t st, const GeoArgs& a, int warpsPerBlock, int blocks);
+cudaError_t launchGeodesic(cudaStream_t st, const GeoArgs& a, int warpsPerBlock, int blocks);
 int geodesicMaxSmemPerBlock();
 
 void launchEuclidCell(cudaStream_t st, const MeshDev& m, const CellGrid& g, int n, const int* face, const double* bary, double* eucl,

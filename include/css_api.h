@@ -80,7 +80,10 @@ enum css_counter {
     CSS_C_TIER_RETRY = 14,   /* sources re-run on a larger-capacity tier */
     CSS_C_OVERFLOW = 15,     /* sources that overflowed every tier (results invalid) */
     CSS_C_KERNELS = 16,      /* kernels launched by this context (host-side count) */
-    CSS_NUM_COUNTERS = 24
+    CSS_C_KMAX_OVERFLOW = 17, /* neighbour stride too small (handled by regrowing and rerunning) */
+    CSS_C_OVF_CANDIDATES = 18, CSS_C_OVF_FACES = 19, CSS_C_OVF_VERTS = 20, CSS_C_OVF_RING = 21, /* tier overflow reasons */
+    CSS_C_CLK_BATCH = 22, CSS_C_CLK_FAN = 23, CSS_C_CLK_PROP = 24, CSS_C_CLK_PATCH = 25, CSS_C_CLK_TOTAL = 26, /* per-warp cycles */
+    CSS_NUM_COUNTERS = 32
 };
 
 int css_create(css_ctx** ctx, int device);
