@@ -39,6 +39,23 @@ API_SYMBOLS = [
 _lib = None
 
 
+def _preload_nccl():
+    """The library links libnccl.so.2.  In a Python process that also imports torch, the NCCL that gets
+    mapped first wins for both (same soname), and torch needs its own bundled, newer build; so map that
+    one first when it exists.  A C++ host simply uses the system libnccl."""
+    import importlib.util
+
+    try:
+        spec = importlib.util.find_spec("nvidia.nccl")
+    except (ImportError, ValueError):
+        spec = None
+    for loc in (spec.submodule_search_locations if spec and spec.submodule_search_locations else []):
+        p = os.path.join(loc, "lib", "libnccl.so.2")
+        if os.path.exists(p):
+            C.CDLL(p, mode=C.RTLD_GLOBAL)
+            return
+
+
 def load_library():
     """Load the CUDA library.  Raises if it has not been built (python -m curvedspacesim_b200.build)."""
     global _lib
@@ -46,6 +63,7 @@ def load_library():
         if not os.path.exists(LIB_PATH):
             raise RuntimeError("libcurvedspacesim_b200.so is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                                "(there is no CPU fallback)")
+        _preload_nccl()
         L = C.CDLL(LIB_PATH)
         L.css_last_error.restype = C.c_char_p
         L.css_last_error.argtypes = [C.c_void_p]

@@ -1,0 +1,57 @@
+"""Worker of tests/test_gpu_parity.py::test_two_gpus_bitwise_equal_to_one.  Launched either directly
+(world 1) or under torch.distributed.run (world 2..8): every rank owns a block of particles
+(mpiModel::determineIndexBounds), the mesh is replicated, positions are all-gathered over NCCL after
+every move (css_gather_positions).  Dumps the final state per rank."""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from curvedspacesim_b200 import binding, meshes, sharding  # noqa: E402
+from helpers import interaction_range, make_state  # noqa: E402
+
+
+def main(out_dir):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    V, F = meshes.torus(200, 60, R=3.0, r=1.0, jitter=0.2, seed=13377)
+    N = 5001
+    corners, face, bary, vel = make_state(V, F, N)
+    area = float(meshes.face_areas(V, F).sum())
+    rc = interaction_range(area, N)
+    kind, params = binding.force_params("harmonic", k=1.0, sigma=rc)
+    lo, hi = sharding.index_bounds(N, rank, world)
+    ctx = binding.Context(local)
+    ctx.set_mesh(V, corners)
+    ctx.set_submeshing(True, rc)
+    if world > 1:
+        uid = [binding.Context.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init(rank, world, uid[0])
+    ctx.set_state(face, bary, vel[lo:hi], None, n_local=hi - lo, min_idx=lo)
+    ctx.compute_forces(kind, params)
+    ctx.step_nve(kind, params, 0.01, 25)
+    ke = ctx.reduce(binding.SUM, [0.5 * float((ctx.get_state()[2] ** 2).sum())])
+    f, b, v, fr = ctx.get_state()
+    np.savez(os.path.join(out_dir, "world%d_rank%d.npz" % (world, rank)), face=f, bary=b, vel=v, frc=fr, lo=lo, hi=hi, ke=ke)
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main(sys.argv[1])
