@@ -953,7 +953,7 @@ __global__ void __launch_bounds__(128, 3) k_geodesic(GeoArgs a, size_t wsBytes)
     if (lane < 16) cnt[lane] = 0;
     __syncwarp();
 
-    const int nSrc = a.xK >= 0 ? 1 : (a.srcList ? *a.srcCount : a.nLocal);
+    const int nSrc = a.srcList ? *a.srcCount : (a.xK >= 0 ? 1 : a.nLocal);
     for (;;) {
         int s = 0;
         if (lane == 0) s = atomicAdd(a.workCounter, 1);
