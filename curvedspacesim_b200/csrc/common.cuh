@@ -16,6 +16,10 @@ struct MeshDev {
     const int4* corner;
     const int4* adj;
     const unsigned char* saddle; // per-vertex: interior angle sum >= 2 pi  (pseudo-source candidate)
+    // edge frames: for face f and edge e (opposite corner e, running A = corner e+1 -> B = corner e+2) the apex
+    // C = corner e in the frame of that edge, normalised by |AB|:  C = A + cxn (B-A) + cyn perp(B-A).
+    // geo[3 f + e] = {cxn, cyn}; lets a window be unfolded across a face with four FMAs and no 3-D geometry.
+    const double2* geo;
 };
 
 struct CellGrid {

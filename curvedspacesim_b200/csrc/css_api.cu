@@ -27,6 +27,7 @@ struct css_ctx {
     int4* d_corner = nullptr;
     int4* d_adj = nullptr;
     unsigned char* d_saddle = nullptr;
+    double2* d_geo = nullptr; // edge frames, [3 nF]
     double bbmin[3] = {0, 0, 0}, bbmax[3] = {0, 0, 0}, area = 0;
     double cellMin[3] = {0, 0, 0}, cellMax[3] = {0, 0, 0};
     bool submeshing = false;
@@ -58,6 +59,11 @@ struct css_ctx {
     GeoCaps capsT0{96, 64, 64, 16, 256, 256}, capsT1{768, 448, 1024, 128, 2048, 1024}, capsT2{0, 0, 0, 0, 0, 0};
     int t2Warps = 32;
     int wpb0 = 4, wpb1 = 1;
+    // two-stage tier 0: patch records (stage 1) -> window propagation (stage 2)
+    bool twoStage = true;
+    int winWpb = 2;
+    unsigned char* d_records = nullptr;
+    size_t capRecords = 0;
     int numSMs = 148;
     // reductions / scratch
     double *d_partial = nullptr, *d_red = nullptr;
@@ -156,6 +162,8 @@ int css_create(css_ctx** out, int device)
         if (n >= 10) ctx->capsT1 = GeoCaps{v[5], v[6], p2(v[7]), v[8], p2(2 * v[5] + 64), p2(2 * v[6] + 128)}, ctx->wpb1 = v[9];
     }
     for (auto& e : ctx->tev) cudaEventCreate(&e);
+    if (const char* v = getenv("CSS_LEGACY_TIER0")) ctx->twoStage = atoi(v) == 0; // developer switch: fused one-kernel tier 0
+    if (const char* v = getenv("CSS_WIN_WPB")) ctx->winWpb = std::max(1, std::min(4, atoi(v)));
     *out = ctx;
     return CSS_OK;
 }
@@ -171,7 +179,7 @@ int css_destroy(css_ctx* ctx)
                     ctx->d_blockSums, ctx->d_fill,   ctx->d_tmpItems, ctx->d_items,  ctx->d_nbrCount, ctx->d_nbrIdx,  ctx->d_nbrDist,
                     ctx->d_nbrTs,  ctx->d_nbrTe,     ctx->d_work,    ctx->d_retry[0], ctx->d_retry[1], ctx->d_retry[2], ctx->d_gws,
                     ctx->d_partial, ctx->d_red,      ctx->d_counters, ctx->d_sendI,  ctx->d_sendD,    ctx->d_recvI,   ctx->d_recvD,
-                    ctx->d_redBuf};
+                    ctx->d_redBuf,  ctx->d_geo,       ctx->d_records};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (auto& e : ctx->ev)
@@ -242,6 +250,19 @@ int css_set_mesh(css_ctx* ctx, int nV, const double* xyz, int nF, const int32_t*
         }
     }
     ctx->area = area;
+    // edge frames (common.cuh MeshDev::geo): apex of each face in the frame of each of its edges
+    std::vector<double2> hg(3 * (size_t)nF);
+    for (int f = 0; f < nF; ++f)
+        for (int e = 0; e < 3; ++e) {
+            const double* A = xyz + 3 * corners[3 * f + (e + 1) % 3];
+            const double* B = xyz + 3 * corners[3 * f + (e + 2) % 3];
+            const double* C = xyz + 3 * corners[3 * f + e];
+            double ab[3] = {B[0] - A[0], B[1] - A[1], B[2] - A[2]}, ac[3] = {C[0] - A[0], C[1] - A[1], C[2] - A[2]};
+            double cr[3] = {ab[1] * ac[2] - ab[2] * ac[1], ab[2] * ac[0] - ab[0] * ac[2], ab[0] * ac[1] - ab[1] * ac[0]};
+            double l2 = ab[0] * ab[0] + ab[1] * ab[1] + ab[2] * ab[2];
+            hg[3 * (size_t)f + e] = make_double2((ac[0] * ab[0] + ac[1] * ab[1] + ac[2] * ab[2]) / l2,
+                                                 std::sqrt(cr[0] * cr[0] + cr[1] * cr[1] + cr[2] * cr[2]) / l2);
+        }
     std::vector<unsigned char> sad(nV);
     for (int i = 0; i < nV; ++i) sad[i] = ang[i] >= 2.0 * M_PI - 1e-9;
     for (int d = 0; d < 3; ++d) ctx->cellMin[d] = ctx->bbmin[d], ctx->cellMax[d] = ctx->bbmax[d];
@@ -250,6 +271,8 @@ int css_set_mesh(css_ctx* ctx, int nV, const double* xyz, int nF, const int32_t*
     CU(regrow(ctx->d_corner, nF));
     CU(regrow(ctx->d_adj, nF));
     CU(regrow(ctx->d_saddle, nV));
+    CU(regrow(ctx->d_geo, 3 * (size_t)nF));
+    CU(cudaMemcpy(ctx->d_geo, hg.data(), sizeof(double2) * 3 * (size_t)nF, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(ctx->d_vert, hv.data(), sizeof(double4) * nV, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(ctx->d_corner, hc.data(), sizeof(int4) * nF, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(ctx->d_adj, ha.data(), sizeof(int4) * nF, cudaMemcpyHostToDevice));
@@ -303,7 +326,7 @@ int css_set_options(css_ctx* ctx, int useCellList, int wantEndTangents)
     return CSS_OK;
 }
 
-static MeshDev meshDev(css_ctx* c) { return MeshDev{c->nV, c->nF, c->d_vert, c->d_corner, c->d_adj, c->d_saddle}; }
+static MeshDev meshDev(css_ctx* c) { return MeshDev{c->nV, c->nF, c->d_vert, c->d_corner, c->d_adj, c->d_saddle, c->d_geo}; }
 
 // ------------------------------------------------------------------------------- per-call parity
 int css_euclidean(css_ctx* ctx, int n, const int32_t* face, const double* bary, double* xyz)
@@ -374,8 +397,34 @@ static int runGeodesicTiers(css_ctx* ctx, GeoArgs a, int nSrc)
     int rc = ensureTierBuffers(ctx, std::max(nSrc, 1));
     if (rc) return rc;
     CU(cudaMemsetAsync(ctx->d_work, 0, 16 * sizeof(int), ctx->st)); // [0..2] work counters, [4..6] retry counts
-    // tier 0: shared memory, several warps per block
-    {
+    const bool staged = ctx->twoStage && a.xK < 0 && a.cellStart != nullptr;
+    if (staged) {
+        // tier 0, two stages: patch records (integer / latency-bound, high occupancy), then window propagation (fp64)
+        size_t need = (size_t)std::max(nSrc, 1) * REC_BYTES;
+        if (need > ctx->capRecords) {
+            CU(cudaStreamSynchronize(ctx->st));
+            CU(regrow(ctx->d_records, need));
+            ctx->capRecords = need;
+        }
+        PatchArgs p{};
+        p.m = a.m, p.grid = a.grid, p.nLocal = a.nLocal, p.minIdx = a.minIdx;
+        p.face = a.face, p.eucl = a.eucl, p.cellStart = a.cellStart, p.cellItems = a.cellItems;
+        p.submeshing = a.submeshing, p.maxDist = a.maxDist, p.kmax = a.kmax;
+        p.workCounter = ctx->d_work + 0, p.retryList = ctx->d_retry[0], p.retryCount = ctx->d_work + 4;
+        p.counters = ctx->d_counters, p.records = ctx->d_records;
+        CU(launchPatch(ctx->st, p, ctx->numSMs));
+        WinArgs w{};
+        w.m = a.m, w.nLocal = a.nLocal, w.minIdx = a.minIdx;
+        w.face = a.face, w.bary = a.bary, w.eucl = a.eucl, w.records = ctx->d_records;
+        w.submeshing = a.submeshing, w.maxDist = a.maxDist, w.kmax = a.kmax;
+        w.nbrCount = a.nbrCount, w.nbrIdx = a.nbrIdx, w.nbrDist = a.nbrDist, w.nbrTs = a.nbrTs, w.nbrTe = a.nbrTe;
+        w.forceMode = a.forceMode, w.fp = a.fp, w.zero = a.zero, w.frc = a.frc, w.kick = a.kick, w.vel = a.vel;
+        w.workCounter = ctx->d_work + 3, w.retryList = ctx->d_retry[0], w.retryCount = ctx->d_work + 4;
+        w.counters = ctx->d_counters;
+        CU(launchWindows(ctx->st, w, ctx->winWpb, ctx->numSMs));
+        ctx->hostKernels += 2;
+    } else {
+        // tier 0, fused: shared memory, several warps per block
         a.caps = ctx->capsT0;
         a.srcList = nullptr, a.srcCount = nullptr;
         a.workCounter = ctx->d_work + 0;

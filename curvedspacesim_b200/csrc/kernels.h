@@ -56,6 +56,80 @@ struct GeoArgs {
 };
 
 cudaError_t launchGeodesic(cudaStream_t st, const GeoArgs& a, int warpsPerBlock, int blocks);
+
+// ---- two-stage tier-0 path: patch records (patch_kernel.cu) -> window propagation (window_kernel.cu) ----
+// Fixed-capacity patch record, one per local source particle, REC_BYTES apart (all offsets 16-byte aligned):
+//   int   hdr[4]            nF, nV, K, status (1 = overflow: handled by the retry tiers, stage 2 skips it)
+//   int   tIdx[REC_MAXK]    ordered candidate particle indices (the neighbour list)
+//   u8    tFace[REC_MAXK]   local face of each target
+//   u8    velig[REC_MAXV]   vertex may act as a pseudo-source (saddle of the mesh or on the patch border)
+//   int   gface[REC_MAXF]   local face -> global face
+//   int   gvert[REC_MAXV]   local vertex -> global vertex
+//   uchar4 fvert[REC_MAXF]  local corner ids + kk bits (index of each edge inside the neighbour, 2 bits per edge)
+//   uchar4 fadj[REC_MAXF]   local face across the edge opposite corner k (REC_NONE = patch border)
+#define REC_MAXF 96
+#define REC_MAXV 64
+#define REC_MAXK 16
+#define REC_NONE 255
+#define REC_OFF_TIDX 16
+#define REC_OFF_TFACE (REC_OFF_TIDX + 4 * REC_MAXK)
+#define REC_OFF_VELIG (REC_OFF_TFACE + REC_MAXK)
+#define REC_OFF_GFACE (REC_OFF_VELIG + REC_MAXV)
+#define REC_OFF_GVERT (REC_OFF_GFACE + 4 * REC_MAXF)
+#define REC_OFF_FVERT (REC_OFF_GVERT + 4 * REC_MAXV)
+#define REC_OFF_FADJ (REC_OFF_FVERT + 4 * REC_MAXF)
+#define REC_BYTES (REC_OFF_FADJ + 4 * REC_MAXF)
+#define PATCH_THREADS 256
+#define WIN_RING 64
+
+struct PatchArgs {
+    MeshDev m;
+    CellGrid grid;
+    int nLocal, minIdx;
+    const int* face;      // [nTotal]
+    const double* eucl;   // [3 nTotal]
+    const int* cellStart;
+    const int* cellItems;
+    int submeshing;
+    double maxDist;
+    int kmax;
+    int* workCounter;
+    int* retryList;
+    int* retryCount;
+    unsigned long long* counters;
+    unsigned char* records; // [nLocal][REC_BYTES]
+};
+cudaError_t launchPatch(cudaStream_t st, const PatchArgs& a, int numSMs);
+size_t patchSmemPerWarp();
+
+struct WinArgs {
+    MeshDev m;
+    int nLocal, minIdx;
+    const int* face;
+    const double* bary;
+    const double* eucl;
+    const unsigned char* records;
+    int submeshing;
+    double maxDist;
+    int kmax;
+    int* nbrCount;
+    int* nbrIdx;
+    double* nbrDist;
+    double* nbrTs;
+    double* nbrTe; // nullable
+    int forceMode;
+    ForceParams fp;
+    int zero;
+    double* frc;
+    double kick;
+    double* vel;
+    int* workCounter;
+    int* retryList;
+    int* retryCount;
+    unsigned long long* counters;
+};
+cudaError_t launchWindows(cudaStream_t st, const WinArgs& a, int warpsPerBlock, int numSMs);
+size_t windowSmemPerWarp();
 int geodesicMaxSmemPerBlock();
 
 void launchEuclidCell(cudaStream_t st, const MeshDev& m, const CellGrid& g, int n, const int* face, const double* bary, double* eucl,

@@ -1,0 +1,676 @@
+// Stage 2 of the many-source geodesic path: exact window propagation on the patch records written by
+// patch_kernel.cu, ONE WARP PER SOURCE, the patch staged in shared memory.
+//
+// Replaces CGAL::Surface_mesh_shortest_path as the reference uses it per source
+// (src/models/triangulatedMeshSpace.cpp:189-203: add_source_point, build_sequence_tree, then
+// shortest_path_points_to_source_points per target, src/utility/meshUtilities.cpp:360-380) and fuses the
+// consumer of its results, force::computeForces (src/forces/baseForce.cpp:12-28) with the second
+// velocity-Verlet half kick (src/updaters/velocityVerletNVE.cpp:27-28).
+//
+// Algorithm: Chen-Han window unfolding with the Xin-Wang vertex-distance filter; saddle and patch-border
+// vertices are pseudo-sources.  Windows live in a FIFO ring in shared memory and are propagated 32 at a
+// time, one per lane; children are compacted into the ring with a ballot-free shuffle scan.  A window is
+// (A, B, S, t0, t1, sigma): the entered edge A->B and the image S of its (pseudo-)source in one common
+// unfolded 2-D frame, the visible interval [t0, t1] of the edge, and the distance sigma from the true source
+// to the pseudo-source.  Unfolding across a face is four FMAs with the precomputed edge frames
+// (MeshDev::geo), so the propagation loop touches no 3-D geometry.  Start directions are carried as 2-D
+// vectors in the source face's frame and lifted to 3-D once per target at the end; end tangents likewise.
+//
+// Everything here is ordinary fp64 with FMA contraction: results agree with the oracle to ~1e-15, far
+// inside the 1e-9 bar.  Pruning decisions are taken in fp32 with conservative margins.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace css {
+
+#define FULL 0xffffffffu
+
+namespace {
+
+constexpr int RING = WIN_RING;
+constexpr int MASKR = RING - 1;
+constexpr unsigned char NOPSV = 255;
+
+__device__ __forceinline__ double dinf() { return __longlong_as_double(0x7ff0000000000000LL); }
+
+struct WinSmem { // per-warp workspace (15.6 KB)
+    double2 geo[3 * REC_MAXF];
+    double vx[REC_MAXV], vy[REC_MAXV], vz[REC_MAXV], D[REC_MAXV], dirx[REC_MAXV], diry[REC_MAXV];
+    double rax[RING], ray[RING], rbx[RING], rby[RING], rsx[RING], rsy[RING], rt0[RING], rt1[RING], rsg[RING];
+    double tbest[REC_MAXK], tb0[REC_MAXK], tb1[REC_MAXK], tb2[REC_MAXK], tsx[REC_MAXK], tsy[REC_MAXK], tdu[REC_MAXK], tdw[REC_MAXK];
+    double tpx[REC_MAXK], tpy[REC_MAXK], tpz[REC_MAXK], tcd0[REC_MAXK], tcd1[REC_MAXK], tcd2[REC_MAXK];
+    double root[6];
+    int rmeta[RING];
+    int tIdx[REC_MAXK];
+    int tcode[REC_MAXK];  // how the best path ends: 0 none, 1 chord in the source face, 2 + 4*(g | e << 8) window, 3 + 4*k corner k
+    int towner[REC_MAXK];
+    alignas(16) uchar4 fvert[REC_MAXF];
+    uchar4 fadj[REC_MAXF];
+    unsigned short tmask[REC_MAXF]; // targets lying in each face (bit t)
+    alignas(16) unsigned char tFace[REC_MAXK];
+    unsigned char velig[REC_MAXV];
+    unsigned char vdirty[REC_MAXV];
+    unsigned char rpsv[RING];
+    int misc[4];
+    unsigned long long wcnt[16];
+};
+
+struct v2 {
+    double x, y;
+};
+__device__ __forceinline__ v2 operator-(const v2& a, const v2& b) { return v2{a.x - b.x, a.y - b.y}; }
+__device__ __forceinline__ v2 lerp2(const v2& a, const v2& b, double t) { return v2{fma(t, b.x - a.x, a.x), fma(t, b.y - a.y, a.y)}; }
+__device__ __forceinline__ double cross2(const v2& a, const v2& b) { return a.x * b.y - a.y * b.x; }
+
+__device__ __forceinline__ double warpMax(double v)
+{
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+__device__ __forceinline__ bool atomicMinD(double* addr, double v)
+{ // non-negative doubles order like their bit patterns
+    unsigned long long nv = (unsigned long long)__double_as_longlong(v);
+    unsigned long long old = atomicMin(reinterpret_cast<unsigned long long*>(addr), nv);
+    return nv < old;
+}
+
+// ~1 ulp reciprocal / square root (hardware seed + Newton); window geometry only
+__device__ __forceinline__ double frcp(double x)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(r, fma(-x, r, 1.0), r);
+    r = fma(r, fma(-x, r, 1.0), r);
+    return r;
+}
+__device__ __forceinline__ double fsqrt(double x)
+{
+    if (!(x > 0)) return 0.0;
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double hx = 0.5 * x;
+    y = y * fma(-hx * y, y, 1.5);
+    y = y * fma(-hx * y, y, 1.5);
+    double s = x * y;
+    return fma(fma(-s, s, x), 0.5 * y, s);
+}
+__device__ __forceinline__ double hitParam(const v2& S, const v2& P, const v2& X, const v2& Y)
+{ // ray S->P against X + mu (Y - X), clamped to the segment
+    v2 d = P - S;
+    double den = cross2(Y - X, d);
+    double mu = cross2(S - X, d) * frcp(den);
+    if (!(mu == mu)) mu = 0.5;
+    return fmin(1.0, fmax(0.0, mu));
+}
+// fp32 lengths for pruning decisions (always used with a conservative margin)
+__device__ __forceinline__ float flen(float x, float y) { return sqrtf(fmaf(x, x, y * y)); }
+__device__ __forceinline__ float fdist(const v2& a, const v2& b) { return flen((float)(a.x - b.x), (float)(a.y - b.y)); }
+__device__ __forceinline__ float fsegDist(const v2& S, const v2& X0, const v2& X1)
+{
+    float ex = (float)(X1.x - X0.x), ey = (float)(X1.y - X0.y), sx = (float)(S.x - X0.x), sy = (float)(S.y - X0.y);
+    float L2 = fmaf(ex, ex, ey * ey);
+    float s = L2 > 0.f ? __fdividef(fmaf(sx, ex, sy * ey), L2) : 0.f;
+    s = fminf(1.f, fmaxf(0.f, s));
+    return flen(fmaf(-s, ex, sx), fmaf(-s, ey, sy));
+}
+
+__device__ __forceinline__ d3 pairForce(const ForceParams& fp, const d3& sep, double d)
+{
+    if (fp.kind == 0) { // harmonicRepulsion.cpp:19-33
+        if (d <= fp.sigma) {
+            double s = -fp.a * (fp.sigma - d);
+            return d3{s * sep.x, s * sep.y, s * sep.z};
+        }
+        return d3{0, 0, 0};
+    }
+    const double sqrtTwoPi = 2.50662827463100050241576528481104525300698674061; // gaussianRepulsion.h:16-24
+    double twoSigmaSquared = 2.0 * fp.sigma * fp.sigma;
+    double s32 = (sqrtTwoPi * fp.sigma) * sqrt(fp.sigma);
+    double pre = d * fp.a * exp(-d * d / twoSigmaSquared) / s32;
+    return d3{-pre * sep.x, -pre * sep.y, -pre * sep.z};
+}
+
+// push up to one window per lane; returns false when the ring would overflow
+__device__ __forceinline__ bool pushWindows(WinSmem& w, int lane, int head, int& tail, bool valid, const v2& A, const v2& B, const v2& S,
+                                            double t0, double t1, double sg, int meta, unsigned char psv)
+{
+    unsigned bal = __ballot_sync(FULL, valid);
+    int tot = __popc(bal);
+    if (tail + tot - head > RING) return false;
+    if (valid) {
+        int q = (tail + __popc(bal & ((1u << lane) - 1))) & MASKR;
+        w.rax[q] = A.x, w.ray[q] = A.y, w.rbx[q] = B.x, w.rby[q] = B.y, w.rsx[q] = S.x, w.rsy[q] = S.y;
+        w.rt0[q] = t0, w.rt1[q] = t1, w.rsg[q] = sg, w.rmeta[q] = meta, w.rpsv[q] = psv;
+    }
+    tail += tot;
+    return true;
+}
+
+// pseudo-source fan of vertex pv (rare: kept out of line to keep the propagation loop compact)
+__device__ __noinline__ bool spawnFan(WinSmem& w, int lane, int nF, int pv, double Ub, int head, int& tail)
+{
+    const double Dv = w.D[pv];
+    const d3 Pv{w.vx[pv], w.vy[pv], w.vz[pv]};
+    const double dvx = w.dirx[pv], dvy = w.diry[pv];
+    bool ok = true;
+    for (int f0 = 0; f0 < nF; f0 += 32) {
+        int f = f0 + lane;
+        bool valid = false;
+        v2 A{0, 0}, B{0, 0};
+        int meta = 0;
+        if (f < nF) {
+            uchar4 fv = w.fvert[f];
+            int i = fv.x == pv ? 0 : (fv.y == pv ? 1 : (fv.z == pv ? 2 : -1));
+            if (i >= 0) {
+                int vp = i == 0 ? fv.y : (i == 1 ? fv.z : fv.x), vq = i == 0 ? fv.z : (i == 1 ? fv.x : fv.y);
+                d3 ep{w.vx[vp] - Pv.x, w.vy[vp] - Pv.y, w.vz[vp] - Pv.z}, eq{w.vx[vq] - Pv.x, w.vy[vq] - Pv.y, w.vz[vq] - Pv.z};
+                double lp = fsqrt(ep.x * ep.x + ep.y * ep.y + ep.z * ep.z), lq = fsqrt(eq.x * eq.x + eq.y * eq.y + eq.z * eq.z);
+                if (atomicMinD(&w.D[vp], Dv + lp)) w.vdirty[vp] = 2; // edge paths
+                if (atomicMinD(&w.D[vq], Dv + lq)) w.vdirty[vq] = 2;
+                uchar4 fa = w.fadj[f];
+                int g2 = i == 0 ? fa.x : (i == 1 ? fa.y : fa.z);
+                if (g2 != REC_NONE) {
+                    double rlp = frcp(lp);
+                    double qx = (eq.x * ep.x + eq.y * ep.y + eq.z * ep.z) * rlp;
+                    d3 cr{ep.y * eq.z - ep.z * eq.y, ep.z * eq.x - ep.x * eq.z, ep.x * eq.y - ep.y * eq.x};
+                    double qy = fsqrt(cr.x * cr.x + cr.y * cr.y + cr.z * cr.z) * rlp;
+                    int kk = (fv.w >> (2 * i)) & 3;
+                    meta = g2 | (kk << 16);
+                    A = v2{qx, qy};
+                    B = v2{lp, 0};
+                    valid = !(Dv + (double)fsegDist(v2{0, 0}, A, B) * (1 - 1e-5) > Ub);
+                }
+            }
+        }
+        __syncwarp();
+        if (f < nF) { // vertices improved along an edge inherit the pseudo-source's start direction
+            uchar4 fv = w.fvert[f];
+            if (w.vdirty[fv.x] == 2) w.dirx[fv.x] = dvx, w.diry[fv.x] = dvy;
+            if (w.vdirty[fv.y] == 2) w.dirx[fv.y] = dvx, w.diry[fv.y] = dvy;
+            if (w.vdirty[fv.z] == 2) w.dirx[fv.z] = dvx, w.diry[fv.z] = dvy;
+        }
+        __syncwarp();
+        if (f < nF) {
+            uchar4 fv = w.fvert[f];
+            if (w.vdirty[fv.x] == 2) w.vdirty[fv.x] = 1;
+            if (w.vdirty[fv.y] == 2) w.vdirty[fv.y] = 1;
+            if (w.vdirty[fv.z] == 2) w.vdirty[fv.z] = 1;
+        }
+        if (ok) ok = pushWindows(w, lane, head, tail, valid, A, B, v2{0, 0}, 0.0, 1.0, Dv, meta, (unsigned char)pv);
+        __syncwarp();
+    }
+    return ok;
+}
+
+// 3-D unit end tangent of a path that enters face g through edge e with direction (du, dw) in that edge's frame
+__device__ __noinline__ d3 liftEnd(const WinSmem& w, int g, int e, double du, double dw)
+{
+    uchar4 fv = w.fvert[g];
+    int c0 = fv.x, c1 = fv.y, c2 = fv.z;
+    int vA = e == 0 ? c1 : (e == 1 ? c2 : c0), vB = e == 0 ? c2 : (e == 1 ? c0 : c1), vC = e == 0 ? c0 : (e == 1 ? c1 : c2);
+    double PAx = w.vx[vA], PAy = w.vy[vA], PAz = w.vz[vA];
+    double abx = w.vx[vB] - PAx, aby = w.vy[vB] - PAy, abz = w.vz[vB] - PAz;
+    double acx = w.vx[vC] - PAx, acy = w.vy[vC] - PAy, acz = w.vz[vC] - PAz;
+    double L3 = sqrt(abx * abx + aby * aby + abz * abz);
+    double Ux = abx / L3, Uy = aby / L3, Uz = abz / L3;
+    double cx = acx * Ux + acy * Uy + acz * Uz;
+    double wx = acx - cx * Ux, wy = acy - cx * Uy, wz = acz - cx * Uz;
+    double cy = sqrt(wx * wx + wy * wy + wz * wz);
+    double dwn = dw / cy;
+    double rx = du * Ux + dwn * wx, ry = du * Uy + dwn * wy, rz = du * Uz + dwn * wz;
+    double L = sqrt(rx * rx + ry * ry + rz * rz);
+    return d3{rx / L, ry / L, rz / L};
+}
+
+enum { WS_OK = 0, WS_RING = 1 };
+
+__device__ int processRecord(const WinArgs& a, WinSmem& w, int li, int lane)
+{
+    unsigned long long* cnt = w.wcnt;
+    const int gi = a.minIdx + li;
+    const unsigned char* rec = a.records + (size_t)li * REC_BYTES;
+    const int4 hdr = *reinterpret_cast<const int4*>(rec);
+    const int nF = hdr.x, nV = hdr.y, K = hdr.z;
+    if (hdr.w) return WS_OK; // overflowed in stage 1: the retry tiers own this source
+    if (K == 0) {
+        if (lane == 0) {
+            cnt[C_SOURCES]++;
+            a.nbrCount[li] = 0;
+            if (a.forceMode) {
+                d3 f = a.zero ? d3{0, 0, 0} : d3{a.frc[3 * li], a.frc[3 * li + 1], a.frc[3 * li + 2]};
+                a.frc[3 * li] = f.x, a.frc[3 * li + 1] = f.y, a.frc[3 * li + 2] = f.z;
+                if (a.kick != 0.0) a.vel[3 * li] += a.kick * f.x, a.vel[3 * li + 1] += a.kick * f.y, a.vel[3 * li + 2] += a.kick * f.z;
+            }
+        }
+        return WS_OK;
+    }
+
+    // ---------------- stage the patch ----------------
+    {
+        const int4* src = reinterpret_cast<const int4*>(rec + REC_OFF_FVERT); // fvert | fadj are contiguous in both layouts
+        int4* dst = reinterpret_cast<int4*>(w.fvert);
+        for (int q = lane; q < (2 * 4 * REC_MAXF) / 16; q += 32)
+            if (q * 4 < nF || (q >= REC_MAXF / 4 && (q - REC_MAXF / 4) * 4 < nF)) dst[q] = src[q];
+        const int* gface = reinterpret_cast<const int*>(rec + REC_OFF_GFACE);
+        for (int q = lane; q < 3 * nF; q += 32) {
+            int f = q / 3, e = q - 3 * f;
+            w.geo[q] = __ldg(a.m.geo + 3 * (size_t)gface[f] + e);
+        }
+        for (int f = lane; f < nF; f += 32) w.tmask[f] = 0;
+        const int* gvert = reinterpret_cast<const int*>(rec + REC_OFF_GVERT);
+        for (int v = lane; v < nV; v += 32) {
+            d3 p = ldvert(a.m, gvert[v]);
+            w.vx[v] = p.x, w.vy[v] = p.y, w.vz[v] = p.z;
+            w.D[v] = dinf();
+            w.velig[v] = rec[REC_OFF_VELIG + v];
+            w.vdirty[v] = 0;
+        }
+        if (lane < K) {
+            int j = reinterpret_cast<const int*>(rec + REC_OFF_TIDX)[lane];
+            w.tIdx[lane] = j;
+            w.tFace[lane] = rec[REC_OFF_TFACE + lane];
+            w.tb0[lane] = a.bary[3 * j], w.tb1[lane] = a.bary[3 * j + 1], w.tb2[lane] = a.bary[3 * j + 2];
+            w.tpx[lane] = a.eucl[3 * j], w.tpy[lane] = a.eucl[3 * j + 1], w.tpz[lane] = a.eucl[3 * j + 2];
+            w.tbest[lane] = dinf();
+            w.tcode[lane] = 0;
+            w.tsx[lane] = 0, w.tsy[lane] = 0;
+            w.towner[lane] = 32;
+        }
+    }
+    const d3 sp{a.eucl[3 * gi], a.eucl[3 * gi + 1], a.eucl[3 * gi + 2]};
+    const double sb0 = a.bary[3 * gi], sb1 = a.bary[3 * gi + 1], sb2 = a.bary[3 * gi + 2];
+    __syncwarp();
+
+    // ---------------- root frame, direct legs ----------------
+    // source face = local face 0: corner 0 at the origin, corner 1 on +x, corner 2 above
+    v2 rq1, rq2, S2;
+    {
+        uchar4 fv = w.fvert[0];
+        d3 P0{w.vx[fv.x], w.vy[fv.x], w.vz[fv.x]}, P1{w.vx[fv.y], w.vy[fv.y], w.vz[fv.y]}, P2{w.vx[fv.z], w.vy[fv.z], w.vz[fv.z]};
+        d3 e01{P1.x - P0.x, P1.y - P0.y, P1.z - P0.z}, e02{P2.x - P0.x, P2.y - P0.y, P2.z - P0.z};
+        double L01 = sqrt(e01.x * e01.x + e01.y * e01.y + e01.z * e01.z);
+        double rL = 1.0 / L01;
+        d3 ex{e01.x * rL, e01.y * rL, e01.z * rL};
+        double x2 = e02.x * ex.x + e02.y * ex.y + e02.z * ex.z;
+        d3 ey{e02.x - x2 * ex.x, e02.y - x2 * ex.y, e02.z - x2 * ex.z};
+        double y2 = sqrt(ey.x * ey.x + ey.y * ey.y + ey.z * ey.z);
+        double ry = 1.0 / y2;
+        ey = d3{ey.x * ry, ey.y * ry, ey.z * ry};
+        rq1 = v2{L01, 0};
+        rq2 = v2{x2, y2};
+        double rbs = 1.0 / (sb0 + sb1 + sb2);
+        S2 = v2{(sb1 * rq1.x + sb2 * rq2.x) * rbs, (sb2 * rq2.y) * rbs};
+        if (lane == 0) w.root[0] = ex.x, w.root[1] = ex.y, w.root[2] = ex.z, w.root[3] = ey.x, w.root[4] = ey.y, w.root[5] = ey.z;
+        if (lane < 3) { // straight legs to the three corners of the source face
+            int cv = lane == 0 ? fv.x : (lane == 1 ? fv.y : fv.z);
+            v2 q = lane == 0 ? v2{0, 0} : (lane == 1 ? rq1 : rq2);
+            d3 P = lane == 0 ? P0 : (lane == 1 ? P1 : P2);
+            d3 d{P.x - sp.x, P.y - sp.y, P.z - sp.z};
+            w.D[cv] = sqrt(d.x * d.x + d.y * d.y + d.z * d.z);
+            w.dirx[cv] = q.x - S2.x, w.diry[cv] = q.y - S2.y;
+            w.vdirty[cv] = 1;
+        }
+        if (lane < K) {
+            int t = lane, lf = w.tFace[t];
+            if (lf == 0) { // target in the source face: the chord
+                d3 d{w.tpx[t] - sp.x, w.tpy[t] - sp.y, w.tpz[t] - sp.z};
+                w.tbest[t] = sqrt(d.x * d.x + d.y * d.y + d.z * d.z);
+                w.tcode[t] = 1;
+            } else {
+                atomicOr(reinterpret_cast<unsigned int*>(w.tmask) + (lf >> 1), (1u << t) << ((lf & 1) * 16));
+                uchar4 tv = w.fvert[lf];
+                double px = w.tpx[t], py = w.tpy[t], pz = w.tpz[t];
+                double ax = px - w.vx[tv.x], ay = py - w.vy[tv.x], az = pz - w.vz[tv.x];
+                double bx = px - w.vx[tv.y], by = py - w.vy[tv.y], bz = pz - w.vz[tv.y];
+                double cx = px - w.vx[tv.z], cy = py - w.vy[tv.z], cz = pz - w.vz[tv.z];
+                w.tcd0[t] = sqrt(ax * ax + ay * ay + az * az);
+                w.tcd1[t] = sqrt(bx * bx + by * by + bz * bz);
+                w.tcd2[t] = sqrt(cx * cx + cy * cy + cz * cz);
+            }
+        }
+    }
+    int head = 0, tail = 0;
+    {
+        bool valid = false;
+        v2 A{0, 0}, B{0, 0};
+        int meta = 0;
+        if (lane < 3) {
+            uchar4 fa = w.fadj[0];
+            int g = lane == 0 ? fa.x : (lane == 1 ? fa.y : fa.z);
+            if (g != REC_NONE) {
+                int kk = (w.fvert[0].w >> (2 * lane)) & 3;
+                valid = true;
+                meta = g | (kk << 16);
+                // edge k runs corner k+1 -> corner k+2; the neighbour sees it reversed
+                A = lane == 0 ? rq2 : (lane == 1 ? v2{0, 0} : rq1);
+                B = lane == 0 ? rq1 : (lane == 1 ? rq2 : v2{0, 0});
+            }
+        }
+        pushWindows(w, lane, head, tail, valid, A, B, S2, 0.0, 1.0, 0.0, meta, NOPSV);
+    }
+    __syncwarp();
+
+    unsigned long long nWin = 0, nPs = 0;
+    for (;;) {
+        // ================= drain the ring, 32 windows per pass =================
+        while (head != tail) {
+            double U = warpMax(lane < K ? w.tbest[lane] : 0.0);
+            const double Ub = U * (1 + 1e-12);
+            const float fUb = Ub < 1e30 ? (float)Ub * (1.f + 2e-5f) : 3e38f;
+            int nb = min(32, tail - head);
+            bool active = lane < nb;
+            int p = (head + lane) & MASKR;
+            head += nb;
+            v2 A{0, 0}, B{1, 0}, S{0, -1};
+            double t0 = 0, t1 = 1, sg = 0;
+            int meta = 0;
+            unsigned char psv = NOPSV;
+            if (active) {
+                A = v2{w.rax[p], w.ray[p]}, B = v2{w.rbx[p], w.rby[p]}, S = v2{w.rsx[p], w.rsy[p]};
+                t0 = w.rt0[p], t1 = w.rt1[p], sg = w.rsg[p], meta = w.rmeta[p], psv = w.rpsv[p];
+            }
+            __syncwarp(); // every slot of this pass is read before anybody pushes
+            const int g = meta & 0xFF, e = (meta >> 16) & 3;
+            const v2 AB = B - A;
+            const v2 P0 = lerp2(A, B, t0), P1 = lerp2(A, B, t1);
+            if (active && (float)sg + fsegDist(S, P0, P1) * (1.f - 1e-5f) > fUb) active = false; // bound tightened since the push
+            // ---- unfold the entered face: apex C from the edge frame
+            int vA = 0, vB = 0, vC = 0, kkbits = 0;
+            uchar4 fa = make_uchar4(REC_NONE, REC_NONE, REC_NONE, 0);
+            v2 C{0, 1};
+            unsigned tm = 0;
+            if (active) {
+                nWin++;
+                uchar4 fv = w.fvert[g];
+                fa = w.fadj[g];
+                kkbits = fv.w;
+                vA = e == 0 ? fv.y : (e == 1 ? fv.z : fv.x);
+                vB = e == 0 ? fv.z : (e == 1 ? fv.x : fv.y);
+                vC = e == 0 ? fv.x : (e == 1 ? fv.y : fv.z);
+                double2 cg = w.geo[3 * g + e];
+                C = v2{fma(cg.x, AB.x, fma(-cg.y, AB.y, A.x)), fma(cg.x, AB.y, fma(cg.y, AB.x, A.y))};
+                tm = w.tmask[g];
+            }
+            // ---- queries: targets inside the entered face (rare: ~K/nF of the windows enter a face that holds a target)
+            while (__any_sync(FULL, tm != 0)) {
+                bool improvedT = false;
+                int myT = 0;
+                double cand = 0;
+                v2 dT{0, 0};
+                if (tm) {
+                    int t = __ffs(tm) - 1;
+                    tm &= tm - 1;
+                    double b0 = w.tb0[t], b1 = w.tb1[t], b2 = w.tb2[t];
+                    double bA = e == 0 ? b1 : (e == 1 ? b2 : b0), bB = e == 0 ? b2 : (e == 1 ? b0 : b1), bC = e == 0 ? b0 : (e == 1 ? b1 : b2);
+                    double rbs = 1.0 / (bA + bB + bC);
+                    v2 T{(bA * A.x + bB * B.x + bC * C.x) * rbs, (bA * A.y + bB * B.y + bC * C.y) * rbs};
+                    v2 d = T - S;
+                    double den = cross2(AB, d);
+                    if (den != 0) {
+                        double mu = cross2(S - A, d) / den;
+                        if (mu >= t0 - 1e-12 && mu <= t1 + 1e-12) {
+                            double c = sg + sqrt(d.x * d.x + d.y * d.y);
+                            if (atomicMinD(&w.tbest[t], c)) improvedT = true, myT = t, cand = c, dT = d;
+                        }
+                    }
+                }
+                if (__any_sync(FULL, improvedT)) { // the winner (lowest lane among equal candidates) records how its path starts and ends
+                    __syncwarp();
+                    bool win = improvedT && w.tbest[myT] == cand;
+                    if (win) atomicMin(&w.towner[myT], lane);
+                    __syncwarp();
+                    if (win && w.towner[myT] == lane) {
+                        if (psv == NOPSV) w.tsx[myT] = dT.x, w.tsy[myT] = dT.y;
+                        else w.tsx[myT] = w.dirx[psv], w.tsy[myT] = w.diry[psv];
+                        w.tcode[myT] = 2 + 4 * (g | (e << 8));
+                        double rl = rsqrt(AB.x * AB.x + AB.y * AB.y);
+                        w.tdu[myT] = (dT.x * AB.x + dT.y * AB.y) * rl;
+                        w.tdw[myT] = (-dT.x * AB.y + dT.y * AB.x) * rl;
+                    }
+                    __syncwarp();
+                    if (lane < K) w.towner[lane] = 32;
+                    __syncwarp();
+                }
+            }
+            // ---- children
+            bool v0 = false, v1 = false, improved = false;
+            int m0meta = 0, m1meta = 0;
+            double c0t0 = 0, c0t1 = 0, c1t0 = 0, c1t1 = 0, dC = 0;
+            if (active) {
+                const v2 dL = P0 - S, dR = P1 - S, dCv = C - S;
+                const double sideL = cross2(dL, dCv), sideR = cross2(dR, dCv);
+                const double lc2 = dCv.x * dCv.x + dCv.y * dCv.y;
+                const float lcf = sqrtf((float)lc2);
+                const double epsL = 1e-12 * (double)(flen((float)dL.x, (float)dL.y) * lcf), epsR = 1e-12 * (double)(flen((float)dR.x, (float)dR.y) * lcf);
+                const bool inside = !(sideL > epsL) && !(sideR < -epsR);
+                double DC = w.D[vC];
+                if (inside) {
+                    dC = sg + fsqrt(lc2);
+                    if (dC < DC) {
+                        improved = atomicMinD(&w.D[vC], dC);
+                        DC = fmin(DC, dC);
+                    }
+                }
+                // Xin-Wang filter and bound test in fp32 with a conservative margin: a window is dropped only when it
+                // is dominated by clearly more than the rounding of the approximation
+                const float keep = 1.f - 2e-5f;
+                const float fsg = (float)sg, fDA = (float)w.D[vA], fDB = (float)w.D[vB], fDC = (float)DC;
+                if (!(sideL > epsL)) { // edge C->A (opposite corner B), seen from the neighbour as A->C
+                    int g2 = e == 0 ? fa.z : (e == 1 ? fa.x : fa.y); // fadj[iB]
+                    if (g2 != REC_NONE) {
+                        double m0 = hitParam(S, P0, A, C);
+                        double m1 = inside ? 1.0 : hitParam(S, P1, A, C);
+                        if (m1 - m0 > 1e-13) {
+                            v2 XA = lerp2(A, C, m0), XC = lerp2(A, C, m1);
+                            float sXA = fsg + fdist(S, XA), sXC = fsg + fdist(S, XC);
+                            bool dom = (fDA + fdist(A, XC) < sXC * keep) || (fDC + fdist(C, XA) < sXA * keep) || (fDB + fdist(B, XA) < sXA * keep);
+                            if (!dom && fsg + fsegDist(S, XA, XC) <= fUb) {
+                                int iB = e == 0 ? 2 : e - 1;
+                                v0 = true, m0meta = g2 | (((kkbits >> (2 * iB)) & 3) << 16), c0t0 = m0, c0t1 = m1;
+                            }
+                        }
+                    }
+                }
+                if (!(sideR < -epsR)) { // edge B->C (opposite corner A), seen from the neighbour as C->B
+                    int g2 = e == 0 ? fa.y : (e == 1 ? fa.z : fa.x); // fadj[iA]
+                    if (g2 != REC_NONE) {
+                        double m0 = inside ? 0.0 : hitParam(S, P0, C, B);
+                        double m1 = hitParam(S, P1, C, B);
+                        if (m1 - m0 > 1e-13) {
+                            v2 XC = lerp2(C, B, m0), XB = lerp2(C, B, m1);
+                            float sXC = fsg + fdist(S, XC), sXB = fsg + fdist(S, XB);
+                            bool dom = (fDB + fdist(B, XC) < sXC * keep) || (fDC + fdist(C, XB) < sXB * keep) || (fDA + fdist(A, XB) < sXB * keep);
+                            if (!dom && fsg + fsegDist(S, XC, XB) <= fUb) {
+                                int iA = e == 2 ? 0 : e + 1;
+                                v1 = true, m1meta = g2 | (((kkbits >> (2 * iA)) & 3) << 16), c1t0 = m0, c1t1 = m1;
+                            }
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (improved && dC == w.D[vC]) { // the winner writes the start direction carried to this vertex
+                if (psv == NOPSV) w.dirx[vC] = C.x - S.x, w.diry[vC] = C.y - S.y;
+                else w.dirx[vC] = w.dirx[psv], w.diry[vC] = w.diry[psv];
+                w.vdirty[vC] = 1;
+            }
+            if (!pushWindows(w, lane, head, tail, v0, A, C, S, c0t0, c0t1, sg, m0meta, psv)) return WS_RING;
+            if (!pushWindows(w, lane, head, tail, v1, C, B, S, c1t0, c1t1, sg, m1meta, psv)) return WS_RING;
+            __syncwarp();
+        }
+
+        // ================= ring empty: straight legs from face corners, then pseudo-source fans =================
+        if (lane < K) {
+            int t = lane;
+            double best = w.tbest[t];
+            if (w.tFace[t] != 0) {
+                uchar4 tv = w.fvert[w.tFace[t]];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    int cv = k == 0 ? tv.x : (k == 1 ? tv.y : tv.z);
+                    double c = w.D[cv] + (k == 0 ? w.tcd0[t] : (k == 1 ? w.tcd1[t] : w.tcd2[t]));
+                    if (c < best) {
+                        best = c;
+                        w.tbest[t] = c;
+                        w.tsx[t] = w.dirx[cv], w.tsy[t] = w.diry[cv];
+                        w.tcode[t] = 3 + 4 * k;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        const double U = warpMax(lane < K ? w.tbest[lane] : 0.0);
+        const double Ub = U * (1 + 1e-12);
+        // A vertex v can lie on a shortest path to target t only if D[v] + |x_v - x_t| (Euclidean lower bound of the
+        // remaining leg) beats the best path known to t.
+        bool spawned = false, ok = true;
+        for (int v0i = 0; v0i < nV; v0i += 32) {
+            int v = v0i + lane;
+            bool fl = v < nV && w.vdirty[v] && w.velig[v] && w.D[v] <= Ub;
+            if (v < nV) w.vdirty[v] = 0;
+            if (fl) {
+                bool useful = false;
+                double Dv = w.D[v], px = w.vx[v], py = w.vy[v], pz = w.vz[v];
+                for (int t = 0; t < K && !useful; ++t) {
+                    double ex = w.tpx[t] - px, ey = w.tpy[t] - py, ez = w.tpz[t] - pz;
+                    float lb = sqrtf((float)(ex * ex + ey * ey + ez * ez)) * (1.f - 2e-6f);
+                    useful = Dv + (double)lb < w.tbest[t];
+                }
+                fl = useful;
+            }
+            unsigned bal = __ballot_sync(FULL, fl);
+            while (bal) {
+                int b = __ffs(bal) - 1;
+                bal &= bal - 1;
+                spawned = true;
+                nPs++;
+                ok = spawnFan(w, lane, nF, v0i + b, Ub, head, tail) && ok;
+            }
+        }
+        if (!ok) return WS_RING;
+        if (!spawned) break;
+    }
+
+    // ---------------- results, pair forces ----------------
+    unsigned long long nDis = 0;
+    double dres = 0;
+    d3 ts{0, 0, 1}, te{0, 0, 1};
+    if (lane < K) {
+        int t = lane;
+        dres = w.tbest[t];
+        int code = w.tcode[t];
+        if (code == 0 || !(dres < dinf())) { // unreachable inside the patch (triangulatedMeshSpace.cpp:198-203)
+            nDis = 1;
+            dres = a.submeshing ? 2.0 * a.maxDist : -1.0;
+            if (!a.submeshing) ts = te = d3{0, 0, 0};
+        } else if (code == 1) {
+            double rl = 1.0 / dres;
+            ts = d3{(w.tpx[t] - sp.x) * rl, (w.tpy[t] - sp.y) * rl, (w.tpz[t] - sp.z) * rl};
+            te = ts;
+        } else {
+            double dx = w.tsx[t], dy = w.tsy[t];
+            double rx = dx * w.root[0] + dy * w.root[3], ry = dx * w.root[1] + dy * w.root[4], rz = dx * w.root[2] + dy * w.root[5];
+            double rl = 1.0 / sqrt(rx * rx + ry * ry + rz * rz);
+            ts = d3{rx * rl, ry * rl, rz * rl};
+            if (a.nbrTe) {
+                if ((code & 3) == 2) {
+                    int ge = code >> 2;
+                    te = liftEnd(w, ge & 0xFF, ge >> 8, w.tdu[t], w.tdw[t]);
+                } else {
+                    int k = code >> 2;
+                    uchar4 tv = w.fvert[w.tFace[t]];
+                    int cv = k == 0 ? tv.x : (k == 1 ? tv.y : tv.z);
+                    double ex = w.tpx[t] - w.vx[cv], ey = w.tpy[t] - w.vy[cv], ez = w.tpz[t] - w.vz[cv];
+                    double rl2 = 1.0 / sqrt(ex * ex + ey * ey + ez * ez);
+                    te = d3{ex * rl2, ey * rl2, ez * rl2};
+                }
+            }
+        }
+        size_t o = (size_t)li * a.kmax + t;
+        a.nbrIdx[o] = w.tIdx[t];
+        a.nbrDist[o] = dres;
+        if (a.nbrTs) a.nbrTs[3 * o] = ts.x, a.nbrTs[3 * o + 1] = ts.y, a.nbrTs[3 * o + 2] = ts.z;
+        if (a.nbrTe) a.nbrTe[3 * o] = te.x, a.nbrTe[3 * o + 1] = te.y, a.nbrTe[3 * o + 2] = te.z;
+    }
+    // force::computeForces accumulates in neighbour order jj = 0..K-1 (baseForce.cpp:22-26): lane 0 adds the pair
+    // forces in that order, fetching them from the lanes that computed them
+    d3 pf{0, 0, 0};
+    if (a.forceMode && lane < K) pf = pairForce(a.fp, ts, dres);
+    d3 f{0, 0, 0};
+    if (a.forceMode) {
+        if (lane == 0 && !a.zero) f = d3{a.frc[3 * li], a.frc[3 * li + 1], a.frc[3 * li + 2]};
+        for (int t = 0; t < K; ++t) {
+            double x = __shfl_sync(FULL, pf.x, t), y = __shfl_sync(FULL, pf.y, t), z = __shfl_sync(FULL, pf.z, t);
+            f.x += x, f.y += y, f.z += z;
+        }
+    }
+    for (int o = 16; o; o >>= 1) {
+        nDis += __shfl_xor_sync(FULL, nDis, o);
+        nWin += __shfl_xor_sync(FULL, nWin, o);
+    }
+    if (lane == 0) {
+        cnt[C_DISCONNECTED] += nDis;
+        cnt[C_WINDOWS] += nWin;
+        cnt[C_PSEUDO] += nPs;
+        cnt[C_SOURCES]++;
+        cnt[C_QUERIES] += K;
+        cnt[C_PATCH_FACES] += nF;
+        cnt[C_PATCH_VERTS] += nV;
+        a.nbrCount[li] = K;
+        if (a.forceMode) {
+            a.frc[3 * li] = f.x, a.frc[3 * li + 1] = f.y, a.frc[3 * li + 2] = f.z;
+            if (a.kick != 0.0) a.vel[3 * li] += a.kick * f.x, a.vel[3 * li + 1] += a.kick * f.y, a.vel[3 * li + 2] += a.kick * f.z;
+        }
+    }
+    return WS_OK;
+}
+
+} // namespace
+
+__global__ void __launch_bounds__(128, 4) k_windows(WinArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    WinSmem& w = reinterpret_cast<WinSmem*>(smemRaw)[wib];
+    unsigned long long* cnt = w.wcnt;
+    if (lane < 16) cnt[lane] = 0;
+    __syncwarp();
+    for (;;) {
+        int li = 0;
+        if (lane == 0) li = atomicAdd(a.workCounter, 1);
+        li = __shfl_sync(FULL, li, 0);
+        if (li >= a.nLocal) break;
+        int st = processRecord(a, w, li, lane);
+        st = __shfl_sync(FULL, st, 0);
+        __syncwarp();
+        if (st != WS_OK && lane == 0) { // ring overflow: rerun on the large-capacity tiers
+            int r = atomicAdd(a.retryCount, 1);
+            a.retryList[r] = li;
+            cnt[C_TIER_RETRY]++;
+            atomicAdd(a.counters + C_OVF_REASON + 3, 1ull);
+        }
+    }
+    __syncwarp();
+    if (lane < 16 && cnt[lane]) atomicAdd(a.counters + lane, cnt[lane]);
+}
+
+size_t windowSmemPerWarp() { return sizeof(WinSmem); }
+
+cudaError_t launchWindows(cudaStream_t st, const WinArgs& a, int warpsPerBlock, int numSMs)
+{
+    size_t smem = sizeof(WinSmem) * warpsPerBlock;
+    static int perSM[5] = {0, 0, 0, 0, 0};
+    if (warpsPerBlock < 1 || warpsPerBlock > 4) return cudaErrorInvalidConfiguration;
+    if (!perSM[warpsPerBlock]) {
+        cudaFuncSetAttribute(k_windows, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_windows, warpsPerBlock * 32, smem) != cudaSuccess || n < 1) n = 1;
+        perSM[warpsPerBlock] = n;
+    }
+    int blocks = min(numSMs * perSM[warpsPerBlock], max(1, (a.nLocal + warpsPerBlock - 1) / warpsPerBlock));
+    k_windows<<<blocks, warpsPerBlock * 32, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+} // namespace css

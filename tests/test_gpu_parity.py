@@ -418,10 +418,11 @@ np.savez(sys.argv[1], off=off, idx=idx, d=d, ts=ts, te=te, retry=c["tier_retry"]
     with tempfile.TemporaryDirectory() as td:
         for i, tune in enumerate((None, "8,8,16,4,4,24,20,32,8,1")):
             env = dict(os.environ)
-            if tune:
+            env.pop("CSS_TUNE", None)
+            env.pop("CSS_LEGACY_TIER0", None)
+            if tune:  # fused tier 0 with tiny capacities: (almost) every source overflows into the next tiers
                 env["CSS_TUNE"] = tune
-            else:
-                env.pop("CSS_TUNE", None)
+                env["CSS_LEGACY_TIER0"] = "1"
             out = os.path.join(td, "o%d.npz" % i)
             subprocess.check_call([sys.executable, "-c", code, out], env=env)
             outs.append(dict(np.load(out)))
