@@ -437,32 +437,40 @@ static int runGeodesicTiers(css_ctx* ctx, GeoArgs a, int nSrc)
         CU(launchGeodesic(ctx->st, a, wpb, blocks));
         ctx->hostKernels++;
     }
-    // tier 1: shared memory, one warp per block, large capacities
+    // tiers 1 and 2 run on a global-memory workspace (no dynamic shared memory: an empty retry list costs a few
+    // microseconds and the SM shared-memory carve-out is left alone)
+    auto ensureWorkspace = [&](size_t bytes) -> int {
+        if (bytes > ctx->gwsBytes) {
+            CU(cudaStreamSynchronize(ctx->st));
+            if (ctx->d_gws) cudaFree(ctx->d_gws);
+            ctx->d_gws = nullptr;
+            ctx->gwsBytes = 0;
+            CU(cudaMalloc(&ctx->d_gws, bytes));
+            ctx->gwsBytes = bytes;
+        }
+        return CSS_OK;
+    };
+    // tier 1: large capacities, many warps
     {
         a.caps = ctx->capsT1;
+        size_t ws = geoWorkspaceBytes(a.caps);
+        int wpb = 2, blocks = std::min(ctx->numSMs * 2, std::max(1, nSrc));
+        if (int rc2 = ensureWorkspace(ws * wpb * blocks)) return rc2;
         a.srcList = ctx->d_retry[0], a.srcCount = ctx->d_work + 4;
         a.workCounter = ctx->d_work + 1;
         a.retryList = ctx->d_retry[1], a.retryCount = ctx->d_work + 5;
-        a.gws = nullptr, a.lastTier = 0;
-        size_t ws1 = geoWorkspaceBytes(a.caps);
-        int bps1 = std::max(1, std::min(12 / ctx->wpb1, (int)(geodesicMaxSmemPerBlock() / (ws1 * ctx->wpb1))));
-        CU(launchGeodesic(ctx->st, a, ctx->wpb1, std::min(ctx->numSMs * bps1, std::max(1, nSrc))));
+        a.gws = ctx->d_gws, a.lastTier = 0;
+        CU(launchGeodesic(ctx->st, a, wpb, blocks));
         ctx->hostKernels++;
     }
-    // tier 2: global-memory workspace sized for the whole mesh
+    // tier 2: capacities sized for the whole mesh
     {
         a.caps = ctx->capsT2;
         if (a.xK >= 0) a.caps.kt = std::max(a.caps.kt, a.xK);
         else if (!ctx->useCellList) a.caps.kt = std::max(a.caps.kt, a.nTotal);
         size_t ws = geoWorkspaceBytes(a.caps);
         int warps = ctx->t2Warps;
-        if (ws * warps > ctx->gwsBytes) {
-            CU(cudaStreamSynchronize(ctx->st));
-            if (ctx->d_gws) cudaFree(ctx->d_gws);
-            ctx->d_gws = nullptr;
-            CU(cudaMalloc(&ctx->d_gws, ws * warps));
-            ctx->gwsBytes = ws * warps;
-        }
+        if (int rc2 = ensureWorkspace(ws * warps)) return rc2;
         a.srcList = ctx->d_retry[1], a.srcCount = ctx->d_work + 5;
         a.workCounter = ctx->d_work + 2;
         a.retryList = ctx->d_retry[2], a.retryCount = ctx->d_work + 6;

@@ -62,12 +62,6 @@ __device__ __forceinline__ v2 operator-(const v2& a, const v2& b) { return v2{a.
 __device__ __forceinline__ v2 lerp2(const v2& a, const v2& b, double t) { return v2{fma(t, b.x - a.x, a.x), fma(t, b.y - a.y, a.y)}; }
 __device__ __forceinline__ double cross2(const v2& a, const v2& b) { return a.x * b.y - a.y * b.x; }
 
-__device__ __forceinline__ double warpMax(double v)
-{
-#pragma unroll
-    for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
-    return v;
-}
 __device__ __forceinline__ bool atomicMinD(double* addr, double v)
 { // non-negative doubles order like their bit patterns
     unsigned long long nv = (unsigned long long)__double_as_longlong(v);
@@ -103,16 +97,33 @@ __device__ __forceinline__ double hitParam(const v2& S, const v2& P, const v2& X
     if (!(mu == mu)) mu = 0.5;
     return fmin(1.0, fmax(0.0, mu));
 }
-// fp32 lengths for pruning decisions (always used with a conservative margin)
-__device__ __forceinline__ float flen(float x, float y) { return sqrtf(fmaf(x, x, y * y)); }
-__device__ __forceinline__ float fdist(const v2& a, const v2& b) { return flen((float)(a.x - b.x), (float)(a.y - b.y)); }
-__device__ __forceinline__ float fsegDist(const v2& S, const v2& X0, const v2& X1)
+// fp32 geometry for pruning decisions (always used with a conservative margin; approximate sqrt is plenty)
+struct f2 {
+    float x, y;
+};
+__device__ __forceinline__ f2 tof2(const v2& a) { return f2{(float)a.x, (float)a.y}; }
+__device__ __forceinline__ float asqrt(float x)
 {
-    float ex = (float)(X1.x - X0.x), ey = (float)(X1.y - X0.y), sx = (float)(S.x - X0.x), sy = (float)(S.y - X0.y);
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float flen(float x, float y) { return asqrt(fmaf(x, x, y * y)); }
+__device__ __forceinline__ float fdist(const f2& a, const f2& b) { return flen(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ f2 flerp(const f2& a, const f2& b, float t) { return f2{fmaf(t, b.x - a.x, a.x), fmaf(t, b.y - a.y, a.y)}; }
+__device__ __forceinline__ float fsegDist(const f2& S, const f2& X0, const f2& X1)
+{
+    float ex = X1.x - X0.x, ey = X1.y - X0.y, sx = S.x - X0.x, sy = S.y - X0.y;
     float L2 = fmaf(ex, ex, ey * ey);
     float s = L2 > 0.f ? __fdividef(fmaf(sx, ex, sy * ey), L2) : 0.f;
     s = fminf(1.f, fmaxf(0.f, s));
     return flen(fmaf(-s, ex, sx), fmaf(-s, ey, sy));
+}
+// upper bound U = max_t best[t] in fp32, rounded up (non-negative floats order like their bit patterns; +inf stays +inf)
+__device__ __forceinline__ float warpBound(const WinSmem& w, int lane, int K)
+{
+    unsigned u = lane < K ? __float_as_uint(__double2float_ru(w.tbest[lane])) : 0u;
+    return __uint_as_float(__reduce_max_sync(FULL, u)) * (1.f + 2e-5f);
 }
 
 __device__ __forceinline__ d3 pairForce(const ForceParams& fp, const d3& sep, double d)
@@ -148,7 +159,7 @@ __device__ __forceinline__ bool pushWindows(WinSmem& w, int lane, int head, int&
 }
 
 // pseudo-source fan of vertex pv (rare: kept out of line to keep the propagation loop compact)
-__device__ __noinline__ bool spawnFan(WinSmem& w, int lane, int nF, int pv, double Ub, int head, int& tail)
+__device__ __noinline__ bool spawnFan(WinSmem& w, int lane, int nF, int pv, float fUb, int head, int& tail)
 {
     const double Dv = w.D[pv];
     const d3 Pv{w.vx[pv], w.vy[pv], w.vz[pv]};
@@ -179,7 +190,7 @@ __device__ __noinline__ bool spawnFan(WinSmem& w, int lane, int nF, int pv, doub
                     meta = g2 | (kk << 16);
                     A = v2{qx, qy};
                     B = v2{lp, 0};
-                    valid = !(Dv + (double)fsegDist(v2{0, 0}, A, B) * (1 - 1e-5) > Ub);
+                    valid = !((float)Dv + fsegDist(f2{0.f, 0.f}, tof2(A), tof2(B)) * (1.f - 1e-5f) > fUb);
                 }
             }
         }
@@ -355,9 +366,7 @@ __device__ int processRecord(const WinArgs& a, WinSmem& w, int li, int lane)
     for (;;) {
         // ================= drain the ring, 32 windows per pass =================
         while (head != tail) {
-            double U = warpMax(lane < K ? w.tbest[lane] : 0.0);
-            const double Ub = U * (1 + 1e-12);
-            const float fUb = Ub < 1e30 ? (float)Ub * (1.f + 2e-5f) : 3e38f;
+            const float fUb = warpBound(w, lane, K);
             int nb = min(32, tail - head);
             bool active = lane < nb;
             int p = (head + lane) & MASKR;
@@ -374,7 +383,9 @@ __device__ int processRecord(const WinArgs& a, WinSmem& w, int li, int lane)
             const int g = meta & 0xFF, e = (meta >> 16) & 3;
             const v2 AB = B - A;
             const v2 P0 = lerp2(A, B, t0), P1 = lerp2(A, B, t1);
-            if (active && (float)sg + fsegDist(S, P0, P1) * (1.f - 1e-5f) > fUb) active = false; // bound tightened since the push
+            const f2 fS = tof2(S);
+            const float fsg = (float)sg;
+            if (active && fsg + fsegDist(fS, tof2(P0), tof2(P1)) * (1.f - 1e-5f) > fUb) active = false; // bound tightened since the push
             // ---- unfold the entered face: apex C from the edge frame
             int vA = 0, vB = 0, vC = 0, kkbits = 0;
             uchar4 fa = make_uchar4(REC_NONE, REC_NONE, REC_NONE, 0);
@@ -434,16 +445,17 @@ __device__ int processRecord(const WinArgs& a, WinSmem& w, int li, int lane)
                 }
             }
             // ---- children
-            bool v0 = false, v1 = false, improved = false;
-            int m0meta = 0, m1meta = 0;
-            double c0t0 = 0, c0t1 = 0, c1t0 = 0, c1t1 = 0, dC = 0;
+            bool improved = false, leftOpen = false, rightOpen = false, inside = false;
+            double dC = 0;
+            float fDA = 0.f, fDB = 0.f, fDC = 0.f;
             if (active) {
                 const v2 dL = P0 - S, dR = P1 - S, dCv = C - S;
                 const double sideL = cross2(dL, dCv), sideR = cross2(dR, dCv);
                 const double lc2 = dCv.x * dCv.x + dCv.y * dCv.y;
-                const float lcf = sqrtf((float)lc2);
-                const double epsL = 1e-12 * (double)(flen((float)dL.x, (float)dL.y) * lcf), epsR = 1e-12 * (double)(flen((float)dR.x, (float)dR.y) * lcf);
-                const bool inside = !(sideL > epsL) && !(sideR < -epsR);
+                // |side| <= 1e-12 |d| |dC| counts as "on the ray" (squared form: no square roots)
+                leftOpen = !(sideL > 0 && sideL * sideL > 1e-24 * (dL.x * dL.x + dL.y * dL.y) * lc2);
+                rightOpen = !(sideR < 0 && sideR * sideR > 1e-24 * (dR.x * dR.x + dR.y * dR.y) * lc2);
+                inside = leftOpen && rightOpen;
                 double DC = w.D[vC];
                 if (inside) {
                     dC = sg + fsqrt(lc2);
@@ -452,42 +464,7 @@ __device__ int processRecord(const WinArgs& a, WinSmem& w, int li, int lane)
                         DC = fmin(DC, dC);
                     }
                 }
-                // Xin-Wang filter and bound test in fp32 with a conservative margin: a window is dropped only when it
-                // is dominated by clearly more than the rounding of the approximation
-                const float keep = 1.f - 2e-5f;
-                const float fsg = (float)sg, fDA = (float)w.D[vA], fDB = (float)w.D[vB], fDC = (float)DC;
-                if (!(sideL > epsL)) { // edge C->A (opposite corner B), seen from the neighbour as A->C
-                    int g2 = e == 0 ? fa.z : (e == 1 ? fa.x : fa.y); // fadj[iB]
-                    if (g2 != REC_NONE) {
-                        double m0 = hitParam(S, P0, A, C);
-                        double m1 = inside ? 1.0 : hitParam(S, P1, A, C);
-                        if (m1 - m0 > 1e-13) {
-                            v2 XA = lerp2(A, C, m0), XC = lerp2(A, C, m1);
-                            float sXA = fsg + fdist(S, XA), sXC = fsg + fdist(S, XC);
-                            bool dom = (fDA + fdist(A, XC) < sXC * keep) || (fDC + fdist(C, XA) < sXA * keep) || (fDB + fdist(B, XA) < sXA * keep);
-                            if (!dom && fsg + fsegDist(S, XA, XC) <= fUb) {
-                                int iB = e == 0 ? 2 : e - 1;
-                                v0 = true, m0meta = g2 | (((kkbits >> (2 * iB)) & 3) << 16), c0t0 = m0, c0t1 = m1;
-                            }
-                        }
-                    }
-                }
-                if (!(sideR < -epsR)) { // edge B->C (opposite corner A), seen from the neighbour as C->B
-                    int g2 = e == 0 ? fa.y : (e == 1 ? fa.z : fa.x); // fadj[iA]
-                    if (g2 != REC_NONE) {
-                        double m0 = inside ? 0.0 : hitParam(S, P0, C, B);
-                        double m1 = hitParam(S, P1, C, B);
-                        if (m1 - m0 > 1e-13) {
-                            v2 XC = lerp2(C, B, m0), XB = lerp2(C, B, m1);
-                            float sXC = fsg + fdist(S, XC), sXB = fsg + fdist(S, XB);
-                            bool dom = (fDB + fdist(B, XC) < sXC * keep) || (fDC + fdist(C, XB) < sXB * keep) || (fDA + fdist(A, XB) < sXB * keep);
-                            if (!dom && fsg + fsegDist(S, XC, XB) <= fUb) {
-                                int iA = e == 2 ? 0 : e + 1;
-                                v1 = true, m1meta = g2 | (((kkbits >> (2 * iA)) & 3) << 16), c1t0 = m0, c1t1 = m1;
-                            }
-                        }
-                    }
-                }
+                fDA = (float)w.D[vA], fDB = (float)w.D[vB], fDC = (float)DC;
             }
             __syncwarp();
             if (improved && dC == w.D[vC]) { // the winner writes the start direction carried to this vertex
@@ -495,8 +472,41 @@ __device__ int processRecord(const WinArgs& a, WinSmem& w, int li, int lane)
                 else w.dirx[vC] = w.dirx[psv], w.diry[vC] = w.diry[psv];
                 w.vdirty[vC] = 1;
             }
-            if (!pushWindows(w, lane, head, tail, v0, A, C, S, c0t0, c0t1, sg, m0meta, psv)) return WS_RING;
-            if (!pushWindows(w, lane, head, tail, v1, C, B, S, c1t0, c1t1, sg, m1meta, psv)) return WS_RING;
+            // child j = 0: edge C->A of this face (opposite corner B), entered by the neighbour as A->C
+            // child j = 1: edge B->C of this face (opposite corner A), entered by the neighbour as C->B
+            // Xin-Wang filter and bound test in fp32 with a conservative margin: a window is dropped only when it is
+            // dominated by clearly more than the rounding of the approximation.
+            const f2 fA = tof2(A), fB = tof2(B), fC = tof2(C);
+#pragma unroll 1
+            for (int j = 0; j < 2; ++j) {
+                const v2 X = j ? C : A, Y = j ? B : C;
+                bool valid = false;
+                double m0 = 0, m1 = 1;
+                int cmeta = 0;
+                if (active && (j ? rightOpen : leftOpen)) {
+                    const int io = j ? (e == 2 ? 0 : e + 1) : (e == 0 ? 2 : e - 1); // corner opposite the child edge: iA / iB
+                    const int g2 = io == 0 ? fa.x : (io == 1 ? fa.y : fa.z);
+                    if (g2 != REC_NONE) {
+                        if (!(j == 1 && inside)) m0 = hitParam(S, P0, X, Y);
+                        if (!(j == 0 && inside)) m1 = hitParam(S, P1, X, Y);
+                        if (m1 - m0 > 1e-13) {
+                            const f2 fX = j ? fC : fA, fY = j ? fB : fC, fO = j ? fA : fB;
+                            const float dX = j ? fDC : fDA, dY = j ? fDB : fDC, dO = j ? fDA : fDB;
+                            const f2 X0 = flerp(fX, fY, (float)m0), X1 = flerp(fX, fY, (float)m1);
+                            if (fsg + fsegDist(fS, X0, X1) <= fUb) {
+                                const float keep = 1.f - 2e-5f;
+                                const float s0 = (fsg + fdist(fS, X0)) * keep, s1 = (fsg + fdist(fS, X1)) * keep;
+                                const f2 Xn = j ? X1 : X0; // the end of the child interval next to the parent edge
+                                const float sn = j ? s1 : s0;
+                                const bool dom = (dX + fdist(fX, X1) < s1) || (dY + fdist(fY, X0) < s0) || (dO + fdist(fO, Xn) < sn);
+                                valid = !dom;
+                                cmeta = g2 | (((kkbits >> (2 * io)) & 3) << 16);
+                            }
+                        }
+                    }
+                }
+                if (!pushWindows(w, lane, head, tail, valid, X, Y, S, m0, m1, sg, cmeta, psv)) return WS_RING;
+            }
             __syncwarp();
         }
 
@@ -520,14 +530,13 @@ __device__ int processRecord(const WinArgs& a, WinSmem& w, int li, int lane)
             }
         }
         __syncwarp();
-        const double U = warpMax(lane < K ? w.tbest[lane] : 0.0);
-        const double Ub = U * (1 + 1e-12);
+        const float fUb = warpBound(w, lane, K);
         // A vertex v can lie on a shortest path to target t only if D[v] + |x_v - x_t| (Euclidean lower bound of the
         // remaining leg) beats the best path known to t.
         bool spawned = false, ok = true;
         for (int v0i = 0; v0i < nV; v0i += 32) {
             int v = v0i + lane;
-            bool fl = v < nV && w.vdirty[v] && w.velig[v] && w.D[v] <= Ub;
+            bool fl = v < nV && w.vdirty[v] && w.velig[v] && (float)w.D[v] * (1.f - 1e-6f) <= fUb;
             if (v < nV) w.vdirty[v] = 0;
             if (fl) {
                 bool useful = false;
@@ -545,7 +554,7 @@ __device__ int processRecord(const WinArgs& a, WinSmem& w, int li, int lane)
                 bal &= bal - 1;
                 spawned = true;
                 nPs++;
-                ok = spawnFan(w, lane, nF, v0i + b, Ub, head, tail) && ok;
+                ok = spawnFan(w, lane, nF, v0i + b, fUb, head, tail) && ok;
             }
         }
         if (!ok) return WS_RING;
