@@ -30,7 +30,7 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
-from curvedspacesim_b200 import meshes  # noqa: E402
+from curvedspacesim_b200 import meshes, sharding  # noqa: E402
 from helpers import interaction_range, make_state  # noqa: E402
 
 METRIC = "particle_timesteps_per_s"
@@ -112,10 +112,8 @@ def build_workload(name):
 
 
 def shard(N, rank, nranks):
-    per = int(math.ceil(N / nranks))
-    lo = min(rank * per, N)
-    hi = N if rank == nranks - 1 else min((rank + 1) * per, N)
-    return lo, hi
+    """mpiModel::determineIndexBounds (src/models/mpiModel.cpp:20-31)."""
+    return sharding.index_bounds(N, rank, nranks)
 
 
 def run_reference(args, rank, world):
@@ -237,7 +235,7 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
-    step_ms, geo_ms, walk_ms, cell_ms = [], [], [], []
+    step_ms, geo_ms, walk_ms, cell_ms, patch_ms, win_ms, retry_ms = [], [], [], [], [], [], []
     t_wall0 = time.perf_counter()
     for _ in range(args.steps):
         flush()
@@ -251,6 +249,10 @@ def main():
         geo_ms.append(k["geodesic_ms"])
         walk_ms.append(k["walk_ms"])
         cell_ms.append(k["celllist_ms"])
+        k = ctx.last_stage_ms()
+        patch_ms.append(k["patch_ms"])
+        win_ms.append(k["window_ms"])
+        retry_ms.append(k["retry_ms"])
     barrier()
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.stop()
@@ -291,21 +293,34 @@ def main():
     h2d = N * (4 + 24) + nloc * 48
     d2h = N * (4 + 24) + nloc * 48
 
-    # ---- roofline of the dominant kernel (k_geodesic): algorithmic bytes per launch / duration
+    # ---- roofline of the dominant kernel (k_windows, stage 2): algorithmic bytes per launch / measured duration.
+    # Per source it must read its patch record (header 16, tIdx 4K, tFace K, velig P_v, gface 4 P_f, gvert 4 P_v,
+    # fvert 4 P_f, fadj 4 P_f), the edge frames of the patch faces (48 P_f), the patch vertices (24 P_v), the targets'
+    # barycentric + Euclidean positions (48 K), its own (52), and write idx/dist/start tangent (36 K), the force (24)
+    # and the kicked velocity (read + write 48).  DESIGN.md "Measurement" states the same formula.
     ns = max(cnt["sources"], 1)
     pf, pv, kq = cnt["patch_faces"] / ns, cnt["patch_verts"] / ns, cnt["queries"] / ns
-    # B_patch = 24 P_f + 24 P_v ; B_cand = 28 K ; B_out = 36 K ; + source position 28 B,
-    # force write 24 B, velocity read+write 48 B (fused half-kick)
-    bytes_per_source = 24 * pf + 24 * pv + 28 * kq + 36 * kq + 28 + 24 + 48
-    launches = args.steps
-    geo_ms_per_launch = float(np.sum(geo_ms)) / launches
-    achieved = (bytes_per_source * nloc) / (geo_ms_per_launch * 1e-3) / 1e9
+    bytes_per_source = (16 + 5 * kq + 5 * pv + 12 * pf) + 48 * pf + 24 * pv + 48 * kq + 52 + 36 * kq + 24 + 48
+    win_ms_per_launch = float(np.mean(win_ms))
+    achieved = (bytes_per_source * nloc) / (win_ms_per_launch * 1e-3) / 1e9
     pk, pk_kind = peaks()
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1_k_windows_traffic.json")
+    if os.path.exists(tpath):  # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this workload
+        with open(tpath) as fh:
+            tj = json.load(fh)
+        if tj.get("workload") == args.workload and world == 1:
+            traffic = tj.get("dram_bytes_per_launch")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
-                "traffic": None, "peak_source": pk_kind + " (MEASURED_PEAKS.json hbm_gbs, burst copy)" if pk_kind == "measured" else "fallback 6650 GB/s",
-                "kernel": "k_geodesic<false> (tier 0)", "algorithmic_bytes_per_source": bytes_per_source,
-                "kernel_ms_per_launch": geo_ms_per_launch, "kernel_share_of_step": geo_total_ms / total_ms,
-                "note": "working set (48 MB mesh + 10 MB state) is L2-resident; the kernel is latency/FP64-bound, not HBM-bound"}
+                "traffic": traffic,
+                "peak_source": pk_kind + " (MEASURED_PEAKS.json hbm_gbs, burst copy)" if pk_kind == "measured" else "fallback 6650 GB/s",
+                "kernel": "k_windows (stage 2: window propagation + queries + pair forces)",
+                "algorithmic_bytes_per_source": bytes_per_source, "kernel_ms_per_launch": win_ms_per_launch,
+                "kernel_share_of_step": max_over_ranks(float(np.sum(win_ms))) / total_ms,
+                "other_kernels_ms_per_step": {"k_patch": float(np.mean(patch_ms)), "retry_tiers": float(np.mean(retry_ms)),
+                                              "k_walk": float(np.mean(walk_ms)), "celllist": float(np.mean(cell_ms))},
+                "note": "mesh SoA + edge frames + patch records stay L2-resident; the kernel is issue/latency-bound fp64 work, "
+                        "not HBM-bound (see profiles/ for FP64-pipe and issue-slot utilisation)"}
 
     # ---- CPU baseline (oracle port, all host cores) on rank 0 at N=1 only
     cpu = None
@@ -335,7 +350,8 @@ def main():
             "queries_per_step": queries / args.steps,
             "value_hot_l2": N * args.steps / (hot_ms * 1e-3), "ms_per_step_hot_l2": hot_ms / args.steps,
             "wall_s_timed_region": t_wall,
-            "phase_ms_per_step": {"walk": float(np.mean(walk_ms)), "celllist": float(np.mean(cell_ms)), "geodesic_force": float(np.mean(geo_ms))},
+            "phase_ms_per_step": {"walk": float(np.mean(walk_ms)), "celllist": float(np.mean(cell_ms)), "geodesic_force": float(np.mean(geo_ms)),
+                                  "patch_records": float(np.mean(patch_ms)), "window_propagation": float(np.mean(win_ms))},
             "patch_mean": {"faces": pf, "verts": pv, "K": kq, "windows_per_source": cnt["windows"] / ns, "tier_retry_frac": cnt["tier_retry"] / ns},
             "flags": {k: cnt[k] for k in ("walk_vertex", "walk_nohit", "walk_itercap", "walk_nan", "walk_border", "disconnected", "overflow")},
             "clocks": clocks,

@@ -32,7 +32,7 @@ API_SYMBOLS = [
     "css_set_forces", "css_find_neighbors", "css_get_neighbors", "css_compute_forces", "css_compute_energy", "css_move",
     "css_get_walk_flags", "css_step_nve", "css_step_gd", "css_nvt_init", "css_step_nvt", "css_nvt_state", "css_fire_init",
     "css_fire_minimize", "css_max_force", "css_force_norm", "css_comm_unique_id", "css_comm_init", "css_gather_positions",
-    "css_reduce", "css_counters", "css_synchronize", "css_device_positions", "css_last_kernel_ms", "css_set_timing",
+    "css_reduce", "css_counters", "css_synchronize", "css_device_positions", "css_last_kernel_ms", "css_set_timing", "css_last_stage_ms",
     "css_timer_record", "css_timer_elapsed_ms",
 ]
 
@@ -305,6 +305,11 @@ class Context:
         g, w, c = C.c_float(), C.c_float(), C.c_float()
         self._ck(self.L.css_last_kernel_ms(self.h, C.byref(g), C.byref(w), C.byref(c)))
         return {"geodesic_ms": g.value, "walk_ms": w.value, "celllist_ms": c.value}
+
+    def last_stage_ms(self):
+        p, w, r = C.c_float(), C.c_float(), C.c_float()
+        self._ck(self.L.css_last_stage_ms(self.h, C.byref(p), C.byref(w), C.byref(r)))
+        return {"patch_ms": p.value, "window_ms": w.value, "retry_ms": r.value}
 
     def timer_record(self, slot):
         self._ck(self.L.css_timer_record(self.h, int(slot)))

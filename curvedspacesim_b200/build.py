@@ -46,3 +46,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))
+
+
+def build_host_example(force: bool = False) -> str:
+    """g++ build of host/example_simulation.cpp (the C++ host layer above the C ABI) against the in-tree library."""
+    root = os.path.dirname(HERE)
+    src = os.path.join(root, "host", "example_simulation.cpp")
+    hdr = os.path.join(root, "host", "css_host.hpp")
+    exe = os.path.join(root, "host", "example_simulation.bin")
+    build()
+    if force or _stale(exe, [src, hdr, LIB, os.path.join(root, "include", "css_api.h")]):
+        subprocess.check_call([os.environ.get("CXX", "g++"), "-std=c++17", "-O2", "-Wall", "-Wextra", "-o", exe, src, "-L" + HERE,
+                               "-lcurvedspacesim_b200", "-Wl,-rpath," + HERE])
+    return exe

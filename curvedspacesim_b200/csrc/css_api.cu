@@ -96,6 +96,7 @@ struct css_ctx {
     bool timing = false;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     float msGeo = 0, msWalk = 0, msCell = 0;
+    cudaEvent_t evS[4] = {nullptr, nullptr, nullptr, nullptr}; // stage boundaries inside the geodesic phase
     cudaEvent_t tev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
@@ -150,6 +151,7 @@ int css_create(css_ctx** out, int device)
     cudaMalloc(&ctx->d_partial, REDUCE_MAX_BLOCKS * 5 * sizeof(double));
     cudaMalloc(&ctx->d_red, 8 * sizeof(double));
     for (auto& e : ctx->ev) cudaEventCreate(&e);
+    for (auto& e : ctx->evS) cudaEventCreate(&e);
     if (const char* tune = getenv("CSS_TUNE")) { // developer tuning: t0 maxF,maxV,ring,kt,warpsPerBlock, t1 ...
         int v[10];
         int n = sscanf(tune, "%d,%d,%d,%d,%d,%d,%d,%d,%d,%d", v, v + 1, v + 2, v + 3, v + 4, v + 5, v + 6, v + 7, v + 8, v + 9);
@@ -185,6 +187,8 @@ int css_destroy(css_ctx* ctx)
     for (auto& e : ctx->ev)
         if (e) cudaEventDestroy(e);
     for (auto& e : ctx->tev)
+        if (e) cudaEventDestroy(e);
+    for (auto& e : ctx->evS)
         if (e) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->st);
     delete ctx;
@@ -412,7 +416,9 @@ static int runGeodesicTiers(css_ctx* ctx, GeoArgs a, int nSrc)
         p.submeshing = a.submeshing, p.maxDist = a.maxDist, p.kmax = a.kmax;
         p.workCounter = ctx->d_work + 0, p.retryList = ctx->d_retry[0], p.retryCount = ctx->d_work + 4;
         p.counters = ctx->d_counters, p.records = ctx->d_records;
+        if (ctx->timing) cudaEventRecord(ctx->evS[0], ctx->st);
         CU(launchPatch(ctx->st, p, ctx->numSMs));
+        if (ctx->timing) cudaEventRecord(ctx->evS[1], ctx->st);
         WinArgs w{};
         w.m = a.m, w.nLocal = a.nLocal, w.minIdx = a.minIdx;
         w.face = a.face, w.bary = a.bary, w.eucl = a.eucl, w.records = ctx->d_records;
@@ -422,6 +428,7 @@ static int runGeodesicTiers(css_ctx* ctx, GeoArgs a, int nSrc)
         w.workCounter = ctx->d_work + 3, w.retryList = ctx->d_retry[0], w.retryCount = ctx->d_work + 4;
         w.counters = ctx->d_counters;
         CU(launchWindows(ctx->st, w, ctx->winWpb, ctx->numSMs));
+        if (ctx->timing) cudaEventRecord(ctx->evS[2], ctx->st);
         ctx->hostKernels += 2;
     } else {
         // tier 0, fused: shared memory, several warps per block
@@ -1187,6 +1194,22 @@ int css_last_kernel_ms(css_ctx* ctx, float* geodesic_ms, float* walk_ms, float* 
     if (geodesic_ms) *geodesic_ms = ctx->msGeo;
     if (walk_ms) *walk_ms = ctx->msWalk;
     if (celllist_ms) *celllist_ms = ctx->msCell;
+    return CSS_OK;
+}
+
+int css_last_stage_ms(css_ctx* ctx, float* patch_ms, float* window_ms, float* retry_ms)
+{
+    if (!ctx) return CSS_EINVAL;
+    if (!ctx->timing || !ctx->twoStage) return fail(ctx, CSS_ESTATE, "stage timing needs css_set_timing(1) and the two-stage path");
+    BIND();
+    CU(cudaEventSynchronize(ctx->ev[2]));
+    float a = 0, b = 0, c = 0;
+    CU(cudaEventElapsedTime(&a, ctx->evS[0], ctx->evS[1]));
+    CU(cudaEventElapsedTime(&b, ctx->evS[1], ctx->evS[2]));
+    CU(cudaEventElapsedTime(&c, ctx->evS[2], ctx->ev[2]));
+    if (patch_ms) *patch_ms = a;
+    if (window_ms) *window_ms = b;
+    if (retry_ms) *retry_ms = c;
     return CSS_OK;
 }
 

@@ -59,6 +59,27 @@ def test_product_package_never_imports_the_oracle():
                 assert "oracle_binding" not in txt and "liboracle" not in txt and "oracle/" not in txt, fn
 
 
+def test_cpp_host_layer_builds_and_refuses_to_run_without_a_gpu(tmp_path):
+    """host/css_host.hpp (the C++ mirror of the reference's space/model/force/updater/simulation surface) compiles with
+    g++ against the C ABI; without a CUDA device css_create fails and the reference's error convention (message +
+    std::exception) takes over - there is no CPU path to fall back to."""
+    import subprocess
+
+    import torch
+
+    from curvedspacesim_b200 import build
+
+    exe = build.build_host_example()
+    V, F = meshes.icosphere(4)
+    off = str(tmp_path / "m.off")
+    meshes.save_off(off, V, F)
+    r = subprocess.run([exe, off, "20", "2", "2", "1", str(tmp_path / "d.bin")], capture_output=True, text=True)
+    if torch.cuda.is_available():
+        assert r.returncode == 0, r.stderr
+    else:
+        assert r.returncode == 1 and "css_create" in r.stderr
+
+
 # ------------------------------------------------------------------------------------------ sharding
 @pytest.mark.parametrize("n,r", [(100, 1), (100, 3), (100000, 8), (7, 4), (5, 8), (0, 2)])
 def test_index_bounds_partition(n, r):

@@ -531,6 +531,64 @@ def test_full_size_step_is_deterministic_and_flag_free(gpu_ctx_factory):
     assert np.max(np.abs((v * nrm[res[0][0]]).sum(1))) < 1e-10  # velocities stay tangent after 20 transports
 
 
+# ------------------------------------------------------------------------------ C++ host layer
+def _read_dump(path):
+    raw = np.fromfile(path, dtype=np.uint8)
+    n = int(raw[:4].view(np.int32)[0])
+    o = 4
+
+    def take(count, dt):
+        nonlocal o
+        a = raw[o:o + count * np.dtype(dt).itemsize].view(dt).copy()
+        o += count * np.dtype(dt).itemsize
+        return a
+
+    ini = (take(n, np.int32), take(3 * n, np.float64).reshape(n, 3), take(3 * n, np.float64).reshape(n, 3))
+    fin = (take(n, np.int32), take(3 * n, np.float64).reshape(n, 3), take(3 * n, np.float64).reshape(n, 3), take(3 * n, np.float64).reshape(n, 3))
+    assert o == len(raw)
+    return n, ini, fin
+
+
+@pytest.mark.parametrize("branch,fused", [(2, 0), (2, 1), (3, 1), (3, 0), (1, 1), (0, 1), (0, 0)])
+def test_cpp_host_layer_matches_the_oracle(branch, fused, tmp_path):
+    """The reference-shaped C++ program (host/example_simulation.cpp on host/css_host.hpp: closedMeshSpace, model, cell
+    list, harmonicRepulsion, simulation, NVE / NVT / GD / FIRE updaters) against the oracle started from the SAME initial
+    state (the program dumps it), both with the host-driven updaters and with the fused device step."""
+    from curvedspacesim_b200 import build
+
+    exe = build.build_host_example()
+    V, F = _mesh("icosphere16")
+    off = str(tmp_path / "m.off")
+    meshes.save_off(off, V, F)
+    N, iters, dt, T = 150, (30 if branch else 25), 0.01, 0.2
+    dump = str(tmp_path / "d.bin")
+    out = subprocess.run([exe, off, str(N), str(iters), str(branch), str(fused), dump, str(dt), str(T)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    n, (f0, b0, v0), (f1, b1, v1, fr1) = _read_dump(dump)
+    corners = meshes.reference_corners(F)
+    orc = Oracle(V, corners)
+    _, _, area = orc.mesh_info()
+    rc = interaction_range(area, N)
+    kind, params = force_params("harmonic", k=1.0, sigma=rc)
+    orc.set_submeshing(True, rc)
+    orc.set_state(f0, b0, v0)          # forces start at zero, as in the reference's mains
+    if branch == 2:
+        orc.run_nve(kind, params, dt, iters)
+    elif branch == 3:
+        orc.nvt_init(dt, T, tau=1.0, M=2)
+        orc.run_nvt(kind, params, iters)
+    elif branch == 1:
+        orc.run_gd(kind, params, dt, iters)
+    else:
+        p = np.array([iters, dt, 0.99, 0.1, 1e-5, 1.1, 0.95, 0.9, 4, 1e-12, 0.0])
+        orc.fire_init(p, dt0=dt, alpha0=0.99)
+        orc.run_fire(kind, params)
+    of, ob, ov, ofr = orc.get_state()
+    assert np.array_equal(of, f1)
+    assert np.max(np.abs(ob - b1)) < 1e-9 and np.max(np.abs(ov - v1)) < 1e-9
+    assert np.max(np.abs(ofr - fr1)) < TOL_FORCE * max(np.abs(ofr).max(), 1e-300) + 1e-12
+
+
 # ------------------------------------------------------------------------------ multi-GPU
 def test_two_gpus_bitwise_equal_to_one(tmp_path):
     import torch
