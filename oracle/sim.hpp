@@ -275,6 +275,9 @@ struct Sim {
     // gradientDescent.cpp:6-18
     void stepGD(double dt, const PairForce& pf)
     {
+        // gradientDescent never asks for vector transport (simpleModel.h defaults: both flags false)
+        transportForce = false;
+        transportVelocity = false;
         disp.resize(N);
         computeForces(pf, true);
         for (int i = 0; i < N; ++i) disp[i] = dt * frc[i];
