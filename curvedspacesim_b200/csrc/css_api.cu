@@ -62,8 +62,8 @@ struct css_ctx {
     // two-stage tier 0: patch records (stage 1) -> window propagation (stage 2)
     bool twoStage = true;
     int winWpb = 2;
-    unsigned char* d_records = nullptr;
-    size_t capRecords = 0;
+    unsigned char *d_records = nullptr, *d_recordsL = nullptr;
+    size_t capRecords = 0, capRecordsL = 0;
     int numSMs = 148;
     // reductions / scratch
     double *d_partial = nullptr, *d_red = nullptr;
@@ -181,7 +181,7 @@ int css_destroy(css_ctx* ctx)
                     ctx->d_blockSums, ctx->d_fill,   ctx->d_tmpItems, ctx->d_items,  ctx->d_nbrCount, ctx->d_nbrIdx,  ctx->d_nbrDist,
                     ctx->d_nbrTs,  ctx->d_nbrTe,     ctx->d_work,    ctx->d_retry[0], ctx->d_retry[1], ctx->d_retry[2], ctx->d_gws,
                     ctx->d_partial, ctx->d_red,      ctx->d_counters, ctx->d_sendI,  ctx->d_sendD,    ctx->d_recvI,   ctx->d_recvD,
-                    ctx->d_redBuf,  ctx->d_geo,       ctx->d_records};
+                    ctx->d_redBuf,  ctx->d_geo,       ctx->d_records, ctx->d_recordsL};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (auto& e : ctx->ev)
@@ -401,37 +401,66 @@ static int runGeodesicTiers(css_ctx* ctx, GeoArgs a, int nSrc)
     int rc = ensureTierBuffers(ctx, std::max(nSrc, 1));
     if (rc) return rc;
     CU(cudaMemsetAsync(ctx->d_work, 0, 16 * sizeof(int), ctx->st)); // [0..2] work counters, [4..6] retry counts
+    auto ensureWorkspace = [&](size_t bytes) -> int { // global-memory workspace of the fused retry kernel
+        if (bytes > ctx->gwsBytes) {
+            CU(cudaStreamSynchronize(ctx->st));
+            if (ctx->d_gws) cudaFree(ctx->d_gws);
+            ctx->d_gws = nullptr;
+            ctx->gwsBytes = 0;
+            CU(cudaMalloc(&ctx->d_gws, bytes));
+            ctx->gwsBytes = bytes;
+        }
+        return CSS_OK;
+    };
     const bool staged = ctx->twoStage && a.xK < 0 && a.cellStart != nullptr;
     if (staged) {
-        // tier 0, two stages: patch records (integer / latency-bound, high occupancy), then window propagation (fp64)
-        size_t need = (size_t)std::max(nSrc, 1) * REC_BYTES;
-        if (need > ctx->capRecords) {
+        // Two-stage tiers: patch records (integer / latency-bound, high occupancy), then window propagation (fp64).
+        // Tier 0 = TierSmall over every local source; tier 1 = TierLarge over the sources tier 0 handed on.
+        const int maxLarge = std::min(std::max(nSrc, 1), 65536);
+        size_t needS = (size_t)std::max(nSrc, 1) * TierSmall::BYTES, needL = (size_t)maxLarge * TierLarge::BYTES;
+        if (needS > ctx->capRecords || needL > ctx->capRecordsL) {
             CU(cudaStreamSynchronize(ctx->st));
-            CU(regrow(ctx->d_records, need));
-            ctx->capRecords = need;
+            if (needS > ctx->capRecords) {
+                CU(regrow(ctx->d_records, needS));
+                ctx->capRecords = needS;
+            }
+            if (needL > ctx->capRecordsL) {
+                CU(regrow(ctx->d_recordsL, needL));
+                ctx->capRecordsL = needL;
+            }
         }
         PatchArgs p{};
         p.m = a.m, p.grid = a.grid, p.nLocal = a.nLocal, p.minIdx = a.minIdx;
         p.face = a.face, p.eucl = a.eucl, p.cellStart = a.cellStart, p.cellItems = a.cellItems;
         p.submeshing = a.submeshing, p.maxDist = a.maxDist, p.kmax = a.kmax;
-        p.workCounter = ctx->d_work + 0, p.retryList = ctx->d_retry[0], p.retryCount = ctx->d_work + 4;
-        p.counters = ctx->d_counters, p.records = ctx->d_records;
-        if (ctx->timing) cudaEventRecord(ctx->evS[0], ctx->st);
-        CU(launchPatch(ctx->st, p, ctx->numSMs));
-        if (ctx->timing) cudaEventRecord(ctx->evS[1], ctx->st);
+        p.counters = ctx->d_counters;
         WinArgs w{};
         w.m = a.m, w.nLocal = a.nLocal, w.minIdx = a.minIdx;
-        w.face = a.face, w.bary = a.bary, w.eucl = a.eucl, w.records = ctx->d_records;
+        w.face = a.face, w.bary = a.bary, w.eucl = a.eucl;
         w.submeshing = a.submeshing, w.maxDist = a.maxDist, w.kmax = a.kmax;
         w.nbrCount = a.nbrCount, w.nbrIdx = a.nbrIdx, w.nbrDist = a.nbrDist, w.nbrTs = a.nbrTs, w.nbrTe = a.nbrTe;
         w.forceMode = a.forceMode, w.fp = a.fp, w.zero = a.zero, w.frc = a.frc, w.kick = a.kick, w.vel = a.vel;
-        w.workCounter = ctx->d_work + 3, w.retryList = ctx->d_retry[0], w.retryCount = ctx->d_work + 4;
         w.counters = ctx->d_counters;
-        CU(launchWindows(ctx->st, w, ctx->winWpb, ctx->numSMs));
+        // tier 0
+        p.srcList = nullptr, p.srcCount = nullptr, p.maxRecords = std::max(nSrc, 1);
+        p.workCounter = ctx->d_work + 0, p.retryList = ctx->d_retry[0], p.retryCount = ctx->d_work + 4, p.records = ctx->d_records;
+        w.srcList = nullptr, w.srcCount = nullptr, w.maxRecords = p.maxRecords;
+        w.workCounter = ctx->d_work + 3, w.retryList = ctx->d_retry[0], w.retryCount = ctx->d_work + 4, w.records = ctx->d_records;
+        if (ctx->timing) cudaEventRecord(ctx->evS[0], ctx->st);
+        CU(launchPatch<TierSmall>(ctx->st, p, ctx->numSMs));
+        if (ctx->timing) cudaEventRecord(ctx->evS[1], ctx->st);
+        CU(launchWindows<TierSmall>(ctx->st, w, ctx->winWpb, ctx->numSMs));
         if (ctx->timing) cudaEventRecord(ctx->evS[2], ctx->st);
-        ctx->hostKernels += 2;
+        // tier 1 (work list = tier 0's retry list; its length is only known on the device)
+        p.srcList = ctx->d_retry[0], p.srcCount = ctx->d_work + 4, p.maxRecords = maxLarge;
+        p.workCounter = ctx->d_work + 1, p.retryList = ctx->d_retry[1], p.retryCount = ctx->d_work + 5, p.records = ctx->d_recordsL;
+        w.srcList = p.srcList, w.srcCount = p.srcCount, w.maxRecords = maxLarge;
+        w.workCounter = ctx->d_work + 7, w.retryList = ctx->d_retry[1], w.retryCount = ctx->d_work + 5, w.records = ctx->d_recordsL;
+        CU(launchPatch<TierLarge>(ctx->st, p, ctx->numSMs));
+        CU(launchWindows<TierLarge>(ctx->st, w, 1, ctx->numSMs));
+        ctx->hostKernels += 4;
     } else {
-        // tier 0, fused: shared memory, several warps per block
+        // fused tier 0 (explicit css_distance queries, all-to-all candidates, developer switch): shared memory
         a.caps = ctx->capsT0;
         a.srcList = nullptr, a.srcCount = nullptr;
         a.workCounter = ctx->d_work + 0;
@@ -443,38 +472,24 @@ static int runGeodesicTiers(css_ctx* ctx, GeoArgs a, int nSrc)
         int blocks = std::min(ctx->numSMs * bps, std::max(1, (nSrc + wpb - 1) / wpb));
         CU(launchGeodesic(ctx->st, a, wpb, blocks));
         ctx->hostKernels++;
-    }
-    // tiers 1 and 2 run on a global-memory workspace (no dynamic shared memory: an empty retry list costs a few
-    // microseconds and the SM shared-memory carve-out is left alone)
-    auto ensureWorkspace = [&](size_t bytes) -> int {
-        if (bytes > ctx->gwsBytes) {
-            CU(cudaStreamSynchronize(ctx->st));
-            if (ctx->d_gws) cudaFree(ctx->d_gws);
-            ctx->d_gws = nullptr;
-            ctx->gwsBytes = 0;
-            CU(cudaMalloc(&ctx->d_gws, bytes));
-            ctx->gwsBytes = bytes;
-        }
-        return CSS_OK;
-    };
-    // tier 1: large capacities, many warps
-    {
+        // fused tier 1: large capacities on a global-memory workspace
         a.caps = ctx->capsT1;
-        size_t ws = geoWorkspaceBytes(a.caps);
-        int wpb = 2, blocks = std::min(ctx->numSMs * 2, std::max(1, nSrc));
+        ws = geoWorkspaceBytes(a.caps);
+        wpb = 2, blocks = std::min(ctx->numSMs * 2, std::max(1, nSrc));
         if (int rc2 = ensureWorkspace(ws * wpb * blocks)) return rc2;
         a.srcList = ctx->d_retry[0], a.srcCount = ctx->d_work + 4;
-        a.workCounter = ctx->d_work + 1;
+        a.workCounter = ctx->d_work + 8;
         a.retryList = ctx->d_retry[1], a.retryCount = ctx->d_work + 5;
         a.gws = ctx->d_gws, a.lastTier = 0;
         CU(launchGeodesic(ctx->st, a, wpb, blocks));
         ctx->hostKernels++;
     }
-    // tier 2: capacities sized for the whole mesh
+    // last tier: the fused kernel with capacities sized for the whole mesh, global-memory workspace
     {
         a.caps = ctx->capsT2;
         if (a.xK >= 0) a.caps.kt = std::max(a.caps.kt, a.xK);
         else if (!ctx->useCellList) a.caps.kt = std::max(a.caps.kt, a.nTotal);
+        else a.caps.kt = std::max(a.caps.kt, a.kmax);
         size_t ws = geoWorkspaceBytes(a.caps);
         int warps = ctx->t2Warps;
         if (int rc2 = ensureWorkspace(ws * warps)) return rc2;

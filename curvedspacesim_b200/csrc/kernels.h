@@ -67,20 +67,26 @@ cudaError_t launchGeodesic(cudaStream_t st, const GeoArgs& a, int warpsPerBlock,
 //   int   gvert[REC_MAXV]   local vertex -> global vertex
 //   uchar4 fvert[REC_MAXF]  local corner ids + kk bits (index of each edge inside the neighbour, 2 bits per edge)
 //   uchar4 fadj[REC_MAXF]   local face across the edge opposite corner k (REC_NONE = patch border)
-#define REC_MAXF 96
-#define REC_MAXV 64
-#define REC_MAXK 16
+// Two capacity classes are instantiated: SMALL (tier 0, covers the design-point configs) and LARGE (tier 1: big patches
+// or many candidates; also the fast path of coarse meshes such as config 1).
+template <int F_, int V_, int K_, int RING_> struct GeoTier {
+    static constexpr int MAXF = F_, MAXV = V_, MAXK = K_, RING = RING_;      // faces < 255, K <= 32 (one target per lane)
+    static constexpr int OFF_TIDX = 16;
+    static constexpr int OFF_TFACE = OFF_TIDX + 4 * K_;
+    static constexpr int OFF_VELIG = OFF_TFACE + K_;
+    static constexpr int OFF_GFACE = OFF_VELIG + V_;
+    static constexpr int OFF_GVERT = OFF_GFACE + 4 * F_;
+    static constexpr int OFF_FVERT = OFF_GVERT + 4 * V_;
+    static constexpr int OFF_FADJ = OFF_FVERT + 4 * F_;
+    static constexpr int BYTES = OFF_FADJ + 4 * F_;
+    static constexpr int HASHF = F_ <= 96 ? 256 : 512, HASHV = V_ <= 64 ? 256 : 512; // >= 2 x capacity + in-flight inserts
+    static_assert(BYTES % 16 == 0 && OFF_FVERT % 16 == 0 && OFF_GFACE % 4 == 0, "record sections must stay aligned");
+    static_assert(F_ < 255 && V_ < 256 && K_ <= 32 && (RING_ & (RING_ - 1)) == 0, "8-bit local ids, one target per lane");
+};
+using TierSmall = GeoTier<96, 64, 16, 64>;
+using TierLarge = GeoTier<240, 160, 32, 256>;
 #define REC_NONE 255
-#define REC_OFF_TIDX 16
-#define REC_OFF_TFACE (REC_OFF_TIDX + 4 * REC_MAXK)
-#define REC_OFF_VELIG (REC_OFF_TFACE + REC_MAXK)
-#define REC_OFF_GFACE (REC_OFF_VELIG + REC_MAXV)
-#define REC_OFF_GVERT (REC_OFF_GFACE + 4 * REC_MAXF)
-#define REC_OFF_FVERT (REC_OFF_GVERT + 4 * REC_MAXV)
-#define REC_OFF_FADJ (REC_OFF_FVERT + 4 * REC_MAXF)
-#define REC_BYTES (REC_OFF_FADJ + 4 * REC_MAXF)
 #define PATCH_THREADS 256
-#define WIN_RING 64
 
 struct PatchArgs {
     MeshDev m;
@@ -93,14 +99,17 @@ struct PatchArgs {
     int submeshing;
     double maxDist;
     int kmax;
+    // work: local particle indices srcList[0..*srcCount) (records indexed by list position), or 0..nLocal-1 when null
+    const int* srcList;
+    const int* srcCount;
+    int maxRecords;       // capacity of `records`; list entries beyond it go straight to the retry list
     int* workCounter;
     int* retryList;
     int* retryCount;
     unsigned long long* counters;
-    unsigned char* records; // [nLocal][REC_BYTES]
+    unsigned char* records; // [maxRecords][Tier::BYTES]
 };
-cudaError_t launchPatch(cudaStream_t st, const PatchArgs& a, int numSMs);
-size_t patchSmemPerWarp();
+template <class Tier> cudaError_t launchPatch(cudaStream_t st, const PatchArgs& a, int numSMs);
 
 struct WinArgs {
     MeshDev m;
@@ -109,6 +118,9 @@ struct WinArgs {
     const double* bary;
     const double* eucl;
     const unsigned char* records;
+    const int* srcList;
+    const int* srcCount;
+    int maxRecords;
     int submeshing;
     double maxDist;
     int kmax;
@@ -128,8 +140,7 @@ struct WinArgs {
     int* retryCount;
     unsigned long long* counters;
 };
-cudaError_t launchWindows(cudaStream_t st, const WinArgs& a, int warpsPerBlock, int numSMs);
-size_t windowSmemPerWarp();
+template <class Tier> cudaError_t launchWindows(cudaStream_t st, const WinArgs& a, int warpsPerBlock, int numSMs);
 int geodesicMaxSmemPerBlock();
 
 void launchEuclidCell(cudaStream_t st, const MeshDev& m, const CellGrid& g, int n, const int* face, const double* bary, double* eucl,

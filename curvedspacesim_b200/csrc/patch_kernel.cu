@@ -29,16 +29,13 @@ namespace css {
 
 namespace {
 
-constexpr int HF = 256; // face hash slots  (>= 2 * REC_MAXF, power of two)
-constexpr int HV = 256; // vertex hash slots (>= 2 * REC_MAXV, power of two)
-
-struct PatchSmem {                   // per-warp scratch
-    int fhKey[HF];                   // global face id -> slot
-    int vhKey[HV];                   // global vertex id -> slot
-    unsigned char fhVal[HF];         // slot -> local face id
-    unsigned char vhVal[HV];         // slot -> local vertex id
+template <class T> struct PatchSmem { // per-warp scratch
+    int fhKey[T::HASHF];             // global face id -> slot
+    int vhKey[T::HASHV];             // global vertex id -> slot
+    unsigned char fhVal[T::HASHF];   // slot -> local face id
+    unsigned char vhVal[T::HASHV];   // slot -> local vertex id
     int misc[4];                     // nF, nV, overflow
-    alignas(16) unsigned char rec[REC_BYTES];
+    alignas(16) unsigned char rec[T::BYTES];
 };
 
 __device__ __forceinline__ unsigned hashInt(int k) { return (unsigned)k * 2654435761u; }
@@ -86,16 +83,17 @@ __device__ __forceinline__ double warpMaxD(double v)
 }
 
 // returns 0 ok, 1 overflow (source goes to the retry tiers)
-__device__ int buildPatch(const PatchArgs& a, PatchSmem& s, int li, int lane)
+template <class T> __device__ int buildPatch(const PatchArgs& a, PatchSmem<T>& s, int li, int lane)
 {
+    constexpr int HF = T::HASHF, HV = T::HASHV;
     const int gi = a.minIdx + li;
-    int* tIdx = reinterpret_cast<int*>(s.rec + REC_OFF_TIDX);
-    int* gface = reinterpret_cast<int*>(s.rec + REC_OFF_GFACE);
-    int* gvert = reinterpret_cast<int*>(s.rec + REC_OFF_GVERT);
-    unsigned char* tFace = s.rec + REC_OFF_TFACE;
-    unsigned char* velig = s.rec + REC_OFF_VELIG;
-    uchar4* fvert = reinterpret_cast<uchar4*>(s.rec + REC_OFF_FVERT);
-    uchar4* fadj = reinterpret_cast<uchar4*>(s.rec + REC_OFF_FADJ);
+    int* tIdx = reinterpret_cast<int*>(s.rec + T::OFF_TIDX);
+    int* gface = reinterpret_cast<int*>(s.rec + T::OFF_GFACE);
+    int* gvert = reinterpret_cast<int*>(s.rec + T::OFF_GVERT);
+    unsigned char* tFace = s.rec + T::OFF_TFACE;
+    unsigned char* velig = s.rec + T::OFF_VELIG;
+    uchar4* fvert = reinterpret_cast<uchar4*>(s.rec + T::OFF_FVERT);
+    uchar4* fadj = reinterpret_cast<uchar4*>(s.rec + T::OFF_FADJ);
     int* hdr = reinterpret_cast<int*>(s.rec);
 
     const int sf = a.face[gi];
@@ -143,7 +141,7 @@ __device__ int buildPatch(const PatchArgs& a, PatchSmem& s, int li, int lane)
             if (lane == 0) atomicAdd(a.counters + C_KMAX_OVERFLOW, 1ull);
             return 1;
         }
-        if (K > REC_MAXK) return 1;
+        if (K > T::MAXK) return 2; // 1 + reason (0 candidates, 1 faces, 2 vertices)
         maxd2 = warpMaxD(maxd2);
         R = xsqrt(maxd2);
         int pos = incl - mine;
@@ -183,14 +181,14 @@ __device__ int buildPatch(const PatchArgs& a, PatchSmem& s, int li, int lane)
         int slot = hashInsert(s.fhKey, HF - 1, g, isNew);
         if (isNew) {
             int id = atomicAdd(&s.misc[0], 1);
-            if (id < REC_MAXF) {
+            if (id < T::MAXF) {
                 gface[id] = g;
                 s.fhVal[slot] = (unsigned char)id;
             } else
                 s.misc[2] = 1;
         }
     };
-    int myTF = lane < K ? a.face[tIdx[lane]] : sf; // K <= REC_MAXK <= 32: one target per lane
+    int myTF = lane < K ? a.face[tIdx[lane]] : sf; // K <= T::MAXK <= 32: one target per lane
     if (lane == 0) addFace(sf);
     __syncwarp();
     if (__any_sync(FULL, myTF != sf)) {
@@ -205,8 +203,8 @@ __device__ int buildPatch(const PatchArgs& a, PatchSmem& s, int li, int lane)
             int head = 1;
             for (;;) {
                 __syncwarp();
-                int tail = min(s.misc[0], REC_MAXF);
-                if (s.misc[2]) return 1;
+                int tail = min(s.misc[0], T::MAXF);
+                if (s.misc[2]) return 3;
                 if (head >= tail) break;
                 int slotF = lane / 3, k = lane - 3 * slotF;
                 int idx = head + slotF;
@@ -218,7 +216,7 @@ __device__ int buildPatch(const PatchArgs& a, PatchSmem& s, int li, int lane)
                         d3 p0 = ldvert(a.m, c.x), p1 = ldvert(a.m, c.y), p2 = ldvert(a.m, c.z);
                         bool far = xsqlen(xsub3(sp, p0)) > thr2 && xsqlen(xsub3(sp, p1)) > thr2 && xsqlen(xsub3(sp, p2)) > thr2;
                         if (!far) {
-                            if (s.misc[0] >= REC_MAXF) s.misc[2] = 1;
+                            if (s.misc[0] >= T::MAXF) s.misc[2] = 1;
                             else addFace(g);
                         }
                     }
@@ -226,13 +224,13 @@ __device__ int buildPatch(const PatchArgs& a, PatchSmem& s, int li, int lane)
                 head = min(head + 10, tail);
             }
             if (hashFind(s.fhKey, HF - 1, myTF) < 0) { // leftover goal faces (submesher.cpp:143-144)
-                if (s.misc[0] >= REC_MAXF) s.misc[2] = 1;
+                if (s.misc[0] >= T::MAXF) s.misc[2] = 1;
                 else addFace(myTF);
             }
         }
     }
     __syncwarp();
-    if (s.misc[2] || s.misc[0] > REC_MAXF) return 1;
+    if (s.misc[2] || s.misc[0] > T::MAXF) return 3;
     const int nF = s.misc[0];
 
     // ---------------- 3. local indexing ----------------
@@ -245,17 +243,17 @@ __device__ int buildPatch(const PatchArgs& a, PatchSmem& s, int li, int lane)
             int slot = hashInsert(s.vhKey, HV - 1, gv, isNew);
             if (isNew) {
                 int id = atomicAdd(&s.misc[1], 1);
-                if (id < REC_MAXV) {
+                if (id < T::MAXV) {
                     gvert[id] = gv;
                     s.vhVal[slot] = (unsigned char)id;
                 } else
                     s.misc[2] = 1;
             }
         }
-        if (s.misc[2]) break; // the table is sized 2 x REC_MAXV + 3 x 32 in-flight inserts: it cannot fill up before this trips
+        if (s.misc[2]) break; // the table is sized 2 x T::MAXV + 3 x 32 in-flight inserts: it cannot fill up before this trips
     }
     __syncwarp();
-    if (s.misc[2] || s.misc[1] > REC_MAXV) return 1;
+    if (s.misc[2] || s.misc[1] > T::MAXV) return 4;
     const int nV = s.misc[1];
     for (int v = lane; v < nV; v += 32) velig[v] = a.m.saddle[gvert[v]];
     __syncwarp();
@@ -289,53 +287,65 @@ __device__ int buildPatch(const PatchArgs& a, PatchSmem& s, int li, int lane)
 
 } // namespace
 
-__global__ void __launch_bounds__(PATCH_THREADS) k_patch(PatchArgs a)
+template <class T> __global__ void __launch_bounds__(PATCH_THREADS) k_patch(PatchArgs a)
 {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    PatchSmem& s = reinterpret_cast<PatchSmem*>(smemRaw)[wib];
+    PatchSmem<T>& s = reinterpret_cast<PatchSmem<T>*>(smemRaw)[wib];
     unsigned long long nRetry = 0;
+    const int nWork = a.srcList ? *a.srcCount : a.nLocal;
     for (;;) {
-        int li = 0;
-        if (lane == 0) li = atomicAdd(a.workCounter, 1);
-        li = __shfl_sync(FULL, li, 0);
-        if (li >= a.nLocal) break;
-        int st = buildPatch(a, s, li, lane);
+        int w = 0;
+        if (lane == 0) w = atomicAdd(a.workCounter, 1);
+        w = __shfl_sync(FULL, w, 0);
+        if (w >= nWork) break;
+        const int li = a.srcList ? a.srcList[w] : w;
+        int* hdr = reinterpret_cast<int*>(s.rec);
+        if (w >= a.maxRecords) { // no record slot left in this tier: hand the source on
+            if (lane == 0) {
+                int r = atomicAdd(a.retryCount, 1);
+                a.retryList[r] = li;
+                nRetry++;
+            }
+            continue;
+        }
+        int st = buildPatch<T>(a, s, li, lane);
         st = __shfl_sync(FULL, st, 0);
         __syncwarp();
-        int* hdr = reinterpret_cast<int*>(s.rec);
         if (st != 0 && lane == 0) {
             hdr[0] = 0, hdr[1] = 0, hdr[2] = 0, hdr[3] = 1; // stage 2 skips this source
             int r = atomicAdd(a.retryCount, 1);
             a.retryList[r] = li;
             nRetry++;
+            if (st >= 2) atomicAdd(a.counters + C_OVF_REASON + st - 2, 1ull);
         }
         __syncwarp();
         // coalesced record store; the unused tail of a record is never read
         const int4* src = reinterpret_cast<const int4*>(s.rec);
-        int4* dst = reinterpret_cast<int4*>(a.records + (size_t)li * REC_BYTES);
+        int4* dst = reinterpret_cast<int4*>(a.records + (size_t)w * T::BYTES);
         int nF = hdr[0];
-        int used = hdr[3] ? 1 : (nF == 0 ? REC_OFF_TFACE / 16 : REC_BYTES / 16);
+        int used = hdr[3] ? 1 : (nF == 0 ? T::OFF_TFACE / 16 : T::BYTES / 16);
         for (int q = lane; q < used; q += 32) dst[q] = src[q];
         __syncwarp();
     }
     if (lane == 0 && nRetry) atomicAdd(a.counters + C_TIER_RETRY, nRetry);
 }
 
-size_t patchSmemPerWarp() { return sizeof(PatchSmem); }
-
-cudaError_t launchPatch(cudaStream_t st, const PatchArgs& a, int numSMs)
+template <class T> cudaError_t launchPatch(cudaStream_t st, const PatchArgs& a, int numSMs)
 {
-    size_t smem = sizeof(PatchSmem) * (PATCH_THREADS / 32);
+    size_t smem = sizeof(PatchSmem<T>) * (PATCH_THREADS / 32);
     static int perSM = 0;
     if (!perSM) {
-        cudaFuncSetAttribute(k_patch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_patch, PATCH_THREADS, smem) != cudaSuccess || perSM < 1) perSM = 1;
+        cudaFuncSetAttribute(k_patch<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_patch<T>, PATCH_THREADS, smem) != cudaSuccess || perSM < 1) perSM = 1;
     }
-    // persistent warps pulling sources from a work counter: one wave of resident blocks
-    int blocks = min(numSMs * perSM, max(1, (a.nLocal + PATCH_THREADS / 32 - 1) / (PATCH_THREADS / 32)));
-    k_patch<<<blocks, PATCH_THREADS, smem, st>>>(a);
+    // persistent warps pulling sources from a work counter: one wave of resident blocks (a retry tier whose list
+    // length is only known on the device gets one block per SM)
+    int blocks = a.srcList ? numSMs : min(numSMs * perSM, max(1, (a.nLocal + PATCH_THREADS / 32 - 1) / (PATCH_THREADS / 32)));
+    k_patch<T><<<blocks, PATCH_THREADS, smem, st>>>(a);
     return cudaGetLastError();
 }
+template cudaError_t launchPatch<TierSmall>(cudaStream_t, const PatchArgs&, int);
+template cudaError_t launchPatch<TierLarge>(cudaStream_t, const PatchArgs&, int);
 
 } // namespace css

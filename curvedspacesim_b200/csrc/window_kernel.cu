@@ -27,32 +27,30 @@ namespace css {
 
 namespace {
 
-constexpr int RING = WIN_RING;
-constexpr int MASKR = RING - 1;
 constexpr unsigned char NOPSV = 255;
 
 __device__ __forceinline__ double dinf() { return __longlong_as_double(0x7ff0000000000000LL); }
 
-struct WinSmem { // per-warp workspace (15.6 KB)
-    double2 geo[3 * REC_MAXF];
-    double vx[REC_MAXV], vy[REC_MAXV], vz[REC_MAXV], D[REC_MAXV], dirx[REC_MAXV], diry[REC_MAXV];
-    double rax[RING], ray[RING], rbx[RING], rby[RING], rsx[RING], rsy[RING], rt0[RING], rt1[RING], rsg[RING];
-    double tbest[REC_MAXK], tb0[REC_MAXK], tb1[REC_MAXK], tb2[REC_MAXK], tsx[REC_MAXK], tsy[REC_MAXK], tdu[REC_MAXK], tdw[REC_MAXK];
-    double tpx[REC_MAXK], tpy[REC_MAXK], tpz[REC_MAXK], tcd0[REC_MAXK], tcd1[REC_MAXK], tcd2[REC_MAXK];
+template <class T> struct WinSmem { // per-warp workspace (15.9 KB for TierSmall)
+    static constexpr int F = T::MAXF, V = T::MAXV, K = T::MAXK, R = T::RING;
+    double2 geo[3 * F];
+    double vx[V], vy[V], vz[V], D[V], dirx[V], diry[V];
+    double rax[R], ray[R], rbx[R], rby[R], rsx[R], rsy[R], rt0[R], rt1[R], rsg[R];
+    double tbest[K], tb0[K], tb1[K], tb2[K], tsx[K], tsy[K], tdu[K], tdw[K];
+    double tpx[K], tpy[K], tpz[K], tcd0[K], tcd1[K], tcd2[K];
     double root[6];
-    int rmeta[RING];
-    int tIdx[REC_MAXK];
-    int tcode[REC_MAXK];  // how the best path ends: 0 none, 1 chord in the source face, 2 + 4*(g | e << 8) window, 3 + 4*k corner k
-    int towner[REC_MAXK];
-    alignas(16) uchar4 fvert[REC_MAXF];
-    uchar4 fadj[REC_MAXF];
-    unsigned short tmask[REC_MAXF]; // targets lying in each face (bit t)
-    alignas(16) unsigned char tFace[REC_MAXK];
-    unsigned char velig[REC_MAXV];
-    unsigned char vdirty[REC_MAXV];
-    unsigned char rpsv[RING];
-    int misc[4];
     unsigned long long wcnt[16];
+    int rmeta[R];
+    int tIdx[K];
+    int tcode[K];  // how the best path ends: 0 none, 1 chord in the source face, 2 + 4*(g | e << 8) window, 3 + 4*k corner k
+    int towner[K];
+    unsigned tmask[F]; // targets lying in each face (bit t)
+    alignas(16) uchar4 fvert[F];
+    uchar4 fadj[F];
+    alignas(16) unsigned char tFace[K];
+    unsigned char velig[V];
+    unsigned char vdirty[V];
+    unsigned char rpsv[R];
 };
 
 struct v2 {
@@ -120,7 +118,7 @@ __device__ __forceinline__ float fsegDist(const f2& S, const f2& X0, const f2& X
     return flen(fmaf(-s, ex, sx), fmaf(-s, ey, sy));
 }
 // upper bound U = max_t best[t] in fp32, rounded up (non-negative floats order like their bit patterns; +inf stays +inf)
-__device__ __forceinline__ float warpBound(const WinSmem& w, int lane, int K)
+template <class W> __device__ __forceinline__ float warpBound(const W& w, int lane, int K)
 {
     unsigned u = lane < K ? __float_as_uint(__double2float_ru(w.tbest[lane])) : 0u;
     return __uint_as_float(__reduce_max_sync(FULL, u)) * (1.f + 2e-5f);
@@ -143,14 +141,14 @@ __device__ __forceinline__ d3 pairForce(const ForceParams& fp, const d3& sep, do
 }
 
 // push up to one window per lane; returns false when the ring would overflow
-__device__ __forceinline__ bool pushWindows(WinSmem& w, int lane, int head, int& tail, bool valid, const v2& A, const v2& B, const v2& S,
+template <class W> __device__ __forceinline__ bool pushWindows(W& w, int lane, int head, int& tail, bool valid, const v2& A, const v2& B, const v2& S,
                                             double t0, double t1, double sg, int meta, unsigned char psv)
 {
     unsigned bal = __ballot_sync(FULL, valid);
     int tot = __popc(bal);
-    if (tail + tot - head > RING) return false;
+    if (tail + tot - head > W::R) return false;
     if (valid) {
-        int q = (tail + __popc(bal & ((1u << lane) - 1))) & MASKR;
+        int q = (tail + __popc(bal & ((1u << lane) - 1))) & (W::R - 1);
         w.rax[q] = A.x, w.ray[q] = A.y, w.rbx[q] = B.x, w.rby[q] = B.y, w.rsx[q] = S.x, w.rsy[q] = S.y;
         w.rt0[q] = t0, w.rt1[q] = t1, w.rsg[q] = sg, w.rmeta[q] = meta, w.rpsv[q] = psv;
     }
@@ -159,7 +157,7 @@ __device__ __forceinline__ bool pushWindows(WinSmem& w, int lane, int head, int&
 }
 
 // pseudo-source fan of vertex pv (rare: kept out of line to keep the propagation loop compact)
-__device__ __noinline__ bool spawnFan(WinSmem& w, int lane, int nF, int pv, float fUb, int head, int& tail)
+template <class W> __device__ __noinline__ bool spawnFan(W& w, int lane, int nF, int pv, float fUb, int head, int& tail)
 {
     const double Dv = w.D[pv];
     const d3 Pv{w.vx[pv], w.vy[pv], w.vz[pv]};
@@ -215,7 +213,7 @@ __device__ __noinline__ bool spawnFan(WinSmem& w, int lane, int nF, int pv, floa
 }
 
 // 3-D unit end tangent of a path that enters face g through edge e with direction (du, dw) in that edge's frame
-__device__ __noinline__ d3 liftEnd(const WinSmem& w, int g, int e, double du, double dw)
+template <class W> __device__ __noinline__ d3 liftEnd(const W& w, int g, int e, double du, double dw)
 {
     uchar4 fv = w.fvert[g];
     int c0 = fv.x, c1 = fv.y, c2 = fv.z;
@@ -236,11 +234,12 @@ __device__ __noinline__ d3 liftEnd(const WinSmem& w, int g, int e, double du, do
 
 enum { WS_OK = 0, WS_RING = 1 };
 
-__device__ int processRecord(const WinArgs& a, WinSmem& w, int li, int lane)
+template <class T> __device__ int processRecord(const WinArgs& a, WinSmem<T>& w, int li, int rslot, int lane)
 {
+    constexpr int MASKR = T::RING - 1;
     unsigned long long* cnt = w.wcnt;
     const int gi = a.minIdx + li;
-    const unsigned char* rec = a.records + (size_t)li * REC_BYTES;
+    const unsigned char* rec = a.records + (size_t)rslot * T::BYTES;
     const int4 hdr = *reinterpret_cast<const int4*>(rec);
     const int nF = hdr.x, nV = hdr.y, K = hdr.z;
     if (hdr.w) return WS_OK; // overflowed in stage 1: the retry tiers own this source
@@ -259,28 +258,28 @@ __device__ int processRecord(const WinArgs& a, WinSmem& w, int li, int lane)
 
     // ---------------- stage the patch ----------------
     {
-        const int4* src = reinterpret_cast<const int4*>(rec + REC_OFF_FVERT); // fvert | fadj are contiguous in both layouts
+        const int4* src = reinterpret_cast<const int4*>(rec + T::OFF_FVERT); // fvert | fadj are contiguous in both layouts
         int4* dst = reinterpret_cast<int4*>(w.fvert);
-        for (int q = lane; q < (2 * 4 * REC_MAXF) / 16; q += 32)
-            if (q * 4 < nF || (q >= REC_MAXF / 4 && (q - REC_MAXF / 4) * 4 < nF)) dst[q] = src[q];
-        const int* gface = reinterpret_cast<const int*>(rec + REC_OFF_GFACE);
+        for (int q = lane; q < (2 * 4 * T::MAXF) / 16; q += 32)
+            if (q * 4 < nF || (q >= T::MAXF / 4 && (q - T::MAXF / 4) * 4 < nF)) dst[q] = src[q];
+        const int* gface = reinterpret_cast<const int*>(rec + T::OFF_GFACE);
         for (int q = lane; q < 3 * nF; q += 32) {
             int f = q / 3, e = q - 3 * f;
             w.geo[q] = __ldg(a.m.geo + 3 * (size_t)gface[f] + e);
         }
         for (int f = lane; f < nF; f += 32) w.tmask[f] = 0;
-        const int* gvert = reinterpret_cast<const int*>(rec + REC_OFF_GVERT);
+        const int* gvert = reinterpret_cast<const int*>(rec + T::OFF_GVERT);
         for (int v = lane; v < nV; v += 32) {
             d3 p = ldvert(a.m, gvert[v]);
             w.vx[v] = p.x, w.vy[v] = p.y, w.vz[v] = p.z;
             w.D[v] = dinf();
-            w.velig[v] = rec[REC_OFF_VELIG + v];
+            w.velig[v] = rec[T::OFF_VELIG + v];
             w.vdirty[v] = 0;
         }
         if (lane < K) {
-            int j = reinterpret_cast<const int*>(rec + REC_OFF_TIDX)[lane];
+            int j = reinterpret_cast<const int*>(rec + T::OFF_TIDX)[lane];
             w.tIdx[lane] = j;
-            w.tFace[lane] = rec[REC_OFF_TFACE + lane];
+            w.tFace[lane] = rec[T::OFF_TFACE + lane];
             w.tb0[lane] = a.bary[3 * j], w.tb1[lane] = a.bary[3 * j + 1], w.tb2[lane] = a.bary[3 * j + 2];
             w.tpx[lane] = a.eucl[3 * j], w.tpy[lane] = a.eucl[3 * j + 1], w.tpz[lane] = a.eucl[3 * j + 2];
             w.tbest[lane] = dinf();
@@ -329,7 +328,7 @@ __device__ int processRecord(const WinArgs& a, WinSmem& w, int li, int lane)
                 w.tbest[t] = sqrt(d.x * d.x + d.y * d.y + d.z * d.z);
                 w.tcode[t] = 1;
             } else {
-                atomicOr(reinterpret_cast<unsigned int*>(w.tmask) + (lf >> 1), (1u << t) << ((lf & 1) * 16));
+                atomicOr(&w.tmask[lf], 1u << t);
                 uchar4 tv = w.fvert[lf];
                 double px = w.tpx[t], py = w.tpy[t], pz = w.tpz[t];
                 double ax = px - w.vx[tv.x], ay = py - w.vy[tv.x], az = pz - w.vz[tv.x];
@@ -415,8 +414,8 @@ __device__ int processRecord(const WinArgs& a, WinSmem& w, int li, int lane)
                     double b0 = w.tb0[t], b1 = w.tb1[t], b2 = w.tb2[t];
                     double bA = e == 0 ? b1 : (e == 1 ? b2 : b0), bB = e == 0 ? b2 : (e == 1 ? b0 : b1), bC = e == 0 ? b0 : (e == 1 ? b1 : b2);
                     double rbs = 1.0 / (bA + bB + bC);
-                    v2 T{(bA * A.x + bB * B.x + bC * C.x) * rbs, (bA * A.y + bB * B.y + bC * C.y) * rbs};
-                    v2 d = T - S;
+                    v2 Tq{(bA * A.x + bB * B.x + bC * C.x) * rbs, (bA * A.y + bB * B.y + bC * C.y) * rbs};
+                    v2 d = Tq - S;
                     double den = cross2(AB, d);
                     if (den != 0) {
                         double mu = cross2(S - A, d) / den;
@@ -637,23 +636,25 @@ __device__ int processRecord(const WinArgs& a, WinSmem& w, int li, int lane)
 
 } // namespace
 
-__global__ void __launch_bounds__(128, 4) k_windows(WinArgs a)
+template <class T> __global__ void __launch_bounds__(128, 4) k_windows(WinArgs a)
 {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    WinSmem& w = reinterpret_cast<WinSmem*>(smemRaw)[wib];
+    WinSmem<T>& w = reinterpret_cast<WinSmem<T>*>(smemRaw)[wib];
     unsigned long long* cnt = w.wcnt;
     if (lane < 16) cnt[lane] = 0;
     __syncwarp();
+    const int nWork = a.srcList ? min(*a.srcCount, a.maxRecords) : a.nLocal;
     for (;;) {
-        int li = 0;
-        if (lane == 0) li = atomicAdd(a.workCounter, 1);
-        li = __shfl_sync(FULL, li, 0);
-        if (li >= a.nLocal) break;
-        int st = processRecord(a, w, li, lane);
+        int s = 0;
+        if (lane == 0) s = atomicAdd(a.workCounter, 1);
+        s = __shfl_sync(FULL, s, 0);
+        if (s >= nWork) break;
+        const int li = a.srcList ? a.srcList[s] : s;
+        int st = processRecord<T>(a, w, li, s, lane);
         st = __shfl_sync(FULL, st, 0);
         __syncwarp();
-        if (st != WS_OK && lane == 0) { // ring overflow: rerun on the large-capacity tiers
+        if (st != WS_OK && lane == 0) { // ring overflow: rerun on the next tier
             int r = atomicAdd(a.retryCount, 1);
             a.retryList[r] = li;
             cnt[C_TIER_RETRY]++;
@@ -664,22 +665,23 @@ __global__ void __launch_bounds__(128, 4) k_windows(WinArgs a)
     if (lane < 16 && cnt[lane]) atomicAdd(a.counters + lane, cnt[lane]);
 }
 
-size_t windowSmemPerWarp() { return sizeof(WinSmem); }
-
-cudaError_t launchWindows(cudaStream_t st, const WinArgs& a, int warpsPerBlock, int numSMs)
+template <class T> cudaError_t launchWindows(cudaStream_t st, const WinArgs& a, int warpsPerBlock, int numSMs)
 {
-    size_t smem = sizeof(WinSmem) * warpsPerBlock;
+    size_t smem = sizeof(WinSmem<T>) * warpsPerBlock;
     static int perSM[5] = {0, 0, 0, 0, 0};
-    if (warpsPerBlock < 1 || warpsPerBlock > 4) return cudaErrorInvalidConfiguration;
+    if (warpsPerBlock < 1 || warpsPerBlock > 4 || smem > 227 * 1024) return cudaErrorInvalidConfiguration;
     if (!perSM[warpsPerBlock]) {
-        cudaFuncSetAttribute(k_windows, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(k_windows<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         int n = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_windows, warpsPerBlock * 32, smem) != cudaSuccess || n < 1) n = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_windows<T>, warpsPerBlock * 32, smem) != cudaSuccess || n < 1) n = 1;
         perSM[warpsPerBlock] = n;
     }
-    int blocks = min(numSMs * perSM[warpsPerBlock], max(1, (a.nLocal + warpsPerBlock - 1) / warpsPerBlock));
-    k_windows<<<blocks, warpsPerBlock * 32, smem, st>>>(a);
+    int blocks = numSMs * perSM[warpsPerBlock];
+    if (!a.srcList) blocks = min(blocks, max(1, (a.nLocal + warpsPerBlock - 1) / warpsPerBlock));
+    k_windows<T><<<blocks, warpsPerBlock * 32, smem, st>>>(a);
     return cudaGetLastError();
 }
+template cudaError_t launchWindows<TierSmall>(cudaStream_t, const WinArgs&, int, int);
+template cudaError_t launchWindows<TierLarge>(cudaStream_t, const WinArgs&, int, int);
 
 } // namespace css

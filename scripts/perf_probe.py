@@ -15,7 +15,7 @@ from curvedspacesim_b200 import binding  # noqa: E402
 _cache = {}
 
 
-def run(workload, steps=5, label=""):
+def run(workload, steps=int(os.environ.get("PROBE_STEPS", "5")), label=""):
     if workload not in _cache:
         _cache[workload] = bench.build_workload(workload)
     V, F, corners, face, bary, vel, N, rc = _cache[workload]
@@ -29,17 +29,18 @@ def run(workload, steps=5, label=""):
     for _ in range(3):
         ctx.step_nve(kind, params, 0.01, 1)
     ctx.counters(reset=True)
-    ms, geo = [], []
+    ms, geo, stg = [], [], []
     for _ in range(steps):
         ctx.timer_record(0)
         ctx.step_nve(kind, params, 0.01, 1)
         ctx.timer_record(1)
         ms.append(ctx.timer_elapsed_ms(0, 1))
         geo.append(ctx.last_kernel_ms()["geodesic_ms"])
+        stg.append(list(ctx.last_stage_ms().values()))
     c = ctx.counters()
     ns = max(c["sources"], 1)
     out = {"label": label, "tune": os.environ.get("CSS_TUNE", ""), "workload": workload, "ms_per_step": float(np.mean(ms)),
-           "geo_ms": float(np.mean(geo)), "Mpts_per_s": N / np.mean(ms) / 1e3, "win_per_src": c["windows"] / ns, "ps_per_src": c["pseudo_sources"] / ns,
+           "geo_ms": float(np.mean(geo)), "patch_win_retry_ms": [round(float(x), 4) for x in np.mean(np.array(stg), 0)], "retry_max_ms": round(float(np.max(np.array(stg)[:, 2])), 4), "Mpts_per_s": N / np.mean(ms) / 1e3, "win_per_src": c["windows"] / ns, "ps_per_src": c["pseudo_sources"] / ns,
            "retry_frac": c["tier_retry"] / ns, "ovf": [c["ovf_candidates"], c["ovf_faces"], c["ovf_verts"], c["ovf_ring"]],
            "overflow": c["overflow"],
            "kcyc_per_src": {k: round(c[k] / ns / 1e3, 1) for k in ("clk_total", "clk_patch", "clk_prop", "clk_batch", "clk_fan")}}
