@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcurvedspacesim_b200.so")
+LIB_PATH = os.environ.get("CSS_LIB_PATH") or os.path.join(_HERE, "libcurvedspacesim_b200.so")  # env: developer variants only
 
 c_dp = C.POINTER(C.c_double)
 c_ip = C.POINTER(C.c_int32)
@@ -191,6 +191,14 @@ class Context:
         frc = np.zeros((self.n_local, 3))
         self._ck(self.L.css_get_state(self.h, _i(face), _d(bary), _d(vel), _d(frc)))
         return face, bary, vel, frc
+
+    def get_state_into(self, face=None, bary=None, vel=None, frc=None):
+        """css_get_state straight into caller-owned (e.g. pinned) arrays; any of them may be None."""
+        for a, n, dt in ((face, self.n_total, np.int32), (bary, 3 * self.n_total, np.float64), (vel, 3 * self.n_local, np.float64),
+                         (frc, 3 * self.n_local, np.float64)):
+            if a is not None and (a.dtype != dt or a.size != n or not a.flags["C_CONTIGUOUS"]):
+                raise ValueError("get_state_into: wrong dtype / size / layout")
+        self._ck(self.L.css_get_state(self.h, _i(face), _d(bary), _d(vel), _d(frc)))
 
     def set_velocities(self, vel):
         vel = np.ascontiguousarray(vel, np.float64)

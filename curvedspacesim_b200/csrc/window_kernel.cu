@@ -362,6 +362,9 @@ template <class T> __device__ int processRecord(const WinArgs& a, WinSmem<T>& w,
     __syncwarp();
 
     unsigned long long nWin = 0, nPs = 0;
+#ifdef CSS_PASS_STATS
+    unsigned nPass = 0, nPass3 = 0, nPass8 = 0;
+#endif
     for (;;) {
         // ================= drain the ring, 32 windows per pass =================
         while (head != tail) {
@@ -385,6 +388,12 @@ template <class T> __device__ int processRecord(const WinArgs& a, WinSmem<T>& w,
             const f2 fS = tof2(S);
             const float fsg = (float)sg;
             if (active && fsg + fsegDist(fS, tof2(P0), tof2(P1)) * (1.f - 1e-5f) > fUb) active = false; // bound tightened since the push
+#ifdef CSS_PASS_STATS
+            {
+                int na = __popc(__ballot_sync(FULL, active));
+                nPass++, nPass3 += na <= 3, nPass8 += na <= 8;
+            }
+#endif
             // ---- unfold the entered face: apex C from the edge frame
             int vA = 0, vB = 0, vC = 0, kkbits = 0;
             uchar4 fa = make_uchar4(REC_NONE, REC_NONE, REC_NONE, 0);
@@ -476,7 +485,11 @@ template <class T> __device__ int processRecord(const WinArgs& a, WinSmem<T>& w,
             // Xin-Wang filter and bound test in fp32 with a conservative margin: a window is dropped only when it is
             // dominated by clearly more than the rounding of the approximation.
             const f2 fA = tof2(A), fB = tof2(B), fC = tof2(C);
+#ifdef CSS_CHILD_UNROLL
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
             for (int j = 0; j < 2; ++j) {
                 const v2 X = j ? C : A, Y = j ? B : C;
                 bool valid = false;
@@ -621,6 +634,10 @@ template <class T> __device__ int processRecord(const WinArgs& a, WinSmem<T>& w,
         cnt[C_DISCONNECTED] += nDis;
         cnt[C_WINDOWS] += nWin;
         cnt[C_PSEUDO] += nPs;
+#ifdef CSS_PASS_STATS
+        atomicAdd(a.counters + C_CLK_BATCH, (unsigned long long)nPass), atomicAdd(a.counters + C_CLK_FAN, (unsigned long long)nPass3);
+        atomicAdd(a.counters + C_CLK_PROP, (unsigned long long)nPass8);
+#endif
         cnt[C_SOURCES]++;
         cnt[C_QUERIES] += K;
         cnt[C_PATCH_FACES] += nF;

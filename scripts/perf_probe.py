@@ -43,7 +43,7 @@ def run(workload, steps=int(os.environ.get("PROBE_STEPS", "5")), label=""):
            "geo_ms": float(np.mean(geo)), "patch_win_retry_ms": [round(float(x), 4) for x in np.mean(np.array(stg), 0)], "retry_max_ms": round(float(np.max(np.array(stg)[:, 2])), 4), "Mpts_per_s": N / np.mean(ms) / 1e3, "win_per_src": c["windows"] / ns, "ps_per_src": c["pseudo_sources"] / ns,
            "retry_frac": c["tier_retry"] / ns, "ovf": [c["ovf_candidates"], c["ovf_faces"], c["ovf_verts"], c["ovf_ring"]],
            "overflow": c["overflow"],
-           "kcyc_per_src": {k: round(c[k] / ns / 1e3, 1) for k in ("clk_total", "clk_patch", "clk_prop", "clk_batch", "clk_fan")}}
+           "dbg_per_src": {k: round(c[k] / ns, 3) for k in ("clk_batch", "clk_fan", "clk_prop", "clk_patch", "clk_total")}}
     print(json.dumps(out), flush=True)
     ctx.close()
 
