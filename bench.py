@@ -168,6 +168,8 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"  # the version banner goes to stdout; rank 0 must print exactly one JSON line
 
     import torch
     import torch.distributed as dist
@@ -235,7 +237,7 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
-    step_ms, geo_ms, walk_ms, cell_ms, patch_ms, win_ms, retry_ms = [], [], [], [], [], [], []
+    step_ms, geo_ms, walk_ms, cell_ms, patch_ms, win_ms, retry_ms, gather_ms = [], [], [], [], [], [], [], []
     t_wall0 = time.perf_counter()
     for _ in range(args.steps):
         flush()
@@ -253,6 +255,7 @@ def main():
         patch_ms.append(k["patch_ms"])
         win_ms.append(k["window_ms"])
         retry_ms.append(k["retry_ms"])
+        gather_ms.append(k["gather_ms"])
     barrier()
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.stop()
@@ -353,7 +356,8 @@ def main():
             "value_hot_l2": N * args.steps / (hot_ms * 1e-3), "ms_per_step_hot_l2": hot_ms / args.steps,
             "wall_s_timed_region": t_wall,
             "phase_ms_per_step": {"walk": float(np.mean(walk_ms)), "celllist": float(np.mean(cell_ms)), "geodesic_force": float(np.mean(geo_ms)),
-                                  "patch_records": float(np.mean(patch_ms)), "window_propagation": float(np.mean(win_ms))},
+                                  "patch_records": float(np.mean(patch_ms)), "window_propagation": float(np.mean(win_ms)),
+                                  "position_allgather": float(np.mean(gather_ms))},
             "patch_mean": {"faces": pf, "verts": pv, "K": kq, "windows_per_source": cnt["windows"] / ns, "tier_retry_frac": cnt["tier_retry"] / ns},
             "flags": {k: cnt[k] for k in ("walk_vertex", "walk_nohit", "walk_itercap", "walk_nan", "walk_border", "disconnected", "overflow")},
             "clocks": clocks,

@@ -315,9 +315,9 @@ class Context:
         return {"geodesic_ms": g.value, "walk_ms": w.value, "celllist_ms": c.value}
 
     def last_stage_ms(self):
-        p, w, r = C.c_float(), C.c_float(), C.c_float()
-        self._ck(self.L.css_last_stage_ms(self.h, C.byref(p), C.byref(w), C.byref(r)))
-        return {"patch_ms": p.value, "window_ms": w.value, "retry_ms": r.value}
+        p, w, r, g = C.c_float(), C.c_float(), C.c_float(), C.c_float()
+        self._ck(self.L.css_last_stage_ms(self.h, C.byref(p), C.byref(w), C.byref(r), C.byref(g)))
+        return {"patch_ms": p.value, "window_ms": w.value, "retry_ms": r.value, "gather_ms": g.value}
 
     def timer_record(self, slot):
         self._ck(self.L.css_timer_record(self.h, int(slot)))

@@ -92,6 +92,12 @@ struct css_ctx {
     double* d_recvD = nullptr;
     int capComm = 0;
     double* d_redBuf = nullptr;
+    // CUDA graph of one fused NVE step (walker, gather, cell list, stages 1-2, retry tiers): one launch per step
+    bool useGraph = true, capturing = false;
+    cudaGraphExec_t nveExec = nullptr;
+    uint64_t nveKey = 0;
+    unsigned long long nveKernels = 0;
+    int nveCalls = 0;
     // timing
     bool timing = false;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -99,6 +105,9 @@ struct css_ctx {
     cudaEvent_t evS[4] = {nullptr, nullptr, nullptr, nullptr}; // stage boundaries inside the geodesic phase
     cudaEvent_t tev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
+
+// event record that stays a real, queryable event when the stream is being captured into a CUDA graph
+static void recordEvent(css_ctx* c, cudaEvent_t e);
 
 static int fail(css_ctx* c, int code, const char* fmt, ...)
 {
@@ -127,6 +136,12 @@ template <class T> static cudaError_t regrow(T*& p, size_t n)
     if (p) cudaFree(p);
     p = nullptr;
     return cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T));
+}
+
+static void recordEvent(css_ctx* c, cudaEvent_t e)
+{
+    if (c->capturing) cudaEventRecordWithFlags(e, c->st, cudaEventRecordExternal);
+    else cudaEventRecord(e, c->st);
 }
 
 #pragma GCC visibility push(default)
@@ -165,6 +180,7 @@ int css_create(css_ctx** out, int device)
     }
     for (auto& e : ctx->tev) cudaEventCreate(&e);
     if (const char* v = getenv("CSS_LEGACY_TIER0")) ctx->twoStage = atoi(v) == 0; // developer switch: fused one-kernel tier 0
+    if (const char* v = getenv("CSS_NO_GRAPH")) ctx->useGraph = atoi(v) == 0;
     if (const char* v = getenv("CSS_WIN_WPB")) ctx->winWpb = std::max(1, std::min(4, atoi(v)));
     *out = ctx;
     return CSS_OK;
@@ -175,6 +191,7 @@ int css_destroy(css_ctx* ctx)
     if (!ctx) return CSS_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->st);
+    if (ctx->nveExec) cudaGraphExecDestroy(ctx->nveExec);
     if (ctx->comm) ncclCommDestroy(ctx->comm);
     void* ptrs[] = {ctx->d_vert,   ctx->d_corner,    ctx->d_adj,     ctx->d_saddle,  ctx->d_face,     ctx->d_bary,    ctx->d_eucl,
                     ctx->d_vel,    ctx->d_frc,       ctx->d_disp,    ctx->d_walkFlags, ctx->d_cellOf, ctx->d_cellCount, ctx->d_cellStart,
@@ -284,6 +301,7 @@ int css_set_mesh(css_ctx* ctx, int nV, const double* xyz, int nF, const int32_t*
     ctx->nV = nV;
     ctx->nF = nF;
     ctx->nbrValid = false;
+    ctx->nveCalls = 0;
     // last-resort tier: the whole mesh fits (local ids are 16 bit)
     int mf = std::min(nF, 65534), mv = std::min(nV, 65534);
     auto p2 = [](int x) {
@@ -309,6 +327,7 @@ int css_mesh_info(css_ctx* ctx, double bbmin[3], double bbmax[3], double* area)
 int css_set_submeshing(css_ctx* ctx, int enabled, double maxDist)
 {
     if (!ctx) return CSS_EINVAL;
+    ctx->nveCalls = 0;
     ctx->submeshing = enabled != 0;
     ctx->maxDist = maxDist;
     ctx->nbrValid = false;
@@ -319,11 +338,13 @@ int css_set_cell_domain(css_ctx* ctx, const double mn[3], const double mx[3])
     if (!ctx || !mn || !mx) return CSS_EINVAL;
     for (int d = 0; d < 3; ++d) ctx->cellMin[d] = mn[d], ctx->cellMax[d] = mx[d];
     ctx->gridRange = -1;
+    ctx->nveCalls = 0;
     return CSS_OK;
 }
 int css_set_options(css_ctx* ctx, int useCellList, int wantEndTangents)
 {
     if (!ctx) return CSS_EINVAL;
+    ctx->nveCalls = 0;
     ctx->useCellList = useCellList != 0;
     ctx->wantEnd = wantEndTangents != 0;
     ctx->nbrValid = false;
@@ -446,11 +467,11 @@ static int runGeodesicTiers(css_ctx* ctx, GeoArgs a, int nSrc)
         p.workCounter = ctx->d_work + 0, p.retryList = ctx->d_retry[0], p.retryCount = ctx->d_work + 4, p.records = ctx->d_records;
         w.srcList = nullptr, w.srcCount = nullptr, w.maxRecords = p.maxRecords;
         w.workCounter = ctx->d_work + 3, w.retryList = ctx->d_retry[0], w.retryCount = ctx->d_work + 4, w.records = ctx->d_records;
-        if (ctx->timing) cudaEventRecord(ctx->evS[0], ctx->st);
+        if (ctx->timing) recordEvent(ctx, ctx->evS[0]);
         CU(launchPatch<TierSmall>(ctx->st, p, ctx->numSMs));
-        if (ctx->timing) cudaEventRecord(ctx->evS[1], ctx->st);
+        if (ctx->timing) recordEvent(ctx, ctx->evS[1]);
         CU(launchWindows<TierSmall>(ctx->st, w, ctx->winWpb, ctx->numSMs));
-        if (ctx->timing) cudaEventRecord(ctx->evS[2], ctx->st);
+        if (ctx->timing) recordEvent(ctx, ctx->evS[2]);
         // tier 1 (work list = tier 0's retry list; its length is only known on the device)
         p.srcList = ctx->d_retry[0], p.srcCount = ctx->d_work + 4, p.maxRecords = maxLarge;
         p.workCounter = ctx->d_work + 1, p.retryList = ctx->d_retry[1], p.retryCount = ctx->d_work + 5, p.records = ctx->d_recordsL;
@@ -594,6 +615,7 @@ int css_set_state(css_ctx* ctx, int nLocal, int nTotal, int minIdx, const int32_
         if (face[i] < 0 || face[i] >= ctx->nF) return fail(ctx, CSS_EINVAL, "css_set_state: face index %d out of range", face[i]);
     int rc = ensureParticles(ctx, nLocal, nTotal);
     if (rc) return rc;
+    if (nLocal != ctx->nLocal || nTotal != ctx->nTotal || minIdx != ctx->minIdx) ctx->nveCalls = 0; // buffers get re-sized by plain steps first
     ctx->nLocal = nLocal, ctx->nTotal = nTotal, ctx->minIdx = minIdx;
     CU(cudaMemcpyAsync(ctx->d_face, face, sizeof(int) * nTotal, cudaMemcpyHostToDevice, ctx->st));
     CU(cudaMemcpyAsync(ctx->d_bary, bary, sizeof(double) * 3 * nTotal, cudaMemcpyHostToDevice, ctx->st));
@@ -667,7 +689,7 @@ static int findNeighborsImpl(css_ctx* ctx, double range, int forceMode, ForcePar
     if (!ctx->nTotal) return fail(ctx, CSS_ESTATE, "state not set");
     int rc;
     MeshDev m = meshDev(ctx);
-    if (ctx->timing) cudaEventRecord(ctx->ev[0], ctx->st);
+    if (ctx->timing) recordEvent(ctx, ctx->ev[0]);
     if (ctx->useCellList) {
         if ((rc = setupGrid(ctx, range))) return rc;
         CU(cudaMemsetAsync(ctx->d_cellCount, 0, sizeof(int) * ((size_t)ctx->nCells + 1), ctx->st));
@@ -683,7 +705,7 @@ static int findNeighborsImpl(css_ctx* ctx, double range, int forceMode, ForcePar
             ctx->capNbr = 0;
         }
     }
-    if (ctx->timing) cudaEventRecord(ctx->ev[1], ctx->st);
+    if (ctx->timing) recordEvent(ctx, ctx->ev[1]);
     if ((rc = ensureNeighbors(ctx))) return rc;
     GeoArgs a{};
     a.m = m;
@@ -700,7 +722,7 @@ static int findNeighborsImpl(css_ctx* ctx, double range, int forceMode, ForcePar
     a.forceMode = forceMode, a.fp = fp, a.zero = zero, a.frc = ctx->d_frc, a.kick = kick, a.vel = ctx->d_vel;
     a.counters = ctx->d_counters;
     if ((rc = runGeodesicTiers(ctx, a, ctx->nLocal))) return rc;
-    if (ctx->timing) cudaEventRecord(ctx->ev[2], ctx->st);
+    if (ctx->timing) recordEvent(ctx, ctx->ev[2]);
     ctx->nbrValid = true;
     return CSS_OK;
 }
@@ -716,6 +738,7 @@ static int checkCapacity(css_ctx* ctx, bool* rerun)
         CU(cudaMemsetAsync(ctx->d_counters + C_KMAX_OVERFLOW, 0, sizeof(unsigned long long), ctx->st));
         ctx->kmax *= 2;
         ctx->capNbr = 0;
+        ctx->nveCalls = 0;
         if (rerun) *rerun = true;
         else return fail(ctx, CSS_ECAPACITY, "neighbour stride exceeded during a fused step; stride doubled, rerun");
     }
@@ -844,11 +867,11 @@ int css_compute_energy(css_ctx* ctx, int kind, const double* params, double* ene
 
 static int moveImpl(css_ctx* ctx, int transportForce, int transportVelocity, int mode, double dt)
 {
-    if (ctx->timing) cudaEventRecord(ctx->ev[3], ctx->st);
+    if (ctx->timing) recordEvent(ctx, ctx->ev[3]);
     launchWalk(ctx->st, meshDev(ctx), ctx->nLocal, ctx->minIdx, ctx->d_face, ctx->d_bary, ctx->d_disp, ctx->d_vel, ctx->d_frc, transportForce,
                transportVelocity, mode, dt, ctx->d_walkFlags, ctx->d_counters);
     ctx->hostKernels++;
-    if (ctx->timing) cudaEventRecord(ctx->ev[4], ctx->st);
+    if (ctx->timing) recordEvent(ctx, ctx->ev[4]);
     ctx->nbrValid = false;
     if (ctx->nranks > 1) return css_gather_positions(ctx);
     return CSS_OK;
@@ -874,6 +897,35 @@ int css_get_walk_flags(css_ctx* ctx, int32_t* flags)
 }
 
 // ---------------------------------------------------------------------------------------- updaters
+static int nveStepLaunches(css_ctx* ctx, const ForceParams& fp, double range, double dt)
+{
+    // first half step fused into the walker; second half kick fused into the geodesic/force kernel
+    int rc = moveImpl(ctx, 0, 1, 1, dt);
+    if (rc) return rc;
+    return findNeighborsImpl(ctx, range, 1, fp, 1, 0.5 * dt);
+}
+
+// everything that decides what the captured launches look like: a change of any of these re-captures the graph
+static uint64_t nveGraphKey(css_ctx* ctx, const ForceParams& fp, double range, double dt)
+{
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&](const void* p, size_t n) {
+        const unsigned char* b = (const unsigned char*)p;
+        for (size_t i = 0; i < n; ++i) h = (h ^ b[i]) * 1099511628211ull;
+    };
+#define MIX(x) mix(&(x), sizeof(x))
+    MIX(fp.kind), MIX(fp.a), MIX(fp.sigma), MIX(range), MIX(dt);
+    MIX(ctx->nLocal), MIX(ctx->nTotal), MIX(ctx->minIdx), MIX(ctx->kmax), MIX(ctx->nranks), MIX(ctx->timing), MIX(ctx->submeshing),
+        MIX(ctx->maxDist), MIX(ctx->useCellList), MIX(ctx->wantEnd), MIX(ctx->twoStage), MIX(ctx->winWpb), MIX(ctx->grid), MIX(ctx->nCells);
+    void* ptrs[] = {ctx->d_vert, ctx->d_corner, ctx->d_adj, ctx->d_geo, ctx->d_saddle, ctx->d_face, ctx->d_bary, ctx->d_eucl, ctx->d_vel, ctx->d_frc,
+                    ctx->d_disp, ctx->d_walkFlags, ctx->d_cellOf, ctx->d_cellCount, ctx->d_cellStart, ctx->d_blockSums, ctx->d_fill, ctx->d_tmpItems,
+                    ctx->d_items, ctx->d_nbrCount, ctx->d_nbrIdx, ctx->d_nbrDist, ctx->d_nbrTs, ctx->d_nbrTe, ctx->d_retry[0], ctx->d_retry[1],
+                    ctx->d_retry[2], ctx->d_gws, ctx->d_records, ctx->d_recordsL, ctx->d_recvI, ctx->d_recvD, (void*)ctx->comm};
+    MIX(ptrs);
+#undef MIX
+    return h ? h : 1;
+}
+
 int css_step_nve(css_ctx* ctx, int kind, const double* params, double dt, int nsteps)
 {
     if (!ctx || !params) return CSS_EINVAL;
@@ -881,13 +933,60 @@ int css_step_nve(css_ctx* ctx, int kind, const double* params, double dt, int ns
     BIND();
     double range;
     ForceParams fp = mkForce(kind, params, &range);
-    for (int s = 0; s < nsteps; ++s) {
-        // first half step fused into the walker; second half kick fused into the geodesic/force kernel
-        int rc = moveImpl(ctx, 0, 1, 1, dt);
-        if (rc) return rc;
-        if ((rc = findNeighborsImpl(ctx, range, 1, fp, 1, 0.5 * dt))) return rc;
+    int rc = CSS_OK;
+    for (int s = 0; s < nsteps && !rc; ++s) {
+        // The first two steps of a configuration run as plain launches (they size every buffer); after that the
+        // step is replayed from a CUDA graph as long as nothing it captured has changed.
+        uint64_t key = ctx->useGraph && ctx->nveCalls >= 2 ? nveGraphKey(ctx, fp, range, dt) : 0;
+        if (key && key == ctx->nveKey && ctx->nveExec) {
+            CU(cudaGraphLaunch(ctx->nveExec, ctx->st));
+            ctx->hostKernels += ctx->nveKernels;
+            ctx->nbrValid = true;
+            continue;
+        }
+        if (key) {
+            if (ctx->nveExec) cudaGraphExecDestroy(ctx->nveExec);
+            ctx->nveExec = nullptr, ctx->nveKey = 0;
+            unsigned long long k0 = ctx->hostKernels;
+            cudaGraph_t g = nullptr;
+            CU(cudaStreamBeginCapture(ctx->st, cudaStreamCaptureModeRelaxed));
+            ctx->capturing = true;
+            rc = nveStepLaunches(ctx, fp, range, dt);
+            ctx->capturing = false;
+            cudaError_t ce = cudaStreamEndCapture(ctx->st, &g);
+            ctx->hostKernels = k0;
+            bool same = rc == CSS_OK && ce == cudaSuccess && g && nveGraphKey(ctx, fp, range, dt) == key; // nothing was re-allocated meanwhile
+            if (same && cudaGraphInstantiate(&ctx->nveExec, g, 0) == cudaSuccess) {
+                ctx->nveKey = key;
+                ctx->nveKernels = 0;
+                size_t nn = 0;
+                if (cudaGraphGetNodes(g, nullptr, &nn) == cudaSuccess) {
+                    std::vector<cudaGraphNode_t> nodes(nn);
+                    cudaGraphGetNodes(g, nodes.data(), &nn);
+                    for (auto nd : nodes) {
+                        cudaGraphNodeType t;
+                        if (cudaGraphNodeGetType(nd, &t) == cudaSuccess && t == cudaGraphNodeTypeKernel) ctx->nveKernels++;
+                    }
+                }
+            } else {
+                (void)cudaGetLastError();
+                ctx->nveExec = nullptr;
+            }
+            if (g) cudaGraphDestroy(g);
+            rc = CSS_OK;
+            if (ctx->nveExec) {
+                CU(cudaGraphLaunch(ctx->nveExec, ctx->st));
+                ctx->hostKernels += ctx->nveKernels;
+                ctx->nbrValid = true;
+                continue;
+            }
+            ctx->useGraph = false; // capture is not possible in this configuration: plain launches from now on
+        }
+        rc = nveStepLaunches(ctx, fp, range, dt);
+        ctx->nveCalls++;
     }
-    int rc = checkCapacity(ctx, nullptr);
+    if (rc) return rc;
+    rc = checkCapacity(ctx, nullptr);
     if (ctx->timing && nsteps > 0) {
         cudaEventElapsedTime(&ctx->msCell, ctx->ev[0], ctx->ev[1]);
         cudaEventElapsedTime(&ctx->msGeo, ctx->ev[1], ctx->ev[2]);
@@ -1111,6 +1210,7 @@ int css_comm_init(css_ctx* ctx, int rank, int nranks, const void* id128)
     if (!ctx || nranks < 1 || rank < 0 || rank >= nranks) return CSS_EINVAL;
     BIND();
     ctx->rank = rank, ctx->nranks = nranks;
+    ctx->nveCalls = 0;
     if (nranks == 1) return CSS_OK;
     if (!id128) return CSS_EINVAL;
     ncclUniqueId id;
@@ -1128,13 +1228,20 @@ int css_gather_positions(css_ctx* ctx)
     BIND();
     int per = (ctx->nTotal + ctx->nranks - 1) / ctx->nranks;
     if (ctx->minIdx != ctx->rank * per) return fail(ctx, CSS_EINVAL, "sharding does not follow mpiModel::determineIndexBounds");
+    if (per * ctx->nranks == ctx->nTotal) { // equal blocks: gather in place, no scratch and no copies
+        NC(ncclGroupStart());
+        NC(ncclAllGather(ctx->d_face + ctx->minIdx, ctx->d_face, per, ncclInt32, ctx->comm, ctx->st));
+        NC(ncclAllGather(ctx->d_bary + 3 * (size_t)ctx->minIdx, ctx->d_bary, 3 * (size_t)per, ncclFloat64, ctx->comm, ctx->st));
+        NC(ncclGroupEnd());
+        return CSS_OK;
+    }
+    // the replicated arrays are already laid out rank-block by rank-block; only the last block is short,
+    // so gather into padded scratch and copy back the first nTotal entries
     if (per > ctx->capComm) {
         CU(regrow(ctx->d_recvI, (size_t)per * ctx->nranks));
         CU(regrow(ctx->d_recvD, 3 * (size_t)per * ctx->nranks));
         ctx->capComm = per;
     }
-    // the replicated arrays are already laid out rank-block by rank-block; only the last block is short,
-    // so gather into padded scratch and copy back the first nTotal entries
     NC(ncclGroupStart());
     NC(ncclAllGather(ctx->d_face + ctx->minIdx, ctx->d_recvI, per, ncclInt32, ctx->comm, ctx->st));
     NC(ncclAllGather(ctx->d_bary + 3 * (size_t)ctx->minIdx, ctx->d_recvD, 3 * (size_t)per, ncclFloat64, ctx->comm, ctx->st));
@@ -1200,6 +1307,7 @@ int css_device_positions(css_ctx* ctx, void** face_dev, void** bary_dev)
 int css_set_timing(css_ctx* ctx, int enabled)
 {
     if (!ctx) return CSS_EINVAL;
+    if ((enabled != 0) != ctx->timing) ctx->nveCalls = 0;
     ctx->timing = enabled != 0;
     return CSS_OK;
 }
@@ -1212,7 +1320,7 @@ int css_last_kernel_ms(css_ctx* ctx, float* geodesic_ms, float* walk_ms, float* 
     return CSS_OK;
 }
 
-int css_last_stage_ms(css_ctx* ctx, float* patch_ms, float* window_ms, float* retry_ms)
+int css_last_stage_ms(css_ctx* ctx, float* patch_ms, float* window_ms, float* retry_ms, float* gather_ms)
 {
     if (!ctx) return CSS_EINVAL;
     if (!ctx->timing || !ctx->twoStage) return fail(ctx, CSS_ESTATE, "stage timing needs css_set_timing(1) and the two-stage path");
@@ -1225,6 +1333,11 @@ int css_last_stage_ms(css_ctx* ctx, float* patch_ms, float* window_ms, float* re
     if (patch_ms) *patch_ms = a;
     if (window_ms) *window_ms = b;
     if (retry_ms) *retry_ms = c;
+    if (gather_ms) { // walker end -> start of the neighbour phase: the position all-gather (0 on one rank)
+        float g = 0;
+        if (cudaEventElapsedTime(&g, ctx->ev[4], ctx->ev[0]) != cudaSuccess) g = 0, (void)cudaGetLastError();
+        *gather_ms = g;
+    }
     return CSS_OK;
 }
 

@@ -147,8 +147,9 @@ int css_device_positions(css_ctx* ctx, void** face_dev, void** bary_dev);
 /* timing of the last css_find_neighbors/compute_forces geodesic kernel, measured with CUDA events on the ctx stream */
 int css_last_kernel_ms(css_ctx* ctx, float* geodesic_ms, float* walk_ms, float* celllist_ms);
 int css_set_timing(css_ctx* ctx, int enabled);
-/* split of the last geodesic phase: stage 1 (patch records), stage 2 (window propagation + forces), retry tiers */
-int css_last_stage_ms(css_ctx* ctx, float* patch_ms, float* window_ms, float* retry_ms);
+/* split of the last geodesic phase: stage 1 (patch records), stage 2 (window propagation + forces), retry tiers;
+ * gather_ms = the position all-gather between the walker and the neighbour phase of the last fused step */
+int css_last_stage_ms(css_ctx* ctx, float* patch_ms, float* window_ms, float* retry_ms, float* gather_ms);
 /* CUDA-event stopwatch on the context's own stream (slots 0..7) */
 int css_timer_record(css_ctx* ctx, int slot);
 int css_timer_elapsed_ms(css_ctx* ctx, int slotA, int slotB, float* ms); /* synchronises on slotB */

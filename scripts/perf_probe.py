@@ -36,7 +36,7 @@ def run(workload, steps=int(os.environ.get("PROBE_STEPS", "5")), label=""):
         ctx.timer_record(1)
         ms.append(ctx.timer_elapsed_ms(0, 1))
         geo.append(ctx.last_kernel_ms()["geodesic_ms"])
-        stg.append(list(ctx.last_stage_ms().values()))
+        stg.append(list(ctx.last_stage_ms().values())[:3])
     c = ctx.counters()
     ns = max(c["sources"], 1)
     out = {"label": label, "tune": os.environ.get("CSS_TUNE", ""), "workload": workload, "ms_per_step": float(np.mean(ms)),
