@@ -60,7 +60,7 @@ struct css_ctx {
     int t2Warps = 32;
     int wpb0 = 4, wpb1 = 1;
     // two-stage tier 0: patch records (stage 1) -> window propagation (stage 2)
-    bool twoStage = true;
+    bool twoStage = true, winLean = true;
     int winWpb = 2;
     unsigned char *d_records = nullptr, *d_recordsL = nullptr;
     size_t capRecords = 0, capRecordsL = 0;
@@ -181,6 +181,7 @@ int css_create(css_ctx** out, int device)
     for (auto& e : ctx->tev) cudaEventCreate(&e);
     if (const char* v = getenv("CSS_LEGACY_TIER0")) ctx->twoStage = atoi(v) == 0; // developer switch: fused one-kernel tier 0
     if (const char* v = getenv("CSS_NO_GRAPH")) ctx->useGraph = atoi(v) == 0;
+    if (const char* v = getenv("CSS_WIN_LEAN")) ctx->winLean = atoi(v) != 0;
     if (const char* v = getenv("CSS_WIN_WPB")) ctx->winWpb = std::max(1, std::min(4, atoi(v)));
     *out = ctx;
     return CSS_OK;
@@ -470,7 +471,7 @@ static int runGeodesicTiers(css_ctx* ctx, GeoArgs a, int nSrc)
         if (ctx->timing) recordEvent(ctx, ctx->evS[0]);
         CU(launchPatch<TierSmall>(ctx->st, p, ctx->numSMs));
         if (ctx->timing) recordEvent(ctx, ctx->evS[1]);
-        CU(launchWindows<TierSmall>(ctx->st, w, ctx->winWpb, ctx->numSMs));
+        CU(launchWindows<TierSmall>(ctx->st, w, ctx->winWpb, ctx->numSMs, ctx->winLean));
         if (ctx->timing) recordEvent(ctx, ctx->evS[2]);
         // tier 1 (work list = tier 0's retry list; its length is only known on the device)
         p.srcList = ctx->d_retry[0], p.srcCount = ctx->d_work + 4, p.maxRecords = maxLarge;
@@ -478,7 +479,7 @@ static int runGeodesicTiers(css_ctx* ctx, GeoArgs a, int nSrc)
         w.srcList = p.srcList, w.srcCount = p.srcCount, w.maxRecords = maxLarge;
         w.workCounter = ctx->d_work + 7, w.retryList = ctx->d_retry[1], w.retryCount = ctx->d_work + 5, w.records = ctx->d_recordsL;
         CU(launchPatch<TierLarge>(ctx->st, p, ctx->numSMs));
-        CU(launchWindows<TierLarge>(ctx->st, w, 1, ctx->numSMs));
+        CU(launchWindows<TierLarge>(ctx->st, w, 1, ctx->numSMs, false));
         ctx->hostKernels += 4;
     } else {
         // fused tier 0 (explicit css_distance queries, all-to-all candidates, developer switch): shared memory
@@ -916,7 +917,7 @@ static uint64_t nveGraphKey(css_ctx* ctx, const ForceParams& fp, double range, d
 #define MIX(x) mix(&(x), sizeof(x))
     MIX(fp.kind), MIX(fp.a), MIX(fp.sigma), MIX(range), MIX(dt);
     MIX(ctx->nLocal), MIX(ctx->nTotal), MIX(ctx->minIdx), MIX(ctx->kmax), MIX(ctx->nranks), MIX(ctx->timing), MIX(ctx->submeshing),
-        MIX(ctx->maxDist), MIX(ctx->useCellList), MIX(ctx->wantEnd), MIX(ctx->twoStage), MIX(ctx->winWpb), MIX(ctx->grid), MIX(ctx->nCells);
+        MIX(ctx->maxDist), MIX(ctx->useCellList), MIX(ctx->wantEnd), MIX(ctx->twoStage), MIX(ctx->winWpb), MIX(ctx->winLean), MIX(ctx->grid), MIX(ctx->nCells);
     void* ptrs[] = {ctx->d_vert, ctx->d_corner, ctx->d_adj, ctx->d_geo, ctx->d_saddle, ctx->d_face, ctx->d_bary, ctx->d_eucl, ctx->d_vel, ctx->d_frc,
                     ctx->d_disp, ctx->d_walkFlags, ctx->d_cellOf, ctx->d_cellCount, ctx->d_cellStart, ctx->d_blockSums, ctx->d_fill, ctx->d_tmpItems,
                     ctx->d_items, ctx->d_nbrCount, ctx->d_nbrIdx, ctx->d_nbrDist, ctx->d_nbrTs, ctx->d_nbrTe, ctx->d_retry[0], ctx->d_retry[1],

@@ -31,11 +31,16 @@ constexpr unsigned char NOPSV = 255;
 
 __device__ __forceinline__ double dinf() { return __longlong_as_double(0x7ff0000000000000LL); }
 
-template <class T> struct WinSmem { // per-warp workspace (15.9 KB for TierSmall)
+// LEAN = true: edge frames and vertex positions are not staged; the kernel reads them from global memory (L2-resident)
+// through the local->global maps.  10.4 KB instead of 15.9 KB per warp for TierSmall -> 20 instead of 14 warps per SM.
+template <class T, bool LEAN> struct WinSmem { // per-warp workspace
     static constexpr int F = T::MAXF, V = T::MAXV, K = T::MAXK, R = T::RING;
-    double2 geo[3 * F];
-    double vx[V], vy[V], vz[V], D[V], dirx[V], diry[V];
-    double rax[R], ray[R], rbx[R], rby[R], rsx[R], rsy[R], rt0[R], rt1[R], rsg[R];
+    static constexpr bool lean = LEAN;
+    double2 geo[LEAN ? 1 : 3 * F];
+    double vx[LEAN ? 1 : V], vy[LEAN ? 1 : V], vz[LEAN ? 1 : V];
+    int gface[LEAN ? F : 1], gvert[LEAN ? V : 1];
+    double D[V], dirx[V], diry[V];
+    double rax[R], ray[R], rbx[R], rby[R], rt0[R], rt1[R]; // ring: the (pseudo-)source image and sigma follow from rpsv
     double tbest[K], tb0[K], tb1[K], tb2[K], tsx[K], tsy[K], tdu[K], tdw[K];
     double tpx[K], tpy[K], tpz[K], tcd0[K], tcd1[K], tcd2[K];
     double root[6];
@@ -140,27 +145,38 @@ __device__ __forceinline__ d3 pairForce(const ForceParams& fp, const d3& sep, do
     return d3{-pre * sep.x, -pre * sep.y, -pre * sep.z};
 }
 
+template <class W> __device__ __forceinline__ d3 vpos(const MeshDev& m, const W& w, int v)
+{
+    if constexpr (W::lean) return ldvert(m, w.gvert[v]);
+    else return d3{w.vx[v], w.vy[v], w.vz[v]};
+}
+template <class W> __device__ __forceinline__ double2 edgeFrame(const MeshDev& m, const W& w, int g, int e)
+{
+    if constexpr (W::lean) return __ldg(m.geo + 3 * (size_t)w.gface[g] + e);
+    else return w.geo[3 * g + e];
+}
+
 // push up to one window per lane; returns false when the ring would overflow
-template <class W> __device__ __forceinline__ bool pushWindows(W& w, int lane, int head, int& tail, bool valid, const v2& A, const v2& B, const v2& S,
-                                            double t0, double t1, double sg, int meta, unsigned char psv)
+template <class W> __device__ __forceinline__ bool pushWindows(W& w, int lane, int head, int& tail, bool valid, const v2& A, const v2& B,
+                                            double t0, double t1, int meta, unsigned char psv)
 {
     unsigned bal = __ballot_sync(FULL, valid);
     int tot = __popc(bal);
     if (tail + tot - head > W::R) return false;
     if (valid) {
         int q = (tail + __popc(bal & ((1u << lane) - 1))) & (W::R - 1);
-        w.rax[q] = A.x, w.ray[q] = A.y, w.rbx[q] = B.x, w.rby[q] = B.y, w.rsx[q] = S.x, w.rsy[q] = S.y;
-        w.rt0[q] = t0, w.rt1[q] = t1, w.rsg[q] = sg, w.rmeta[q] = meta, w.rpsv[q] = psv;
+        w.rax[q] = A.x, w.ray[q] = A.y, w.rbx[q] = B.x, w.rby[q] = B.y;
+        w.rt0[q] = t0, w.rt1[q] = t1, w.rmeta[q] = meta, w.rpsv[q] = psv;
     }
     tail += tot;
     return true;
 }
 
 // pseudo-source fan of vertex pv (rare: kept out of line to keep the propagation loop compact)
-template <class W> __device__ __noinline__ bool spawnFan(W& w, int lane, int nF, int pv, float fUb, int head, int& tail)
+template <class W> __device__ __noinline__ bool spawnFan(const MeshDev& m, W& w, int lane, int nF, int pv, float fUb, int head, int& tail)
 {
     const double Dv = w.D[pv];
-    const d3 Pv{w.vx[pv], w.vy[pv], w.vz[pv]};
+    const d3 Pv = vpos(m, w, pv);
     const double dvx = w.dirx[pv], dvy = w.diry[pv];
     bool ok = true;
     for (int f0 = 0; f0 < nF; f0 += 32) {
@@ -173,7 +189,8 @@ template <class W> __device__ __noinline__ bool spawnFan(W& w, int lane, int nF,
             int i = fv.x == pv ? 0 : (fv.y == pv ? 1 : (fv.z == pv ? 2 : -1));
             if (i >= 0) {
                 int vp = i == 0 ? fv.y : (i == 1 ? fv.z : fv.x), vq = i == 0 ? fv.z : (i == 1 ? fv.x : fv.y);
-                d3 ep{w.vx[vp] - Pv.x, w.vy[vp] - Pv.y, w.vz[vp] - Pv.z}, eq{w.vx[vq] - Pv.x, w.vy[vq] - Pv.y, w.vz[vq] - Pv.z};
+                const d3 Pp = vpos(m, w, vp), Pq = vpos(m, w, vq);
+                d3 ep{Pp.x - Pv.x, Pp.y - Pv.y, Pp.z - Pv.z}, eq{Pq.x - Pv.x, Pq.y - Pv.y, Pq.z - Pv.z};
                 double lp = fsqrt(ep.x * ep.x + ep.y * ep.y + ep.z * ep.z), lq = fsqrt(eq.x * eq.x + eq.y * eq.y + eq.z * eq.z);
                 if (atomicMinD(&w.D[vp], Dv + lp)) w.vdirty[vp] = 2; // edge paths
                 if (atomicMinD(&w.D[vq], Dv + lq)) w.vdirty[vq] = 2;
@@ -206,21 +223,21 @@ template <class W> __device__ __noinline__ bool spawnFan(W& w, int lane, int nF,
             if (w.vdirty[fv.y] == 2) w.vdirty[fv.y] = 1;
             if (w.vdirty[fv.z] == 2) w.vdirty[fv.z] = 1;
         }
-        if (ok) ok = pushWindows(w, lane, head, tail, valid, A, B, v2{0, 0}, 0.0, 1.0, Dv, meta, (unsigned char)pv);
+        if (ok) ok = pushWindows(w, lane, head, tail, valid, A, B, 0.0, 1.0, meta, (unsigned char)pv);
         __syncwarp();
     }
     return ok;
 }
 
 // 3-D unit end tangent of a path that enters face g through edge e with direction (du, dw) in that edge's frame
-template <class W> __device__ __noinline__ d3 liftEnd(const W& w, int g, int e, double du, double dw)
+template <class W> __device__ __noinline__ d3 liftEnd(const MeshDev& m, const W& w, int g, int e, double du, double dw)
 {
     uchar4 fv = w.fvert[g];
     int c0 = fv.x, c1 = fv.y, c2 = fv.z;
     int vA = e == 0 ? c1 : (e == 1 ? c2 : c0), vB = e == 0 ? c2 : (e == 1 ? c0 : c1), vC = e == 0 ? c0 : (e == 1 ? c1 : c2);
-    double PAx = w.vx[vA], PAy = w.vy[vA], PAz = w.vz[vA];
-    double abx = w.vx[vB] - PAx, aby = w.vy[vB] - PAy, abz = w.vz[vB] - PAz;
-    double acx = w.vx[vC] - PAx, acy = w.vy[vC] - PAy, acz = w.vz[vC] - PAz;
+    const d3 PA = vpos(m, w, vA), PB = vpos(m, w, vB), PC = vpos(m, w, vC);
+    double abx = PB.x - PA.x, aby = PB.y - PA.y, abz = PB.z - PA.z;
+    double acx = PC.x - PA.x, acy = PC.y - PA.y, acz = PC.z - PA.z;
     double L3 = sqrt(abx * abx + aby * aby + abz * abz);
     double Ux = abx / L3, Uy = aby / L3, Uz = abz / L3;
     double cx = acx * Ux + acy * Uy + acz * Uz;
@@ -234,7 +251,7 @@ template <class W> __device__ __noinline__ d3 liftEnd(const W& w, int g, int e, 
 
 enum { WS_OK = 0, WS_RING = 1 };
 
-template <class T> __device__ int processRecord(const WinArgs& a, WinSmem<T>& w, int li, int rslot, int lane)
+template <class T, bool LEAN> __device__ int processRecord(const WinArgs& a, WinSmem<T, LEAN>& w, int li, int rslot, int lane)
 {
     constexpr int MASKR = T::RING - 1;
     unsigned long long* cnt = w.wcnt;
@@ -263,15 +280,22 @@ template <class T> __device__ int processRecord(const WinArgs& a, WinSmem<T>& w,
         for (int q = lane; q < (2 * 4 * T::MAXF) / 16; q += 32)
             if (q * 4 < nF || (q >= T::MAXF / 4 && (q - T::MAXF / 4) * 4 < nF)) dst[q] = src[q];
         const int* gface = reinterpret_cast<const int*>(rec + T::OFF_GFACE);
-        for (int q = lane; q < 3 * nF; q += 32) {
-            int f = q / 3, e = q - 3 * f;
-            w.geo[q] = __ldg(a.m.geo + 3 * (size_t)gface[f] + e);
+        if constexpr (LEAN) {
+            for (int f = lane; f < nF; f += 32) w.gface[f] = gface[f];
+        } else {
+            for (int q = lane; q < 3 * nF; q += 32) {
+                int f = q / 3, e = q - 3 * f;
+                w.geo[q] = __ldg(a.m.geo + 3 * (size_t)gface[f] + e);
+            }
         }
         for (int f = lane; f < nF; f += 32) w.tmask[f] = 0;
         const int* gvert = reinterpret_cast<const int*>(rec + T::OFF_GVERT);
         for (int v = lane; v < nV; v += 32) {
-            d3 p = ldvert(a.m, gvert[v]);
-            w.vx[v] = p.x, w.vy[v] = p.y, w.vz[v] = p.z;
+            if constexpr (LEAN) w.gvert[v] = gvert[v];
+            else {
+                d3 p = ldvert(a.m, gvert[v]);
+                w.vx[v] = p.x, w.vy[v] = p.y, w.vz[v] = p.z;
+            }
             w.D[v] = dinf();
             w.velig[v] = rec[T::OFF_VELIG + v];
             w.vdirty[v] = 0;
@@ -297,7 +321,7 @@ template <class T> __device__ int processRecord(const WinArgs& a, WinSmem<T>& w,
     v2 rq1, rq2, S2;
     {
         uchar4 fv = w.fvert[0];
-        d3 P0{w.vx[fv.x], w.vy[fv.x], w.vz[fv.x]}, P1{w.vx[fv.y], w.vy[fv.y], w.vz[fv.y]}, P2{w.vx[fv.z], w.vy[fv.z], w.vz[fv.z]};
+        const d3 P0 = vpos(a.m, w, fv.x), P1 = vpos(a.m, w, fv.y), P2 = vpos(a.m, w, fv.z);
         d3 e01{P1.x - P0.x, P1.y - P0.y, P1.z - P0.z}, e02{P2.x - P0.x, P2.y - P0.y, P2.z - P0.z};
         double L01 = sqrt(e01.x * e01.x + e01.y * e01.y + e01.z * e01.z);
         double rL = 1.0 / L01;
@@ -331,9 +355,10 @@ template <class T> __device__ int processRecord(const WinArgs& a, WinSmem<T>& w,
                 atomicOr(&w.tmask[lf], 1u << t);
                 uchar4 tv = w.fvert[lf];
                 double px = w.tpx[t], py = w.tpy[t], pz = w.tpz[t];
-                double ax = px - w.vx[tv.x], ay = py - w.vy[tv.x], az = pz - w.vz[tv.x];
-                double bx = px - w.vx[tv.y], by = py - w.vy[tv.y], bz = pz - w.vz[tv.y];
-                double cx = px - w.vx[tv.z], cy = py - w.vy[tv.z], cz = pz - w.vz[tv.z];
+                const d3 Q0 = vpos(a.m, w, tv.x), Q1 = vpos(a.m, w, tv.y), Q2 = vpos(a.m, w, tv.z);
+                double ax = px - Q0.x, ay = py - Q0.y, az = pz - Q0.z;
+                double bx = px - Q1.x, by = py - Q1.y, bz = pz - Q1.z;
+                double cx = px - Q2.x, cy = py - Q2.y, cz = pz - Q2.z;
                 w.tcd0[t] = sqrt(ax * ax + ay * ay + az * az);
                 w.tcd1[t] = sqrt(bx * bx + by * by + bz * bz);
                 w.tcd2[t] = sqrt(cx * cx + cy * cy + cz * cz);
@@ -357,7 +382,7 @@ template <class T> __device__ int processRecord(const WinArgs& a, WinSmem<T>& w,
                 B = lane == 0 ? rq1 : (lane == 1 ? rq2 : v2{0, 0});
             }
         }
-        pushWindows(w, lane, head, tail, valid, A, B, S2, 0.0, 1.0, 0.0, meta, NOPSV);
+        pushWindows(w, lane, head, tail, valid, A, B, 0.0, 1.0, meta, NOPSV);
     }
     __syncwarp();
 
@@ -378,8 +403,12 @@ template <class T> __device__ int processRecord(const WinArgs& a, WinSmem<T>& w,
             int meta = 0;
             unsigned char psv = NOPSV;
             if (active) {
-                A = v2{w.rax[p], w.ray[p]}, B = v2{w.rbx[p], w.rby[p]}, S = v2{w.rsx[p], w.rsy[p]};
-                t0 = w.rt0[p], t1 = w.rt1[p], sg = w.rsg[p], meta = w.rmeta[p], psv = w.rpsv[p];
+                A = v2{w.rax[p], w.ray[p]}, B = v2{w.rbx[p], w.rby[p]};
+                t0 = w.rt0[p], t1 = w.rt1[p], meta = w.rmeta[p], psv = w.rpsv[p];
+                // a window family lives in the frame of its (pseudo-)source: the real source sits at S2 in the root frame,
+                // a pseudo-source at the origin of its fan frame with sigma = its current vertex distance
+                if (psv == NOPSV) S = S2;
+                else S = v2{0, 0}, sg = w.D[psv];
             }
             __syncwarp(); // every slot of this pass is read before anybody pushes
             const int g = meta & 0xFF, e = (meta >> 16) & 3;
@@ -407,7 +436,7 @@ template <class T> __device__ int processRecord(const WinArgs& a, WinSmem<T>& w,
                 vA = e == 0 ? fv.y : (e == 1 ? fv.z : fv.x);
                 vB = e == 0 ? fv.z : (e == 1 ? fv.x : fv.y);
                 vC = e == 0 ? fv.x : (e == 1 ? fv.y : fv.z);
-                double2 cg = w.geo[3 * g + e];
+                double2 cg = edgeFrame(a.m, w, g, e);
                 C = v2{fma(cg.x, AB.x, fma(-cg.y, AB.y, A.x)), fma(cg.x, AB.y, fma(cg.y, AB.x, A.y))};
                 tm = w.tmask[g];
             }
@@ -517,7 +546,7 @@ template <class T> __device__ int processRecord(const WinArgs& a, WinSmem<T>& w,
                         }
                     }
                 }
-                if (!pushWindows(w, lane, head, tail, valid, X, Y, S, m0, m1, sg, cmeta, psv)) return WS_RING;
+                if (!pushWindows(w, lane, head, tail, valid, X, Y, m0, m1, cmeta, psv)) return WS_RING;
             }
             __syncwarp();
         }
@@ -552,7 +581,8 @@ template <class T> __device__ int processRecord(const WinArgs& a, WinSmem<T>& w,
             if (v < nV) w.vdirty[v] = 0;
             if (fl) {
                 bool useful = false;
-                double Dv = w.D[v], px = w.vx[v], py = w.vy[v], pz = w.vz[v];
+                const d3 Pq = vpos(a.m, w, v);
+                double Dv = w.D[v], px = Pq.x, py = Pq.y, pz = Pq.z;
                 for (int t = 0; t < K && !useful; ++t) {
                     double ex = w.tpx[t] - px, ey = w.tpy[t] - py, ez = w.tpz[t] - pz;
                     float lb = sqrtf((float)(ex * ex + ey * ey + ez * ez)) * (1.f - 2e-6f);
@@ -566,7 +596,7 @@ template <class T> __device__ int processRecord(const WinArgs& a, WinSmem<T>& w,
                 bal &= bal - 1;
                 spawned = true;
                 nPs++;
-                ok = spawnFan(w, lane, nF, v0i + b, fUb, head, tail) && ok;
+                ok = spawnFan(a.m, w, lane, nF, v0i + b, fUb, head, tail) && ok;
             }
         }
         if (!ok) return WS_RING;
@@ -597,12 +627,13 @@ template <class T> __device__ int processRecord(const WinArgs& a, WinSmem<T>& w,
             if (a.nbrTe) {
                 if ((code & 3) == 2) {
                     int ge = code >> 2;
-                    te = liftEnd(w, ge & 0xFF, ge >> 8, w.tdu[t], w.tdw[t]);
+                    te = liftEnd(a.m, w, ge & 0xFF, ge >> 8, w.tdu[t], w.tdw[t]);
                 } else {
                     int k = code >> 2;
                     uchar4 tv = w.fvert[w.tFace[t]];
                     int cv = k == 0 ? tv.x : (k == 1 ? tv.y : tv.z);
-                    double ex = w.tpx[t] - w.vx[cv], ey = w.tpy[t] - w.vy[cv], ez = w.tpz[t] - w.vz[cv];
+                    const d3 Pc = vpos(a.m, w, cv);
+                    double ex = w.tpx[t] - Pc.x, ey = w.tpy[t] - Pc.y, ez = w.tpz[t] - Pc.z;
                     double rl2 = 1.0 / sqrt(ex * ex + ey * ey + ez * ez);
                     te = d3{ex * rl2, ey * rl2, ez * rl2};
                 }
@@ -653,11 +684,14 @@ template <class T> __device__ int processRecord(const WinArgs& a, WinSmem<T>& w,
 
 } // namespace
 
-template <class T> __global__ void __launch_bounds__(128, 4) k_windows(WinArgs a)
+#ifndef CSS_LEAN_MINBLOCKS
+#define CSS_LEAN_MINBLOCKS 5
+#endif
+template <class T, bool LEAN> __global__ void __launch_bounds__(128, LEAN ? CSS_LEAN_MINBLOCKS : 4) k_windows(WinArgs a)
 {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    WinSmem<T>& w = reinterpret_cast<WinSmem<T>*>(smemRaw)[wib];
+    WinSmem<T, LEAN>& w = reinterpret_cast<WinSmem<T, LEAN>*>(smemRaw)[wib];
     unsigned long long* cnt = w.wcnt;
     if (lane < 16) cnt[lane] = 0;
     __syncwarp();
@@ -668,7 +702,7 @@ template <class T> __global__ void __launch_bounds__(128, 4) k_windows(WinArgs a
         s = __shfl_sync(FULL, s, 0);
         if (s >= nWork) break;
         const int li = a.srcList ? a.srcList[s] : s;
-        int st = processRecord<T>(a, w, li, s, lane);
+        int st = processRecord<T, LEAN>(a, w, li, s, lane);
         st = __shfl_sync(FULL, st, 0);
         __syncwarp();
         if (st != WS_OK && lane == 0) { // ring overflow: rerun on the next tier
@@ -682,23 +716,27 @@ template <class T> __global__ void __launch_bounds__(128, 4) k_windows(WinArgs a
     if (lane < 16 && cnt[lane]) atomicAdd(a.counters + lane, cnt[lane]);
 }
 
-template <class T> cudaError_t launchWindows(cudaStream_t st, const WinArgs& a, int warpsPerBlock, int numSMs)
+template <class T, bool LEAN> static cudaError_t launchWindowsImpl(cudaStream_t st, const WinArgs& a, int warpsPerBlock, int numSMs)
 {
-    size_t smem = sizeof(WinSmem<T>) * warpsPerBlock;
+    size_t smem = sizeof(WinSmem<T, LEAN>) * warpsPerBlock;
     static int perSM[5] = {0, 0, 0, 0, 0};
     if (warpsPerBlock < 1 || warpsPerBlock > 4 || smem > 227 * 1024) return cudaErrorInvalidConfiguration;
     if (!perSM[warpsPerBlock]) {
-        cudaFuncSetAttribute(k_windows<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(k_windows<T, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         int n = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_windows<T>, warpsPerBlock * 32, smem) != cudaSuccess || n < 1) n = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_windows<T, LEAN>, warpsPerBlock * 32, smem) != cudaSuccess || n < 1) n = 1;
         perSM[warpsPerBlock] = n;
     }
     int blocks = numSMs * perSM[warpsPerBlock];
     if (!a.srcList) blocks = min(blocks, max(1, (a.nLocal + warpsPerBlock - 1) / warpsPerBlock));
-    k_windows<T><<<blocks, warpsPerBlock * 32, smem, st>>>(a);
+    k_windows<T, LEAN><<<blocks, warpsPerBlock * 32, smem, st>>>(a);
     return cudaGetLastError();
 }
-template cudaError_t launchWindows<TierSmall>(cudaStream_t, const WinArgs&, int, int);
-template cudaError_t launchWindows<TierLarge>(cudaStream_t, const WinArgs&, int, int);
+template <class T> cudaError_t launchWindows(cudaStream_t st, const WinArgs& a, int warpsPerBlock, int numSMs, bool lean)
+{
+    return lean ? launchWindowsImpl<T, true>(st, a, warpsPerBlock, numSMs) : launchWindowsImpl<T, false>(st, a, warpsPerBlock, numSMs);
+}
+template cudaError_t launchWindows<TierSmall>(cudaStream_t, const WinArgs&, int, int, bool);
+template cudaError_t launchWindows<TierLarge>(cudaStream_t, const WinArgs&, int, int, bool);
 
 } // namespace css
