@@ -396,8 +396,9 @@ __device__ int processSource(const GeoArgs& a, const WS& w, int li, int lane)
             int head = 1;
             for (;;) {
                 __syncwarp();
-                int tail = min(w.misc[0], cp.maxF);
-                if (w.misc[2]) return ST_OVF_F;
+                // one lane's view of the queue for the whole warp (see patch_kernel.cu)
+                int tail = min(__shfl_sync(FULL, w.misc[0], 0), cp.maxF);
+                if (__shfl_sync(FULL, w.misc[2], 0)) return ST_OVF_F;
                 if (head >= tail) break;
                 int idx = head + lane;
                 if (idx < tail) {

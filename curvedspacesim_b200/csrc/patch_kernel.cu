@@ -203,8 +203,10 @@ template <class T> __device__ int buildPatch(const PatchArgs& a, PatchSmem<T>& s
             int head = 1;
             for (;;) {
                 __syncwarp();
-                int tail = min(s.misc[0], T::MAXF);
-                if (s.misc[2]) return 3;
+                // one lane's view of the queue for the whole warp: a lane that read it later could already see pushes of this
+                // pass, and lanes disagreeing on `head` would leave the loop at different times
+                const int tail = min(__shfl_sync(FULL, s.misc[0], 0), T::MAXF);
+                if (__shfl_sync(FULL, s.misc[2], 0)) return 3;
                 if (head >= tail) break;
                 int slotF = lane / 3, k = lane - 3 * slotF;
                 int idx = head + slotF;
