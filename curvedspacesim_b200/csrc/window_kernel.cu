@@ -391,12 +391,15 @@ template <class T, bool LEAN> __device__ int processRecord(const WinArgs& a, Win
     unsigned nPass = 0, nPass3 = 0, nPass8 = 0;
 #endif
     for (;;) {
-        // ================= drain the ring, 32 windows per pass =================
+        // ================= drain the ring, 16 windows per pass: a PAIR of lanes per window, one child edge each ==========
+        // (the two lanes of a pair run the same instructions up to the children, so the pass costs one child instead of two;
+        //  BFS levels of these patches rarely exceed 16 windows)
         while (head != tail) {
             const float fUb = warpBound(w, lane, K);
-            int nb = min(32, tail - head);
-            bool active = lane < nb;
-            int p = (head + lane) & MASKR;
+            const int nb = min(16, tail - head);
+            const int j = lane & 1; // which child edge this lane propagates into
+            bool active = (lane >> 1) < nb;
+            const int p = (head + (lane >> 1)) & MASKR;
             head += nb;
             v2 A{0, 0}, B{1, 0}, S{0, -1};
             double t0 = 0, t1 = 1, sg = 0;
@@ -429,7 +432,7 @@ template <class T, bool LEAN> __device__ int processRecord(const WinArgs& a, Win
             v2 C{0, 1};
             unsigned tm = 0;
             if (active) {
-                nWin++;
+                nWin += j == 0;
                 uchar4 fv = w.fvert[g];
                 fa = w.fadj[g];
                 kkbits = fv.w;
@@ -438,7 +441,7 @@ template <class T, bool LEAN> __device__ int processRecord(const WinArgs& a, Win
                 vC = e == 0 ? fv.x : (e == 1 ? fv.y : fv.z);
                 double2 cg = edgeFrame(a.m, w, g, e);
                 C = v2{fma(cg.x, AB.x, fma(-cg.y, AB.y, A.x)), fma(cg.x, AB.y, fma(cg.y, AB.x, A.y))};
-                tm = w.tmask[g];
+                if (j == 0) tm = w.tmask[g]; // the even lane of the pair answers the queries
             }
             // ---- queries: targets inside the entered face (rare: ~K/nF of the windows enter a face that holds a target)
             while (__any_sync(FULL, tm != 0)) {
@@ -497,7 +500,7 @@ template <class T, bool LEAN> __device__ int processRecord(const WinArgs& a, Win
                 if (inside) {
                     dC = sg + fsqrt(lc2);
                     if (dC < DC) {
-                        improved = atomicMinD(&w.D[vC], dC);
+                        if (j == 0) improved = atomicMinD(&w.D[vC], dC);
                         DC = fmin(DC, dC);
                     }
                 }
@@ -514,12 +517,7 @@ template <class T, bool LEAN> __device__ int processRecord(const WinArgs& a, Win
             // Xin-Wang filter and bound test in fp32 with a conservative margin: a window is dropped only when it is
             // dominated by clearly more than the rounding of the approximation.
             const f2 fA = tof2(A), fB = tof2(B), fC = tof2(C);
-#ifdef CSS_CHILD_UNROLL
-#pragma unroll
-#else
-#pragma unroll 1
-#endif
-            for (int j = 0; j < 2; ++j) {
+            {
                 const v2 X = j ? C : A, Y = j ? B : C;
                 bool valid = false;
                 double m0 = 0, m1 = 1;

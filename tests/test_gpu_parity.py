@@ -364,14 +364,16 @@ def test_edge_cases(gpu_ctx_factory):
     assert _rel(g[2], o[2]) < TOL_DIST
 
 
-def test_dense_neighbourhoods_grow_the_stride(gpu_ctx_factory):
-    """config 2b-like stress: K ~ 55 neighbours per particle, large patches (tier 1)."""
+@pytest.mark.parametrize("area_fraction,kmin", [(12.0, 33), (3.5, 17)])
+def test_dense_neighbourhoods_grow_the_stride(area_fraction, kmin, gpu_ctx_factory):
+    """config 2b-like stress: K ~ 55 neighbours per particle and large patches (last, whole-mesh tier), and a
+    medium density whose K of 17..32 and ~150-face patches run on the large record tier."""
     V, F = _mesh("torus60x24")
-    orc, ctx, corners, face, bary, vel, rc, kind, params = _pair(V, F, 600, "harmonic", gpu_ctx_factory, area_fraction=12.0)
+    orc, ctx, corners, face, bary, vel, rc, kind, params = _pair(V, F, 600, "harmonic", gpu_ctx_factory, area_fraction=area_fraction)
     o = orc.find_neighbors(rc)
     g = ctx.find_neighbors(rc, want_end=True)
     assert np.array_equal(o[0], g[0]) and np.array_equal(o[1], g[1])
-    assert np.diff(o[0]).max() > 32                         # beyond the initial neighbour stride
+    assert np.diff(o[0]).max() >= kmin                      # beyond the small tier (and, for the dense case, the initial stride)
     assert _rel(g[2], o[2]) < TOL_DIST and np.max(np.abs(g[3] - o[3])) < TOL_TAN
     c = ctx.counters()
     assert c["overflow"] == 0 and c["tier_retry"] > 0
