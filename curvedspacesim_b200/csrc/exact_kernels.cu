@@ -359,7 +359,7 @@ __device__ __forceinline__ int walkOne(const MeshDev& m, int& face, double bary[
 }
 
 // particles [0,n) of this rank; global index = minIdx + i in face/bary
-__global__ void k_walk(MeshDev m, int n, int minIdx, int* __restrict__ face, double* __restrict__ bary, double* __restrict__ disp,
+__global__ void __launch_bounds__(64, 12) k_walk(MeshDev m, int n, int minIdx, int* __restrict__ face, double* __restrict__ bary, double* __restrict__ disp,
                        double* __restrict__ vel, double* __restrict__ frc, int transportForce, int transportVelocity, int mode,
                        double dt, int* __restrict__ flagsOut, unsigned long long* __restrict__ counters)
 {
@@ -572,7 +572,7 @@ void launchWalk(cudaStream_t st, const MeshDev& m, int n, int minIdx, int* face,
                 int transportForce, int transportVelocity, int mode, double dt, int* flags, unsigned long long* counters)
 {
     if (n > 0)
-        k_walk<<<gridFor(n, 128), 128, 0, st>>>(m, n, minIdx, face, bary, disp, vel, frc, transportForce, transportVelocity, mode, dt,
+        k_walk<<<gridFor(n, 64), 64, 0, st>>>(m, n, minIdx, face, bary, disp, vel, frc, transportForce, transportVelocity, mode, dt,
                                                 flags, counters);
 }
 void launchTransportGeneric(cudaStream_t st, const MeshDev& m, int n, int* face, double* bary, double* disp, int nVec, double* vecs,

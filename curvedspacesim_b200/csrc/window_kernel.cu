@@ -41,6 +41,7 @@ template <class T, bool LEAN> struct WinSmem { // per-warp workspace
     int gface[LEAN ? F : 1], gvert[LEAN ? V : 1];
     double D[V], dirx[V], diry[V];
     double rax[R], ray[R], rbx[R], rby[R], rt0[R], rt1[R]; // ring: the (pseudo-)source image and sigma follow from rpsv
+    double2 rcg[LEAN ? R : 1];                             // ring: edge frame of the face the window enters (fetched at push time)
     double tbest[K], tb0[K], tb1[K], tb2[K], tsx[K], tsy[K], tdu[K], tdw[K];
     double tpx[K], tpy[K], tpz[K], tcd0[K], tcd1[K], tcd2[K];
     double root[6];
@@ -158,7 +159,7 @@ template <class W> __device__ __forceinline__ double2 edgeFrame(const MeshDev& m
 
 // push up to one window per lane; returns false when the ring would overflow
 template <class W> __device__ __forceinline__ bool pushWindows(W& w, int lane, int head, int& tail, bool valid, const v2& A, const v2& B,
-                                            double t0, double t1, int meta, unsigned char psv)
+                                            double t0, double t1, int meta, unsigned char psv, const double2& cg)
 {
     unsigned bal = __ballot_sync(FULL, valid);
     int tot = __popc(bal);
@@ -167,6 +168,7 @@ template <class W> __device__ __forceinline__ bool pushWindows(W& w, int lane, i
         int q = (tail + __popc(bal & ((1u << lane) - 1))) & (W::R - 1);
         w.rax[q] = A.x, w.ray[q] = A.y, w.rbx[q] = B.x, w.rby[q] = B.y;
         w.rt0[q] = t0, w.rt1[q] = t1, w.rmeta[q] = meta, w.rpsv[q] = psv;
+        if constexpr (W::lean) w.rcg[q] = cg;
     }
     tail += tot;
     return true;
@@ -223,7 +225,10 @@ template <class W> __device__ __noinline__ bool spawnFan(const MeshDev& m, W& w,
             if (w.vdirty[fv.y] == 2) w.vdirty[fv.y] = 1;
             if (w.vdirty[fv.z] == 2) w.vdirty[fv.z] = 1;
         }
-        if (ok) ok = pushWindows(w, lane, head, tail, valid, A, B, 0.0, 1.0, meta, (unsigned char)pv);
+        double2 cg{0, 0};
+        if constexpr (W::lean)
+            if (valid) cg = edgeFrame(m, w, meta & 0xFF, (meta >> 16) & 3);
+        if (ok) ok = pushWindows(w, lane, head, tail, valid, A, B, 0.0, 1.0, meta, (unsigned char)pv, cg);
         __syncwarp();
     }
     return ok;
@@ -382,7 +387,10 @@ template <class T, bool LEAN> __device__ int processRecord(const WinArgs& a, Win
                 B = lane == 0 ? rq1 : (lane == 1 ? rq2 : v2{0, 0});
             }
         }
-        pushWindows(w, lane, head, tail, valid, A, B, 0.0, 1.0, meta, NOPSV);
+        double2 cg{0, 0};
+        if constexpr (LEAN)
+            if (valid) cg = edgeFrame(a.m, w, meta & 0xFF, (meta >> 16) & 3);
+        pushWindows(w, lane, head, tail, valid, A, B, 0.0, 1.0, meta, NOPSV, cg);
     }
     __syncwarp();
 
@@ -439,7 +447,9 @@ template <class T, bool LEAN> __device__ int processRecord(const WinArgs& a, Win
                 vA = e == 0 ? fv.y : (e == 1 ? fv.z : fv.x);
                 vB = e == 0 ? fv.z : (e == 1 ? fv.x : fv.y);
                 vC = e == 0 ? fv.x : (e == 1 ? fv.y : fv.z);
-                double2 cg = edgeFrame(a.m, w, g, e);
+                double2 cg;
+                if constexpr (LEAN) cg = w.rcg[p];
+                else cg = edgeFrame(a.m, w, g, e);
                 C = v2{fma(cg.x, AB.x, fma(-cg.y, AB.y, A.x)), fma(cg.x, AB.y, fma(cg.y, AB.x, A.y))};
                 if (j == 0) tm = w.tmask[g]; // the even lane of the pair answers the queries
             }
@@ -522,10 +532,13 @@ template <class T, bool LEAN> __device__ int processRecord(const WinArgs& a, Win
                 bool valid = false;
                 double m0 = 0, m1 = 1;
                 int cmeta = 0;
+                double2 ccg{0, 0};
                 if (active && (j ? rightOpen : leftOpen)) {
                     const int io = j ? (e == 2 ? 0 : e + 1) : (e == 0 ? 2 : e - 1); // corner opposite the child edge: iA / iB
                     const int g2 = io == 0 ? fa.x : (io == 1 ? fa.y : fa.z);
                     if (g2 != REC_NONE) {
+                        const int kk = (kkbits >> (2 * io)) & 3;
+                        if constexpr (LEAN) ccg = edgeFrame(a.m, w, g2, kk); // needed by the child at the next pass: issued here, stored with the push
                         if (!(j == 1 && inside)) m0 = hitParam(S, P0, X, Y);
                         if (!(j == 0 && inside)) m1 = hitParam(S, P1, X, Y);
                         if (m1 - m0 > 1e-13) {
@@ -539,12 +552,12 @@ template <class T, bool LEAN> __device__ int processRecord(const WinArgs& a, Win
                                 const float sn = j ? s1 : s0;
                                 const bool dom = (dX + fdist(fX, X1) < s1) || (dY + fdist(fY, X0) < s0) || (dO + fdist(fO, Xn) < sn);
                                 valid = !dom;
-                                cmeta = g2 | (((kkbits >> (2 * io)) & 3) << 16);
+                                cmeta = g2 | (kk << 16);
                             }
                         }
                     }
                 }
-                if (!pushWindows(w, lane, head, tail, valid, X, Y, m0, m1, cmeta, psv)) return WS_RING;
+                if (!pushWindows(w, lane, head, tail, valid, X, Y, m0, m1, cmeta, psv, ccg)) return WS_RING;
             }
             __syncwarp();
         }
