@@ -28,7 +28,7 @@ NUM_COUNTERS = 32
 # every symbol include/css_api.h declares (tests check that the library exports all of them)
 API_SYMBOLS = [
     "css_create", "css_destroy", "css_last_error", "css_set_mesh", "css_mesh_info", "css_set_submeshing", "css_set_cell_domain",
-    "css_set_options", "css_euclidean", "css_distance", "css_transport", "css_set_state", "css_get_state", "css_set_velocities",
+    "css_set_options", "css_set_boundary", "css_euclidean", "css_distance", "css_transport", "css_set_state", "css_get_state", "css_set_velocities",
     "css_set_forces", "css_find_neighbors", "css_get_neighbors", "css_compute_forces", "css_compute_energy", "css_move",
     "css_get_walk_flags", "css_step_nve", "css_step_gd", "css_nvt_init", "css_step_nvt", "css_nvt_state", "css_fire_init",
     "css_fire_minimize", "css_max_force", "css_force_norm", "css_comm_unique_id", "css_comm_init", "css_gather_positions",
@@ -142,6 +142,10 @@ class Context:
         mn = np.ascontiguousarray(mn, np.float64)
         mx = np.ascontiguousarray(mx, np.float64)
         self._ck(self.L.css_set_cell_domain(self.h, _d(mn), _d(mx)))
+
+    def set_boundary(self, mode):
+        """0 closed, 1 absorbing, 2 tangential (open-mesh variants of the walker)."""
+        self._ck(self.L.css_set_boundary(self.h, int(mode)))
 
     def set_options(self, use_cell_list=True, want_end_tangents=False):
         self._ck(self.L.css_set_options(self.h, int(bool(use_cell_list)), int(bool(want_end_tangents))))

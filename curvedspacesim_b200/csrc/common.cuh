@@ -20,6 +20,7 @@ struct MeshDev {
     // C = corner e in the frame of that edge, normalised by |AB|:  C = A + cxn (B-A) + cyn perp(B-A).
     // geo[3 f + e] = {cxn, cyn}; lets a window be unfolded across a face with four FMAs and no 3-D geometry.
     const double2* geo;
+    int boundary; // walker at a border edge: 0 closed space (flag + stop), 1 absorbing, 2 tangential (openMeshSpace variants)
 };
 
 struct CellGrid {

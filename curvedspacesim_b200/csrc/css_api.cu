@@ -33,6 +33,7 @@ struct css_ctx {
     bool submeshing = false;
     double maxDist = 0;
     bool useCellList = true, wantEnd = false;
+    int boundaryMode = 0; // 0 closed, 1 absorbing, 2 tangential
     // particles
     int nLocal = 0, nTotal = 0, minIdx = 0, capLocal = 0, capTotal = 0;
     int* d_face = nullptr;
@@ -342,6 +343,13 @@ int css_set_cell_domain(css_ctx* ctx, const double mn[3], const double mx[3])
     ctx->nveCalls = 0;
     return CSS_OK;
 }
+int css_set_boundary(css_ctx* ctx, int mode)
+{
+    if (!ctx || mode < 0 || mode > 2) return fail(ctx, CSS_EINVAL, "css_set_boundary: mode must be 0 (closed), 1 (absorbing) or 2 (tangential)");
+    ctx->boundaryMode = mode;
+    ctx->nveCalls = 0;
+    return CSS_OK;
+}
 int css_set_options(css_ctx* ctx, int useCellList, int wantEndTangents)
 {
     if (!ctx) return CSS_EINVAL;
@@ -352,7 +360,7 @@ int css_set_options(css_ctx* ctx, int useCellList, int wantEndTangents)
     return CSS_OK;
 }
 
-static MeshDev meshDev(css_ctx* c) { return MeshDev{c->nV, c->nF, c->d_vert, c->d_corner, c->d_adj, c->d_saddle, c->d_geo}; }
+static MeshDev meshDev(css_ctx* c) { return MeshDev{c->nV, c->nF, c->d_vert, c->d_corner, c->d_adj, c->d_saddle, c->d_geo, c->boundaryMode}; }
 
 // ------------------------------------------------------------------------------- per-call parity
 int css_euclidean(css_ctx* ctx, int n, const int32_t* face, const double* bary, double* xyz)
@@ -917,7 +925,7 @@ static uint64_t nveGraphKey(css_ctx* ctx, const ForceParams& fp, double range, d
 #define MIX(x) mix(&(x), sizeof(x))
     MIX(fp.kind), MIX(fp.a), MIX(fp.sigma), MIX(range), MIX(dt);
     MIX(ctx->nLocal), MIX(ctx->nTotal), MIX(ctx->minIdx), MIX(ctx->kmax), MIX(ctx->nranks), MIX(ctx->timing), MIX(ctx->submeshing),
-        MIX(ctx->maxDist), MIX(ctx->useCellList), MIX(ctx->wantEnd), MIX(ctx->twoStage), MIX(ctx->winWpb), MIX(ctx->winLean), MIX(ctx->grid), MIX(ctx->nCells);
+        MIX(ctx->maxDist), MIX(ctx->boundaryMode), MIX(ctx->useCellList), MIX(ctx->wantEnd), MIX(ctx->twoStage), MIX(ctx->winWpb), MIX(ctx->winLean), MIX(ctx->grid), MIX(ctx->nCells);
     void* ptrs[] = {ctx->d_vert, ctx->d_corner, ctx->d_adj, ctx->d_geo, ctx->d_saddle, ctx->d_face, ctx->d_bary, ctx->d_eucl, ctx->d_vel, ctx->d_frc,
                     ctx->d_disp, ctx->d_walkFlags, ctx->d_cellOf, ctx->d_cellCount, ctx->d_cellStart, ctx->d_blockSums, ctx->d_fill, ctx->d_tmpItems,
                     ctx->d_items, ctx->d_nbrCount, ctx->d_nbrIdx, ctx->d_nbrDist, ctx->d_nbrTs, ctx->d_nbrTe, ctx->d_retry[0], ctx->d_retry[1],

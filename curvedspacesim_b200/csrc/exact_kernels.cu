@@ -275,6 +275,21 @@ __device__ __forceinline__ int edgeHits(const double S[3], const double E[3], in
     return nh;
 }
 
+// triangulatedMeshSpace::projectVectorsIfOverBoundary (triangulatedMeshSpace.cpp:411-426)
+template <int NT> __device__ __forceinline__ void projectVectorsIfOverBoundary(d3 (&T)[NT > 0 ? NT : 1], int nT, const d3& orthogonal, const d3& inward)
+{
+    bool pointsOut = dot(orthogonal, inward) < 0;
+#pragma unroll
+    for (int i = 0; i < NT; ++i)
+        if (i < nT) {
+            bool along = dot(T[i], orthogonal) > 0;
+            if ((pointsOut && along) || (!pointsOut && !along)) {
+                d3 dhat = orthogonal / norm(orthogonal);
+                T[i] = T[i] - dot(T[i], dhat) * dhat;
+            }
+        }
+}
+
 template <int NT>
 __device__ __forceinline__ int walkOne(const MeshDev& m, int& face, double bary[3], d3& disp, d3 (&T)[NT > 0 ? NT : 1], int nT,
                                        int& nCross)
@@ -324,10 +339,40 @@ __device__ __forceinline__ int walkOne(const MeshDev& m, int& face, double bary[
         if (nh >= 2) flags |= WALK_VERTEX;
         int4 a = __ldg(m.adj + f);
         int g = k == 0 ? a.x : (k == 1 ? a.y : a.z);
-        if (g < 0) {
+        if (g < 0) { // border edge: openMeshSpace.cpp:114-238 and its absorbing / tangential subclasses
             flags |= WALK_BORDER;
-            E[0] = S[0], E[1] = S[1], E[2] = S[2];
-            break;
+            if (m.boundary == 0) {
+                E[0] = S[0], E[1] = S[1], E[2] = S[2];
+                break;
+            }
+            const d3 ev1 = k == 0 ? tri.p1 : (k == 1 ? tri.p2 : tri.p0), ev2 = k == 0 ? tri.p2 : (k == 1 ? tri.p0 : tri.p1);
+            const d3 inner = k == 0 ? tri.p0 : (k == 1 ? tri.p1 : tri.p2);
+            d3 edge = ev2 - ev1;
+            d3 orth = cross(n, edge);
+            orth = orth / norm(orth);
+            d3 inward = inner - p;
+            if (m.boundary == 1) { // absorbing: stop on the edge
+                if (nT > 0) projectVectorsIfOverBoundary<NT>(T, nT, orth, inward);
+                E[0] = S[0], E[1] = S[1], E[2] = S[2];
+                break;
+            }
+            d3 fwd = edge / norm(edge); // tangential: slide along the edge
+            d3 back = ev1 - ev2;
+            d3 bwd = back / norm(back);
+            double len = norm(disp);
+            d3 dhat = disp / len;
+            double fd = dot(dhat, fwd), bd = dot(dhat, bwd);
+            projectVectorsIfOverBoundary<NT>(T, nT, orth, inward);
+            if (fd <= 0 && bd <= 0) {
+                E[0] = S[0], E[1] = S[1], E[2] = S[2];
+                break;
+            }
+            if (fd > bd) disp = (fd * len) * fwd;
+            else disp = (bd * len) * bwd;
+            q = p + disp;
+            last = -1;
+            nCross++;
+            continue;
         }
         Tri tri2 = ldtri(m, g);
         d3 n2 = tnormal(tri2);

@@ -154,6 +154,19 @@ def plane_grid(nx: int, ny: int, lx: float = 1.0, ly: float = 1.0, normal_up: bo
     return V, F
 
 
+def bowl(nx: int = 24, ny: int = 24, depth: float = 0.35, jitter: float = 0.15, seed: int = 13377):
+    """Open curved sheet z = depth (x^2 + y^2) over [-1,1]^2 with jittered interior vertices: a synthetic stand-in for the
+    reference's open example meshes (silo_omega0.012_R2.0.off, sp_rb20_isotropic.off) for the open-mesh boundary rules."""
+    V, F = plane_grid(nx, ny, 2.0, 2.0)
+    V = V - np.array([1.0, 1.0, 0.0])
+    rng = np.random.default_rng(seed)
+    interior = (np.abs(V[:, 0]) < 1 - 1e-9) & (np.abs(V[:, 1]) < 1 - 1e-9)
+    h = 2.0 / max(nx, ny)
+    V[interior, :2] += (rng.random((int(interior.sum()), 2)) - 0.5) * 2 * jitter * h
+    V[:, 2] = depth * (V[:, 0] ** 2 + V[:, 1] ** 2)
+    return V, F
+
+
 def cube(n: int = 1, side: float = 1.0):
     """Closed cube surface, each side split into n x n quads -> 2 triangles; outward orientation."""
     verts = {}

@@ -248,7 +248,7 @@ public:
         for (size_t i = 0; i < transportVectors.size(); ++i)
             for (int k = 0; k < 3; ++k) v[3 * i + k] = transportVectors[i][k];
         cssHost::check(ctx(), css_transport(ctx(), 1, &f, b, d, (int)transportVectors.size(), v.empty() ? nullptr : v.data(), &flags), "css_transport");
-        if (flags & 16) ERRORERROR("a border edge was met in a closed mesh space"); // triangulatedMeshSpace.cpp:522-523
+        if ((flags & 16) && boundaryMode == 0) ERRORERROR("a border edge was met in a closed mesh space"); // triangulatedMeshSpace.cpp:522-523
         if (flags & 2) ERRORERROR("no edge intersection found although the target lies outside the face");
         pos = meshPosition(point3(b[0], b[1], b[2]), f);
         displacementVector = vector3(d[0], d[1], d[2]);
@@ -330,6 +330,14 @@ public:
         }
     void setNewSubmeshCutoff(double newCutoff) { useSubmeshingRoutines(true, newCutoff); }
 
+    //! 0 closed (border edges are an error), 1 absorbing, 2 tangential: the rule the walker applies at border edges
+    void setBoundaryMode(int mode)
+        {
+        boundaryMode = mode;
+        cssHost::check(ctx(), css_set_boundary(ctx(), mode), "css_set_boundary");
+        }
+    int getBoundaryMode() const { return boundaryMode; }
+
     css_ctx* ctx() const { return holder->ctx; }
     double3 minVertexPosition{0, 0, 0}, maxVertexPosition{0, 0, 0};
     vector<double> vertices;  // [nV][3]
@@ -354,9 +362,23 @@ protected:
     double area = 0;
     bool submeshingActivated = false;
     double maximumDistance = 0;
+    int boundaryMode = 0;
     };
 typedef gpuMeshSpace triangulatedMeshSpace;
 typedef gpuMeshSpace closedMeshSpace;
+
+//! openMeshSpace subclasses (src/models/absorbingOpenMeshSpace.h, tangentialOpenMeshSpace.h): the same walker kernel with the
+//! border-edge rule switched on the device (css_set_boundary); distance() already treats boundary vertices as pseudo-sources.
+class absorbingOpenMeshSpace : public gpuMeshSpace
+    {
+public:
+    explicit absorbingOpenMeshSpace(int device = 0) : gpuMeshSpace(device) { setBoundaryMode(1); }
+    };
+class tangentialOpenMeshSpace : public gpuMeshSpace
+    {
+public:
+    explicit tangentialOpenMeshSpace(int device = 0) : gpuMeshSpace(device) { setBoundaryMode(2); }
+    };
 
 inline double totalArea(gpuMeshSpace& space) { return space.getArea(); }
 

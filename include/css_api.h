@@ -6,6 +6,7 @@
  *   css_set_mesh            triangulatedMeshSpace::loadMeshFromFile + updateMeshSpanAndTree
  *                           (src/models/triangulatedMeshSpace.cpp:6-72)
  *   css_set_submeshing      triangulatedMeshSpace::useSubmeshingRoutines (src/models/triangulatedMeshSpace.h:60-66)
+ *   css_set_boundary        openMeshSpace / absorbingOpenMeshSpace / tangentialOpenMeshSpace (src/models/openMeshSpace.cpp:114-238)
  *   css_set_cell_domain     cellListNeighborStructure ctor (src/utility/cellListNeighborStructure.cpp:4-20)
  *   css_euclidean           triangulatedMeshSpace::meshPositionToEuclideanLocation (.cpp:82-106)
  *   css_distance            baseSpace::distance / triangulatedMeshSpace::distance (src/models/baseSpace.h:36-39,
@@ -94,6 +95,9 @@ int css_set_mesh(css_ctx* ctx, int nV, const double* xyz, int nF, const int32_t*
 int css_mesh_info(css_ctx* ctx, double bbmin[3], double bbmax[3], double* area);
 int css_set_submeshing(css_ctx* ctx, int enabled, double maxDist);
 int css_set_cell_domain(css_ctx* ctx, const double mn[3], const double mx[3]);
+/* open-mesh boundary rule of the walker: 0 closed space (a border edge is flagged, triangulatedMeshSpace.cpp:547-548),
+ * 1 absorbingOpenMeshSpace (src/models/absorbingOpenMeshSpace.cpp:2-50), 2 tangentialOpenMeshSpace (tangentialOpenMeshSpace.cpp:3-64) */
+int css_set_boundary(css_ctx* ctx, int mode);
 /* useCellList=0 reproduces baseNeighborStructure (all-to-all candidates) */
 int css_set_options(css_ctx* ctx, int useCellList, int wantEndTangents);
 

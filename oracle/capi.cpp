@@ -60,6 +60,8 @@ ORC_API void orc_set_options(void* h, int useCellList, int strictTrig, int nThre
     s->nThreads = nThreads;
 }
 // override of the cell-list domain (cellListNeighborStructure ctor, cellListNeighborStructure.cpp:4-15)
+ORC_API void orc_set_boundary(void* h, int mode) { ((Sim*)h)->boundaryMode = mode; }
+
 ORC_API void orc_set_cell_domain(void* h, const double* mn, const double* mx)
 {
     Sim* s = (Sim*)h;
@@ -171,7 +173,7 @@ ORC_API void orc_transport(void* h, int n, int* face, double* bary, double* disp
         for (int j = 0; j < nVec && j < 8; ++j)
             T[j] = V3{vecs[3 * (i * nVec + j)], vecs[3 * (i * nVec + j) + 1], vecs[3 * (i * nVec + j) + 2]};
         int cr = 0;
-        int fl = transport(s->mesh, face[i], bary + 3 * i, d, T, nVec, s->strictTrig, &cr);
+        int fl = transport(s->mesh, face[i], bary + 3 * i, d, T, nVec, s->strictTrig, &cr, s->boundaryMode);
         if (flags) flags[i] = fl;
         if (crossings) crossings[i] = cr;
         disp[3 * i] = d.x, disp[3 * i + 1] = d.y, disp[3 * i + 2] = d.z;

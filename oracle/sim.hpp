@@ -79,6 +79,7 @@ struct Sim {
     std::vector<std::vector<V3>> nbrStart, nbrEnd;
     std::vector<int> walkFlags;
     bool transportForce = false, transportVelocity = true;
+    int boundaryMode = 0; // openMeshSpace variants: 0 closed, 1 absorbing, 2 tangential (walker.hpp BoundaryMode)
     bool strictTrig = false;
     int nThreads = 1;
     GeoStats stats;
@@ -234,7 +235,7 @@ struct Sim {
                 if (transportForce) T[nT++] = frc[i];
                 if (transportVelocity) T[nT++] = vel[i];
                 int cr = 0;
-                walkFlags[i] = transport(mesh, face[i], &bary[3 * i], disp[i], T, nT, strictTrig, &cr);
+                walkFlags[i] = transport(mesh, face[i], &bary[3 * i], disp[i], T, nT, strictTrig, &cr, boundaryMode);
                 tc[tid] += cr;
                 nT = 0;
                 if (transportForce) frc[i] = T[nT++];

@@ -8,6 +8,10 @@
 //  * rotation angle: the reference takes theta = acos(n.n') and then sin/cos(theta); here (and in the
 //    CUDA kernel) cos = n.n' and sin = |n x n'| so no libm call can differ between host and device.
 //    strictTrig=true restores the reference's acos/sin/cos for comparison.
+//  * open meshes (openMeshSpace.cpp:114-238): a border edge ends the walk in the closed space (flag), stops the particle on
+//    the edge in the absorbing space (absorbingOpenMeshSpace.cpp:2-24) or redirects the displacement along the edge in the
+//    tangential space (tangentialOpenMeshSpace.cpp:3-42); transported vectors pointing over the boundary are projected
+//    (triangulatedMeshSpace.cpp:411-426).  Boundary VERTEX events take the edge rule of the last edge hit and are flagged.
 //  * vertex crossings (two edges hit), no-hit and runaway loops do not throw: they set a flag bit and
 //    continue/stop in a defined way; the north star excludes them from parity and counts them.
 #pragma once
@@ -18,6 +22,20 @@ namespace orc {
 
 enum WalkFlags { WALK_VERTEX = 1, WALK_NOHIT = 2, WALK_ITERCAP = 4, WALK_NAN = 8, WALK_BORDER = 16 };
 static const int WALK_MAX_CROSSINGS = 100000;
+enum BoundaryMode { BOUNDARY_CLOSED = 0, BOUNDARY_ABSORBING = 1, BOUNDARY_TANGENTIAL = 2 };
+
+// triangulatedMeshSpace::projectVectorsIfOverBoundary (:411-426) with projectVectorOrthogonalToDirection (meshUtilities.cpp:125-129)
+inline void projectVectorsIfOverBoundary(V3* T, int nT, const V3& orthogonal, const V3& inward)
+{
+    bool pointsOut = dot(orthogonal, inward) < 0;
+    for (int i = 0; i < nT; ++i) {
+        bool along = dot(T[i], orthogonal) > 0;
+        if ((pointsOut && along) || (!pointsOut && !along)) {
+            V3 dhat = orthogonal / norm(orthogonal);
+            T[i] = T[i] - dot(T[i], dhat) * dhat;
+        }
+    }
+}
 
 inline void belowZeroClamp(double b[3], double tol = 1e-11) // meshUtilities.cpp:138-150
 {
@@ -93,7 +111,8 @@ inline int edgeHits(const double S[3], const double E[3], int lastEdge, int hitK
 }
 
 // Returns flag word; crossings (optional) counts edge hops.
-inline int transport(const Mesh& m, int& face, double bary[3], V3& disp, V3* T, int nT, bool strictTrig = false, int* crossings = nullptr)
+inline int transport(const Mesh& m, int& face, double bary[3], V3& disp, V3* T, int nT, bool strictTrig = false, int* crossings = nullptr,
+                     int boundaryMode = BOUNDARY_CLOSED)
 {
     int flags = 0;
     int f = face;
@@ -139,10 +158,40 @@ inline int transport(const Mesh& m, int& face, double bary[3], V3& disp, V3* T, 
         int k = nh >= 2 ? hk[1] : hk[0];
         if (nh >= 2) flags |= WALK_VERTEX;                 // :520-532 (see header: treated as a crossing of the last hit edge)
         int g = m.adj[3 * f + k];
-        if (g < 0) {                                       // :547-548 border edge in a closed space (reference throws)
+        if (g < 0) {                                       // border edge
             flags |= WALK_BORDER;
-            E[0] = S[0], E[1] = S[1], E[2] = S[2];
-            break;
+            if (boundaryMode == BOUNDARY_CLOSED) {         // :547-548 (the closed space throws)
+                E[0] = S[0], E[1] = S[1], E[2] = S[2];
+                break;
+            }
+            const V3 &ev1 = m.v[m.c[3 * f + (k + 1) % 3]], &ev2 = m.v[m.c[3 * f + (k + 2) % 3]], &inner = m.v[m.c[3 * f + k]];
+            V3 edge = ev2 - ev1;
+            V3 orth = cross(n, edge);
+            orth = orth / norm(orth);
+            V3 inward = inner - p;                         // p = point(sourceFace, sourceBCs) = the intersection point
+            if (boundaryMode == BOUNDARY_ABSORBING) {      // absorbingOpenMeshSpace.cpp:2-24: stop on the edge
+                if (nT > 0) projectVectorsIfOverBoundary(T, nT, orth, inward);
+                E[0] = S[0], E[1] = S[1], E[2] = S[2];
+                break;
+            }
+            // tangentialOpenMeshSpace.cpp:3-42: slide along the edge in the direction that overlaps the displacement
+            V3 fwd = edge / norm(edge);
+            V3 back = ev1 - ev2;
+            V3 bwd = back / norm(back);
+            double len = norm(disp);                       // NB the reference uses the pre-hop displacement (source -> target)
+            V3 dhat = disp / len;
+            double fd = dot(dhat, fwd), bd = dot(dhat, bwd);
+            projectVectorsIfOverBoundary(T, nT, orth, inward);
+            if (fd <= 0 && bd <= 0) {                      // exactly perpendicular: nothing left to slide (the reference then
+                E[0] = S[0], E[1] = S[1], E[2] = S[2];     // leaves the particle at a target outside the face; we stop on the edge)
+                break;
+            }
+            if (fd > bd) disp = (fd * len) * fwd;
+            else disp = (bd * len) * bwd;
+            q = p + disp;
+            last = -1;
+            nCross++;
+            continue;
         }
         V3 n2 = m.normal(g);                               // :626
         double c = dot(n, n2);                             // :627

@@ -92,6 +92,10 @@ class Oracle:
     def set_options(self, use_cell_list=True, strict_trig=False, threads=1):
         self.L.orc_set_options(self.h, int(use_cell_list), int(strict_trig), int(threads))
 
+    def set_boundary(self, mode):
+        """0 closed (triangulatedMeshSpace), 1 absorbing, 2 tangential (openMeshSpace variants)."""
+        self.L.orc_set_boundary(self.h, int(mode))
+
     def set_cell_domain(self, mn, mx):
         mn = np.ascontiguousarray(mn, np.float64)
         mx = np.ascontiguousarray(mx, np.float64)

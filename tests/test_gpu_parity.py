@@ -268,6 +268,64 @@ def test_transport_per_call_with_vectors(gpu_ctx_factory):
     assert np.array_equal(gf2[ok], gf[ok]) and np.array_equal(gb2[ok], gb[ok])
 
 
+# ------------------------------------------------------------------------------ open meshes
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("sheet", ["plane", "bowl"])
+def test_open_mesh_boundary_rules(mode, sheet, gpu_ctx_factory):
+    """absorbingOpenMeshSpace / tangentialOpenMeshSpace (openMeshSpace.cpp:114-238): the walker stops on, or slides along,
+    border edges and projects transported vectors that point over the boundary.  Bit-exact against the oracle except
+    flagged vertex events; border events themselves are part of the compared set."""
+    V, F = meshes.plane_grid(12, 12, 2.0, 2.0) if sheet == "plane" else meshes.bowl(16, 16)
+    corners = meshes.reference_corners(F)
+    orc = Oracle(V, corners)
+    orc.set_boundary(mode)
+    ctx = gpu_ctx_factory()
+    ctx.set_mesh(V, corners)
+    ctx.set_boundary(mode)
+    rng = np.random.default_rng(21 + mode)
+    n = 2000
+    face, bary = random_positions(len(F), n, rng)
+    vecs = np.stack([random_velocities(V, corners, face, 1.0, rng) for _ in range(2)], 1)
+    disp = random_velocities(V, corners, face, 1.0, rng) * rng.uniform(0.0, 1.5, n)[:, None]
+    of, ob, od, ov, ofl, _ = orc.transport(face, bary, disp, vecs)
+    gf, gb, gd, gv, gfl = ctx.transport(face, bary, disp, vecs)
+    assert np.array_equal(ofl, gfl)
+    assert (ofl & 16).sum() > 200                                                          # many particles met the border
+    ok = (ofl & ~16) == 0
+    assert ok.mean() > 0.95
+    assert np.array_equal(of[ok], gf[ok]) and np.array_equal(ob[ok], gb[ok])
+    assert np.array_equal(ov[ok], gv[ok]) and np.array_equal(od[ok], gd[ok])
+    assert np.all(gb[ok] >= 0)                                                             # nobody left the sheet
+    # the closed rule on the same inputs only flags (and differs from the open rules for the flagged particles)
+    ctx.set_boundary(0)
+    cf, cb, _, cv, cfl = ctx.transport(face, bary, disp, vecs)
+    assert np.array_equal(cfl & 16, gfl & 16) or mode == 2                                 # tangential slides may meet more borders
+    inside = gfl == 0
+    assert np.array_equal(cf[inside], gf[inside]) and np.array_equal(cb[inside], gb[inside])
+    # a short NVE run with the fused step on the open sheet: same trajectory as the oracle
+    N = 300
+    corners, face, bary, vel = make_state(V, F, N)
+    _, _, area = orc.mesh_info()
+    rc = interaction_range(area, N)
+    kind, params = force_params("harmonic", k=1.0, sigma=rc)
+    for sim in (orc, ctx):
+        sim.set_boundary(mode)
+        sim.set_submeshing(True, rc)
+        sim.set_state(face, bary, vel * 2)
+        sim.compute_forces(kind, params)
+    flagged = np.zeros(N, bool)
+    for _ in range(4):
+        orc.run_nve(kind, params, 0.01, 10)
+        ctx.step_nve(kind, params, 0.01, 10)
+        flagged |= ((orc.walk_flags() | ctx.walk_flags()) & ~16) != 0
+    of, ob, ov, ofr = orc.get_state()
+    gf, gb, gv, gfr = ctx.get_state()
+    ok = ~flagged
+    assert ok.sum() >= N - 5 and orc.counters()["border"] > 0 and ctx.counters()["walk_border"] == orc.counters()["border"]
+    assert np.array_equal(of[ok], gf[ok])
+    assert np.max(np.abs(ob - gb)[ok]) < TOL_TRAJ and np.max(np.abs(ov - gv)[ok]) < TOL_TRAJ
+
+
 # ------------------------------------------------------------------------------ golden fixtures
 def test_golden_bruteforce_geodesics(gpu_ctx_factory):
     g = np.load(os.path.join(GOLDEN, "bruteforce_geodesics.npz"))

@@ -344,3 +344,70 @@ def test_oracle_matches_its_committed_regression_fixture():
         orc.run_nve(kind, params, 0.01, 50)
         f2, b2, v2, fr2 = orc.get_state()
         assert np.array_equal(f2, g[key + "/face50"]) and np.array_equal(b2, g[key + "/bary50"]) and np.array_equal(v2, g[key + "/vel50"])
+
+
+# --------------------------------------------------------------------------------- open meshes
+def _open_plane():
+    V, F = meshes.plane_grid(8, 8, 1.0, 1.0)
+    return V, F, meshes.reference_corners(F)
+
+
+def test_absorbing_boundary_stops_on_the_edge_and_projects_vectors():
+    """absorbingOpenMeshSpace::updateAtBoundaryEdge (absorbingOpenMeshSpace.cpp:2-24): the particle stops where its path
+    meets the border; transported vectors lose their outward component (triangulatedMeshSpace.cpp:411-426)."""
+    V, F, corners = _open_plane()
+    orc = Oracle(V, corners)
+    orc.set_boundary(1)
+    from test_oracle_geodesic import _locate
+
+    f, b = _locate(V, corners, np.array([0.52, 0.47, 0.0]))
+    disp = np.array([0.8, 0.1, 0.0])
+    vecs = np.array([[[1.0, 0.3, 0.0], [-1.0, 0.2, 0.0]]])
+    f2, b2, d2, v2, flags, cr = orc.transport([f], [b], [disp], vecs)
+    P = orc.euclidean(f2, b2)[0]
+    y_hit = 0.47 + 0.1 * (1.0 - 0.52) / 0.8
+    assert flags[0] == 16 and abs(P[0] - 1.0) < 1e-9 and abs(P[1] - y_hit) < 1e-9
+    assert np.allclose(v2[0, 0], [0.0, 0.3, 0.0], atol=1e-12)       # pointed over the boundary: outward part removed
+    assert np.allclose(v2[0, 1], [-1.0, 0.2, 0.0], atol=1e-12)      # pointed inward: untouched
+    # the closed space only flags the event and stops (the reference throws there)
+    orc.set_boundary(0)
+    f3, b3, _, v3, fl3, _ = orc.transport([f], [b], [disp], vecs)
+    assert fl3[0] == 16 and np.allclose(v3[0, 0], [1.0, 0.3, 0.0], atol=1e-12)
+    # a displacement that stays inside is unaffected by the boundary rule
+    orc.set_boundary(1)
+    f4, b4, _, _, fl4, _ = orc.transport([f], [b], [np.array([0.2, 0.1, 0.0])])
+    assert fl4[0] == 0 and np.allclose(orc.euclidean(f4, b4)[0], [0.72, 0.57, 0.0], atol=1e-9)
+
+
+def test_tangential_boundary_slides_along_the_edge():
+    """tangentialOpenMeshSpace::updateAtBoundaryEdge (tangentialOpenMeshSpace.cpp:3-42): the displacement is redirected
+    along the border edge in the direction that overlaps it, with the length of the displacement the face iteration
+    started with times that overlap."""
+    V, F, corners = _open_plane()
+    orc = Oracle(V, corners)
+    orc.set_boundary(2)
+    from test_oracle_geodesic import _locate
+
+    f, b = _locate(V, corners, np.array([0.52, 0.47, 0.0]))
+    for dy in (0.1, -0.1):
+        disp = np.array([0.8, dy, 0.0])
+        f2, b2, d2, v2, flags, cr = orc.transport([f], [b], [disp], np.array([[[1.0, 0.3, 0.0]]]))
+        P = orc.euclidean(f2, b2)[0]
+        y_hit = 0.47 + dy * (1.0 - 0.52) / 0.8
+        assert flags[0] == 16 and abs(P[0] - 1.0) < 1e-9
+        assert (P[1] - y_hit) * dy > 0 and abs(P[1] - y_hit) < abs(dy)   # slid in the direction of the tangential component
+        assert np.allclose(v2[0, 0], [0.0, 0.3, 0.0], atol=1e-12)
+    # an NVE run on an open sheet keeps every particle on the mesh (short enough that no two particles have yet slid into
+    # the same corner of the sheet: coincident particles have no tangent, in the reference as here)
+    N = 60
+    corners, face, bary, vel = make_state(V, F, N)
+    orc.set_submeshing(True, 0.2)
+    orc.set_state(face, bary, vel * 2)
+    kind, params = force_params("harmonic", k=1.0, sigma=0.2)
+    orc.compute_forces(kind, params)
+    orc.run_nve(kind, params, 0.01, 40)
+    f3, b3, v3, _ = orc.get_state()
+    P = orc.euclidean(f3, b3)
+    c = orc.counters()
+    assert c["nan"] == 0 and c["border"] > 100
+    assert np.all(b3 >= 0) and np.all((P[:, :2] >= -1e-9) & (P[:, :2] <= 1 + 1e-9))
