@@ -363,7 +363,8 @@ __device__ __forceinline__ int walkOne(const MeshDev& m, int& face, double bary[
             d3 dhat = disp / len;
             double fd = dot(dhat, fwd), bd = dot(dhat, bwd);
             projectVectorsIfOverBoundary<NT>(T, nT, orth, inward);
-            if (fd <= 0 && bd <= 0) {
+            double slide = (fd > bd ? fd : bd) * len;
+            if (!(slide > 1e-9 * norm(edge))) { // nothing left to slide, or a slide at the scale of the 1e-11 source clamp (limit cycle in sheet corners)
                 E[0] = S[0], E[1] = S[1], E[2] = S[2];
                 break;
             }

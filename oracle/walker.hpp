@@ -18,6 +18,10 @@
 #include "mesh.hpp"
 #include <vector>
 
+#ifndef ORC_WALK_TRACE
+#define ORC_WALK_TRACE(...) ((void)0)
+#endif
+
 namespace orc {
 
 enum WalkFlags { WALK_VERTEX = 1, WALK_NOHIT = 2, WALK_ITERCAP = 4, WALK_NAN = 8, WALK_BORDER = 16 };
@@ -156,6 +160,8 @@ inline int transport(const Mesh& m, int& face, double bary[3], V3& disp, V3* T, 
         S[0] = I[0], S[1] = I[1], S[2] = I[2];             // :517
         p = x;                                             // :518
         int k = nh >= 2 ? hk[1] : hk[0];
+        ORC_WALK_TRACE("hop %d face %d nh %d k %d S=(%.3e %.3e %.3e) E=(%.3e %.3e %.3e) |disp| %.3e adj %d\n", nCross, f, nh, k, S[0], S[1], S[2], E[0],
+                       E[1], E[2], norm(disp), m.adj[3 * f + k]);
         if (nh >= 2) flags |= WALK_VERTEX;                 // :520-532 (see header: treated as a crossing of the last hit edge)
         int g = m.adj[3 * f + k];
         if (g < 0) {                                       // border edge
@@ -182,8 +188,12 @@ inline int transport(const Mesh& m, int& face, double bary[3], V3& disp, V3* T, 
             V3 dhat = disp / len;
             double fd = dot(dhat, fwd), bd = dot(dhat, bwd);
             projectVectorsIfOverBoundary(T, nT, orth, inward);
-            if (fd <= 0 && bd <= 0) {                      // exactly perpendicular: nothing left to slide (the reference then
-                E[0] = S[0], E[1] = S[1], E[2] = S[2];     // leaves the particle at a target outside the face; we stop on the edge)
+            double slide = (fd > bd ? fd : bd) * len;
+            // exactly perpendicular: nothing left to slide (the reference then leaves the particle at a target outside the
+            // face; we stop on the edge).  Likewise when the slide is below 1e-9 edge lengths, i.e. at the scale of the 1e-11 barycentric clamp of the source
+            // point: in a corner of the sheet the two clamps otherwise feed a limit cycle (the reference never leaves it).
+            if (!(slide > 1e-9 * norm(edge))) {
+                E[0] = S[0], E[1] = S[1], E[2] = S[2];
                 break;
             }
             if (fd > bd) disp = (fd * len) * fwd;

@@ -302,7 +302,9 @@ def test_open_mesh_boundary_rules(mode, sheet, gpu_ctx_factory):
     assert np.array_equal(cfl & 16, gfl & 16) or mode == 2                                 # tangential slides may meet more borders
     inside = gfl == 0
     assert np.array_equal(cf[inside], gf[inside]) and np.array_equal(cb[inside], gb[inside])
-    # a short NVE run with the fused step on the open sheet: same trajectory as the oracle
+    # NVE steps with the fused step on the open sheet.  A particle parked in a corner of the sheet is a vertex-degenerate
+    # event every step (flagged) and reacts discontinuously to 1e-13 differences, so the GPU is re-seeded with the oracle's
+    # state before every step and the one-step map is compared: bit-exact faces, 1e-9 on everything else.
     N = 300
     corners, face, bary, vel = make_state(V, F, N)
     _, _, area = orc.mesh_info()
@@ -313,18 +315,20 @@ def test_open_mesh_boundary_rules(mode, sheet, gpu_ctx_factory):
         sim.set_submeshing(True, rc)
         sim.set_state(face, bary, vel * 2)
         sim.compute_forces(kind, params)
-    flagged = np.zeros(N, bool)
-    for _ in range(4):
-        orc.run_nve(kind, params, 0.01, 10)
-        ctx.step_nve(kind, params, 0.01, 10)
-        flagged |= ((orc.walk_flags() | ctx.walk_flags()) & ~16) != 0
-    of, ob, ov, ofr = orc.get_state()
-    gf, gb, gv, gfr = ctx.get_state()
-    ok = ~flagged
-    assert ok.sum() >= N - 5 and orc.counters()["border"] > 0 and ctx.counters()["walk_border"] == orc.counters()["border"]
-    assert np.array_equal(of[ok], gf[ok])
-    assert np.max(np.abs(ob - gb)[ok]) < TOL_TRAJ and np.max(np.abs(ov - gv)[ok]) < TOL_TRAJ
-
+    compared = 0
+    for _ in range(40):
+        of, ob, ov, ofr = orc.get_state()
+        ctx.set_state(of, ob, ov, ofr)
+        orc.run_nve(kind, params, 0.01, 1)
+        ctx.step_nve(kind, params, 0.01, 1)
+        assert np.array_equal(orc.walk_flags(), ctx.walk_flags())
+        ok = (orc.walk_flags() & ~16) == 0
+        of, ob, ov, ofr = orc.get_state()
+        gf, gb, gv, gfr = ctx.get_state()
+        assert np.array_equal(of[ok], gf[ok])
+        assert np.max(np.abs(ob - gb)[ok]) < 1e-9 and np.max(np.abs(ov - gv)[ok]) < 1e-9
+        compared += int(ok.sum())
+    assert compared > 39 * N and orc.counters()["border"] > 100 and ctx.counters()["walk_border"] == orc.counters()["border"]
 
 # ------------------------------------------------------------------------------ golden fixtures
 def test_golden_bruteforce_geodesics(gpu_ctx_factory):
