@@ -350,6 +350,8 @@ def main():
             "data": "synthetic",
             "config": {"workload": args.workload, "N": N, "faces": int(len(F)), "vertices": int(len(V)), "r_c": rc, "dt": args.dt,
                        "potential": "harmonic k=1", "integrator": "velocity-Verlet NVE", "sharding": "particle blocks (mpiModel), mesh replicated",
+                       "exchange": "none (1 rank)" if world == 1 else ("peer-memory stores fused into the walker + flag barrier (NVLink, CUDA IPC)"
+                                                                        if ctx.comm_info()[2] else "NCCL all-gather"),
                        "l2": "hot-L2 run reported separately" if args.no_flush else "L2 flushed (256 MiB write, untimed) between timed steps"},
             "geodesic_queries_per_s": queries / (geo_total_ms * 1e-3),
             "queries_per_step": queries / args.steps,

@@ -22,7 +22,7 @@ SUM, MAX = 0, 1
 COUNTER_NAMES = ["walk_vertex", "walk_nohit", "walk_itercap", "walk_nan", "walk_border", "disconnected", "ties", "crossings",
                  "windows", "pseudo_sources", "patch_faces", "patch_verts", "queries", "sources", "tier_retry", "overflow",
                  "kernels", "kmax_overflow", "ovf_candidates", "ovf_faces", "ovf_verts", "ovf_ring", "clk_batch", "clk_fan", "clk_prop",
-                 "clk_patch", "clk_total"]
+                 "clk_patch", "clk_total", "peer_timeout"]
 NUM_COUNTERS = 32
 
 # every symbol include/css_api.h declares (tests check that the library exports all of them)
@@ -31,7 +31,7 @@ API_SYMBOLS = [
     "css_set_options", "css_set_boundary", "css_euclidean", "css_distance", "css_transport", "css_set_state", "css_get_state", "css_set_velocities",
     "css_set_forces", "css_find_neighbors", "css_get_neighbors", "css_compute_forces", "css_compute_energy", "css_move",
     "css_get_walk_flags", "css_step_nve", "css_step_gd", "css_nvt_init", "css_step_nvt", "css_nvt_state", "css_fire_init",
-    "css_fire_minimize", "css_max_force", "css_force_norm", "css_comm_unique_id", "css_comm_init", "css_gather_positions",
+    "css_fire_minimize", "css_max_force", "css_force_norm", "css_comm_unique_id", "css_comm_init", "css_comm_info", "css_gather_positions",
     "css_reduce", "css_counters", "css_synchronize", "css_device_positions", "css_last_kernel_ms", "css_set_timing", "css_last_stage_ms",
     "css_timer_record", "css_timer_elapsed_ms",
 ]
@@ -295,6 +295,12 @@ class Context:
 
     def gather_positions(self):
         self._ck(self.L.css_gather_positions(self.h))
+
+    def comm_info(self):
+        """(rank, nranks, peer_exchange): peer_exchange is True when the exchange after every move runs over peer memory."""
+        r, n, p = C.c_int(0), C.c_int(0), C.c_int(0)
+        self._ck(self.L.css_comm_info(self.h, C.byref(r), C.byref(n), C.byref(p)))
+        return r.value, n.value, bool(p.value)
 
     def reduce(self, op, data):
         data = np.array(data, np.float64)

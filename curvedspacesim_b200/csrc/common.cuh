@@ -89,6 +89,7 @@ enum {
     C_PSEUDO, C_PATCH_FACES, C_PATCH_VERTS, C_QUERIES, C_SOURCES, C_TIER_RETRY, C_OVERFLOW, C_KERNELS, C_KMAX_OVERFLOW,
     C_OVF_REASON /* 18..21: candidates, faces, vertices, ring */,
     C_CLK_BATCH = 22, C_CLK_FAN = 23, C_CLK_PROP = 24, C_CLK_PATCH = 25, C_CLK_TOTAL = 26, /* summed per-warp clock64 cycles */
+    C_PEER_TIMEOUT = 27, /* a peer-exchange flag wait gave up (a rank died or left the collective sequence) */
     NUM_COUNTERS = 32
 };
 #define CSS_WALK_MAX_CROSSINGS 100000

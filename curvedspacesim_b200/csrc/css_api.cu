@@ -93,6 +93,16 @@ struct css_ctx {
     double* d_recvD = nullptr;
     int capComm = 0;
     double* d_redBuf = nullptr;
+    // peer-memory exchange window (kernels.h PeerWin): cudaMalloc + CUDA IPC, mapped by every rank of the node
+    bool p2pEnabled = true; // CSS_P2P=0 keeps the NCCL all-gather
+    bool p2pFailed = false; // IPC mapping is not possible here: NCCL from now on (decided collectively)
+    void* winLocal = nullptr;
+    void* winPeer[CSS_MAX_PEERS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int winCap = 0; // particles
+    PeerWin pw{};
+    unsigned long long* d_epoch = nullptr;
+    unsigned* d_ticket = nullptr;
+    unsigned char* d_ipcBuf = nullptr;
     // CUDA graph of one fused NVE step (walker, gather, cell list, stages 1-2, retry tiers): one launch per step
     bool useGraph = true, capturing = false;
     cudaGraphExec_t nveExec = nullptr;
@@ -109,6 +119,7 @@ struct css_ctx {
 
 // event record that stays a real, queryable event when the stream is being captured into a CUDA graph
 static void recordEvent(css_ctx* c, cudaEvent_t e);
+static void releasePeerWindow(css_ctx* c);
 
 static int fail(css_ctx* c, int code, const char* fmt, ...)
 {
@@ -143,6 +154,100 @@ static void recordEvent(css_ctx* c, cudaEvent_t e)
 {
     if (c->capturing) cudaEventRecordWithFlags(e, c->st, cudaEventRecordExternal);
     else cudaEventRecord(e, c->st);
+}
+
+// ------------------------------------------------------------------------------- peer exchange window
+static void releasePeerWindow(css_ctx* c)
+{
+    for (int r = 0; r < CSS_MAX_PEERS; ++r) {
+        if (c->winPeer[r] && c->winPeer[r] != c->winLocal) cudaIpcCloseMemHandle(c->winPeer[r]);
+        c->winPeer[r] = nullptr;
+    }
+    if (c->winLocal) cudaFree(c->winLocal);
+    c->winLocal = nullptr;
+    c->winCap = 0;
+    c->pw = PeerWin{};
+}
+static size_t peerFaceBytes(int cap) { return ((size_t)cap * sizeof(int) + 255) / 256 * 256; }
+
+// Collective over the communicator (every rank calls it with the same nTotal, from the same place of the same call
+// sequence): (re)creates the exchange windows for at least nTotal particles and maps every peer's window.  On any
+// failure all ranks agree to stay on the NCCL all-gather.
+static int ensurePeerWindow(css_ctx* ctx)
+{
+    if (ctx->nranks <= 1 || !ctx->p2pEnabled || ctx->p2pFailed || ctx->nranks > CSS_MAX_PEERS) return CSS_OK;
+    if (ctx->pw.n > 1 && ctx->winCap >= ctx->nTotal) return CSS_OK;
+    if (ctx->capturing) return fail(ctx, CSS_ESTATE, "peer window must exist before a step is captured");
+    const int R = ctx->nranks;
+    if (!ctx->d_ipcBuf) {
+        CU(regrow(ctx->d_ipcBuf, 128 * (size_t)(CSS_MAX_PEERS + 1)));
+        CU(regrow(ctx->d_epoch, 1));
+        CU(regrow(ctx->d_ticket, 1));
+        CU(cudaMemsetAsync(ctx->d_ticket, 0, sizeof(unsigned), ctx->st));
+    }
+    struct Msg {
+        cudaIpcMemHandle_t h;
+        int ok, pad[15];
+    };
+    static_assert(sizeof(Msg) == 128, "IPC message size");
+    auto exchange = [&](const Msg& mine, std::vector<Msg>& all) -> int {
+        CU(cudaMemcpyAsync(ctx->d_ipcBuf, &mine, sizeof(Msg), cudaMemcpyHostToDevice, ctx->st));
+        NC(ncclAllGather(ctx->d_ipcBuf, ctx->d_ipcBuf + 128, sizeof(Msg), ncclUint8, ctx->comm, ctx->st));
+        all.resize(R);
+        CU(cudaMemcpyAsync(all.data(), ctx->d_ipcBuf + 128, sizeof(Msg) * R, cudaMemcpyDeviceToHost, ctx->st));
+        CU(cudaStreamSynchronize(ctx->st));
+        return CSS_OK;
+    };
+    std::vector<Msg> all;
+    Msg mine{};
+    // 1. nobody is still using the old windows (all earlier exchanges are stream-ordered before this all-gather)
+    int rc = exchange(mine, all);
+    if (rc) return rc;
+    releasePeerWindow(ctx);
+    // 2. new local window, flags and epoch zeroed before anybody can signal
+    const int cap = ctx->capTotal;
+    const size_t bytes = CSS_PEER_FLAG_BYTES + peerFaceBytes(cap) + sizeof(double) * 3 * (size_t)cap;
+    mine.ok = cudaMalloc(&ctx->winLocal, bytes) == cudaSuccess;
+    if (mine.ok) {
+        mine.ok = cudaMemsetAsync(ctx->winLocal, 0, bytes, ctx->st) == cudaSuccess && cudaMemsetAsync(ctx->d_epoch, 0, 8, ctx->st) == cudaSuccess &&
+                  cudaStreamSynchronize(ctx->st) == cudaSuccess && cudaIpcGetMemHandle(&mine.h, ctx->winLocal) == cudaSuccess;
+    }
+    (void)cudaGetLastError();
+    rc = exchange(mine, all);
+    if (rc) return rc;
+    bool okAll = true;
+    for (int r = 0; r < R; ++r) okAll = okAll && all[r].ok;
+    // 3. map the peers
+    Msg st2{};
+    st2.ok = okAll;
+    if (okAll) {
+        for (int r = 0; r < R && st2.ok; ++r) {
+            if (r == ctx->rank) ctx->winPeer[r] = ctx->winLocal;
+            else if (cudaIpcOpenMemHandle(&ctx->winPeer[r], all[r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                ctx->winPeer[r] = nullptr;
+                st2.ok = 0;
+                (void)cudaGetLastError();
+            }
+        }
+    }
+    rc = exchange(st2, all);
+    if (rc) return rc;
+    for (int r = 0; r < R; ++r) okAll = okAll && all[r].ok;
+    if (!okAll) { // every rank takes the same decision
+        releasePeerWindow(ctx);
+        ctx->p2pFailed = true;
+        return CSS_OK;
+    }
+    ctx->winCap = cap;
+    ctx->pw.n = R, ctx->pw.rank = ctx->rank;
+    for (int r = 0; r < R; ++r) {
+        unsigned char* base = (unsigned char*)ctx->winPeer[r];
+        ctx->pw.flags[r] = (unsigned long long*)base;
+        ctx->pw.face[r] = (int*)(base + CSS_PEER_FLAG_BYTES);
+        ctx->pw.bary[r] = (double*)(base + CSS_PEER_FLAG_BYTES + peerFaceBytes(cap));
+    }
+    ctx->nveCalls = 0;
+    return CSS_OK;
 }
 
 #pragma GCC visibility push(default)
@@ -184,6 +289,7 @@ int css_create(css_ctx** out, int device)
     if (const char* v = getenv("CSS_NO_GRAPH")) ctx->useGraph = atoi(v) == 0;
     if (const char* v = getenv("CSS_WIN_LEAN")) ctx->winLean = atoi(v) != 0;
     if (const char* v = getenv("CSS_WIN_WPB")) ctx->winWpb = std::max(1, std::min(4, atoi(v)));
+    if (const char* v = getenv("CSS_P2P")) ctx->p2pEnabled = atoi(v) != 0;
     *out = ctx;
     return CSS_OK;
 }
@@ -194,13 +300,14 @@ int css_destroy(css_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->st);
     if (ctx->nveExec) cudaGraphExecDestroy(ctx->nveExec);
+    releasePeerWindow(ctx);
     if (ctx->comm) ncclCommDestroy(ctx->comm);
     void* ptrs[] = {ctx->d_vert,   ctx->d_corner,    ctx->d_adj,     ctx->d_saddle,  ctx->d_face,     ctx->d_bary,    ctx->d_eucl,
                     ctx->d_vel,    ctx->d_frc,       ctx->d_disp,    ctx->d_walkFlags, ctx->d_cellOf, ctx->d_cellCount, ctx->d_cellStart,
                     ctx->d_blockSums, ctx->d_fill,   ctx->d_tmpItems, ctx->d_items,  ctx->d_nbrCount, ctx->d_nbrIdx,  ctx->d_nbrDist,
                     ctx->d_nbrTs,  ctx->d_nbrTe,     ctx->d_work,    ctx->d_retry[0], ctx->d_retry[1], ctx->d_retry[2], ctx->d_gws,
                     ctx->d_partial, ctx->d_red,      ctx->d_counters, ctx->d_sendI,  ctx->d_sendD,    ctx->d_recvI,   ctx->d_recvD,
-                    ctx->d_redBuf,  ctx->d_geo,       ctx->d_records, ctx->d_recordsL};
+                    ctx->d_redBuf,  ctx->d_geo,       ctx->d_records, ctx->d_recordsL, ctx->d_epoch, ctx->d_ticket, ctx->d_ipcBuf};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (auto& e : ctx->ev)
@@ -755,6 +862,10 @@ static int checkCapacity(css_ctx* ctx, bool* rerun)
         CU(cudaMemsetAsync(ctx->d_counters + C_OVERFLOW, 0, sizeof(unsigned long long), ctx->st));
         return fail(ctx, CSS_ECAPACITY, "%llu sources exceeded the patch/window capacity of every tier", h[C_OVERFLOW]);
     }
+    if (h[C_PEER_TIMEOUT]) {
+        CU(cudaMemsetAsync(ctx->d_counters + C_PEER_TIMEOUT, 0, sizeof(unsigned long long), ctx->st));
+        return fail(ctx, CSS_ENCCL, "peer position exchange timed out (%llu flag waits gave up): a rank left the collective sequence", h[C_PEER_TIMEOUT]);
+    }
     return CSS_OK;
 }
 
@@ -876,12 +987,26 @@ int css_compute_energy(css_ctx* ctx, int kind, const double* params, double* ene
 
 static int moveImpl(css_ctx* ctx, int transportForce, int transportVelocity, int mode, double dt)
 {
+    int rc = ensurePeerWindow(ctx);
+    if (rc) return rc;
+    const bool p2p = ctx->nranks > 1 && ctx->pw.n > 1;
+    if (p2p) { // the staging copies of the previous exchange must have been drained everywhere before they are overwritten
+        launchPeerWaitConsumed(ctx->st, ctx->pw, ctx->d_epoch, ctx->d_counters);
+        ctx->hostKernels++;
+    }
     if (ctx->timing) recordEvent(ctx, ctx->ev[3]);
     launchWalk(ctx->st, meshDev(ctx), ctx->nLocal, ctx->minIdx, ctx->d_face, ctx->d_bary, ctx->d_disp, ctx->d_vel, ctx->d_frc, transportForce,
-               transportVelocity, mode, dt, ctx->d_walkFlags, ctx->d_counters);
+               transportVelocity, mode, dt, ctx->d_walkFlags, ctx->d_counters, p2p ? ctx->pw : PeerWin{});
     ctx->hostKernels++;
     if (ctx->timing) recordEvent(ctx, ctx->ev[4]);
     ctx->nbrValid = false;
+    if (p2p) {
+        launchPeerBarrier(ctx->st, ctx->pw, ctx->d_epoch, ctx->d_counters);
+        launchPeerCopy(ctx->st, ctx->pw, ctx->nTotal, ctx->minIdx, ctx->minIdx + ctx->nLocal, ctx->d_face, ctx->d_bary, ctx->d_epoch, ctx->d_ticket);
+        ctx->hostKernels += 2;
+        CU(cudaGetLastError());
+        return CSS_OK;
+    }
     if (ctx->nranks > 1) return css_gather_positions(ctx);
     return CSS_OK;
 }
@@ -929,7 +1054,9 @@ static uint64_t nveGraphKey(css_ctx* ctx, const ForceParams& fp, double range, d
     void* ptrs[] = {ctx->d_vert, ctx->d_corner, ctx->d_adj, ctx->d_geo, ctx->d_saddle, ctx->d_face, ctx->d_bary, ctx->d_eucl, ctx->d_vel, ctx->d_frc,
                     ctx->d_disp, ctx->d_walkFlags, ctx->d_cellOf, ctx->d_cellCount, ctx->d_cellStart, ctx->d_blockSums, ctx->d_fill, ctx->d_tmpItems,
                     ctx->d_items, ctx->d_nbrCount, ctx->d_nbrIdx, ctx->d_nbrDist, ctx->d_nbrTs, ctx->d_nbrTe, ctx->d_retry[0], ctx->d_retry[1],
-                    ctx->d_retry[2], ctx->d_gws, ctx->d_records, ctx->d_recordsL, ctx->d_recvI, ctx->d_recvD, (void*)ctx->comm};
+                    ctx->d_retry[2], ctx->d_gws, ctx->d_records, ctx->d_recordsL, ctx->d_recvI, ctx->d_recvD, (void*)ctx->comm, ctx->winLocal,
+                    ctx->winPeer[0], ctx->winPeer[1], ctx->winPeer[2], ctx->winPeer[3], ctx->winPeer[4], ctx->winPeer[5], ctx->winPeer[6],
+                    ctx->winPeer[7]};
     MIX(ptrs);
 #undef MIX
     return h ? h : 1;
@@ -1218,6 +1345,8 @@ int css_comm_init(css_ctx* ctx, int rank, int nranks, const void* id128)
 {
     if (!ctx || nranks < 1 || rank < 0 || rank >= nranks) return CSS_EINVAL;
     BIND();
+    releasePeerWindow(ctx);
+    ctx->p2pFailed = false;
     ctx->rank = rank, ctx->nranks = nranks;
     ctx->nveCalls = 0;
     if (nranks == 1) return CSS_OK;
@@ -1226,6 +1355,14 @@ int css_comm_init(css_ctx* ctx, int rank, int nranks, const void* id128)
     std::memcpy(&id, id128, 128);
     NC(ncclCommInitRank(&ctx->comm, nranks, id, rank));
     CU(regrow(ctx->d_redBuf, 64 * (size_t)nranks));
+    return CSS_OK;
+}
+int css_comm_info(css_ctx* ctx, int* rank, int* nranks, int* peerExchange)
+{
+    if (!ctx) return CSS_EINVAL;
+    if (rank) *rank = ctx->rank;
+    if (nranks) *nranks = ctx->nranks;
+    if (peerExchange) *peerExchange = ctx->nranks > 1 && ctx->pw.n > 1;
     return CSS_OK;
 }
 // mpiSimulation::synchronizeAndTransferBuffers: every rank contributes a block padded to per = ceil(N/R)

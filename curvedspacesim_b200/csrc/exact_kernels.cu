@@ -407,7 +407,7 @@ __device__ __forceinline__ int walkOne(const MeshDev& m, int& face, double bary[
 // particles [0,n) of this rank; global index = minIdx + i in face/bary
 __global__ void __launch_bounds__(64, 12) k_walk(MeshDev m, int n, int minIdx, int* __restrict__ face, double* __restrict__ bary, double* __restrict__ disp,
                        double* __restrict__ vel, double* __restrict__ frc, int transportForce, int transportVelocity, int mode,
-                       double dt, int* __restrict__ flagsOut, unsigned long long* __restrict__ counters)
+                       double dt, int* __restrict__ flagsOut, unsigned long long* __restrict__ counters, PeerWin pw)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int fl = 0, nc = 0;
@@ -430,6 +430,15 @@ __global__ void __launch_bounds__(64, 12) k_walk(MeshDev m, int n, int minIdx, i
         fl = walkOne<2>(m, f, b, d, T, nT, nc);
         face[gi] = f;
         bary[3 * gi] = b[0], bary[3 * gi + 1] = b[1], bary[3 * gi + 2] = b[2];
+        if (pw.n > 1) { // the exchange step of the multi-rank model, fused: store the new position into every peer's window
+            for (int r = 0; r < pw.n; ++r)
+                if (r != pw.rank) {
+                    pw.face[r][gi] = f;
+                    double* pb = pw.bary[r] + 3 * (size_t)gi;
+                    pb[0] = b[0], pb[1] = b[1], pb[2] = b[2];
+                }
+            __threadfence_system();
+        }
         st3(disp, i, d);
         nT = 0;
         if (transportForce) st3(frc, i, T[nT++]);
@@ -615,11 +624,101 @@ void launchCellBuild(cudaStream_t st, int n, int nCells, const int* cellOf, cons
     }
 }
 void launchWalk(cudaStream_t st, const MeshDev& m, int n, int minIdx, int* face, double* bary, double* disp, double* vel, double* frc,
-                int transportForce, int transportVelocity, int mode, double dt, int* flags, unsigned long long* counters)
+                int transportForce, int transportVelocity, int mode, double dt, int* flags, unsigned long long* counters, const PeerWin& pw)
 {
     if (n > 0)
         k_walk<<<gridFor(n, 64), 64, 0, st>>>(m, n, minIdx, face, bary, disp, vel, frc, transportForce, transportVelocity, mode, dt,
-                                                flags, counters);
+                                                flags, counters, pw);
+}
+
+// ---------------------------------------------------------------------------------- peer-memory exchange
+namespace {
+__device__ __forceinline__ unsigned long long ldAcquireSys(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void stReleaseSys(unsigned long long* p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long globalTimerNs()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// spin until *p >= e; gives up after 10 s (a rank died or left the collective sequence) and counts the event
+__device__ __forceinline__ void waitFlag(const unsigned long long* p, unsigned long long e, unsigned long long* counters)
+{
+    if (ldAcquireSys(p) >= e) return;
+    const unsigned long long t0 = globalTimerNs();
+    while (ldAcquireSys(p) < e) {
+        __nanosleep(64);
+        if (globalTimerNs() - t0 > 10000000000ull) {
+            atomicAdd(counters + C_PEER_TIMEOUT, 1ull);
+            return;
+        }
+    }
+}
+} // namespace
+
+// before the walker: every peer must have drained the previous epoch from its staging copy
+__global__ void k_peer_wait_consumed(PeerWin pw, const unsigned long long* __restrict__ epoch, unsigned long long* counters)
+{
+    const int r = threadIdx.x;
+    if (r < pw.n && r != pw.rank) waitFlag(pw.flags[pw.rank] + (CSS_MAX_PEERS + r) * CSS_PEER_FLAG_STRIDE, *epoch, counters);
+}
+// after the walker: publish "this rank finished epoch e" in every window, wait until every rank did, advance the epoch
+__global__ void k_peer_barrier(PeerWin pw, unsigned long long* epoch, unsigned long long* counters)
+{
+    const int r = threadIdx.x;
+    const unsigned long long e = *epoch + 1;
+    __syncwarp();
+    __threadfence_system();
+    if (r < pw.n && r != pw.rank) stReleaseSys(pw.flags[r] + pw.rank * CSS_PEER_FLAG_STRIDE, e);
+    if (r < pw.n && r != pw.rank) waitFlag(pw.flags[pw.rank] + r * CSS_PEER_FLAG_STRIDE, e, counters);
+    __syncwarp();
+    if (r == 0) *epoch = e;
+}
+// staging -> live arrays for the particles the other ranks own; the last block publishes "this rank drained epoch e"
+__global__ void k_peer_copy(PeerWin pw, int nTotal, int lo, int hi, int* __restrict__ face, double* __restrict__ bary,
+                            const unsigned long long* __restrict__ epoch, unsigned* ticket)
+{
+    const int* sf = pw.face[pw.rank];
+    const double* sb = pw.bary[pw.rank];
+    const int nOther = nTotal - (hi - lo);
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nOther; q += gridDim.x * blockDim.x) {
+        const int i = q < lo ? q : q + (hi - lo);
+        face[i] = __ldcg(sf + i);
+        const double b0 = __ldcg(sb + 3 * (size_t)i), b1 = __ldcg(sb + 3 * (size_t)i + 1), b2 = __ldcg(sb + 3 * (size_t)i + 2);
+        bary[3 * (size_t)i] = b0, bary[3 * (size_t)i + 1] = b1, bary[3 * (size_t)i + 2] = b2;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1) {
+            const unsigned long long e = *epoch;
+            for (int r = 0; r < pw.n; ++r)
+                if (r != pw.rank) stReleaseSys(pw.flags[r] + (CSS_MAX_PEERS + pw.rank) * CSS_PEER_FLAG_STRIDE, e);
+        }
+    }
+}
+void launchPeerWaitConsumed(cudaStream_t st, const PeerWin& pw, const unsigned long long* epoch, unsigned long long* counters)
+{
+    k_peer_wait_consumed<<<1, 32, 0, st>>>(pw, epoch, counters);
+}
+void launchPeerBarrier(cudaStream_t st, const PeerWin& pw, unsigned long long* epoch, unsigned long long* counters)
+{
+    k_peer_barrier<<<1, 32, 0, st>>>(pw, epoch, counters);
+}
+void launchPeerCopy(cudaStream_t st, const PeerWin& pw, int nTotal, int lo, int hi, int* face, double* bary, const unsigned long long* epoch,
+                    unsigned* ticket)
+{
+    int nOther = nTotal - (hi - lo);
+    int blocks = max(1, min(296, gridFor(max(nOther, 1), 256)));
+    k_peer_copy<<<blocks, 256, 0, st>>>(pw, nTotal, lo, hi, face, bary, epoch, ticket);
 }
 void launchTransportGeneric(cudaStream_t st, const MeshDev& m, int n, int* face, double* bary, double* disp, int nVec, double* vecs,
                             int* flags)

@@ -148,8 +148,28 @@ void launchEuclidCell(cudaStream_t st, const MeshDev& m, const CellGrid& g, int 
 int scanBlocks(int nCells);
 void launchCellBuild(cudaStream_t st, int n, int nCells, const int* cellOf, const int* cellCount, int* cellStart, int* blockSums,
                      int* fill, int* tmpItems, int* items);
+// ---- peer-memory position exchange, fused with the walker (replaces the all-gather after every move:
+// mpiSimulation::synchronizeAndTransferBuffers, src/simulation/mpiSimulation.cpp:11-42).  Every rank owns an exchange
+// window (cudaMalloc + CUDA IPC, mapped by all peers over NVLink/NVSwitch): a staging copy of the replicated position
+// arrays indexed by GLOBAL particle index, and two rows of epoch flags.  The walker stores each new position into its
+// own live arrays and into every peer's staging copy; k_peer_barrier publishes "rank r finished epoch e" in every
+// window and waits for all ranks; k_peer_copy moves the other ranks' blocks from staging to the live arrays and
+// publishes "rank r drained epoch e", which the next walker waits for before it overwrites the staging copies.
+#define CSS_MAX_PEERS 8
+#define CSS_PEER_FLAG_STRIDE 16            /* one 128-byte line per writer */
+#define CSS_PEER_FLAG_BYTES 4096           /* arrived[8 x 16] | consumed[8 x 16] (u64), padded */
+struct PeerWin {
+    int n, rank; // n <= 1: no peer exchange
+    int* face[CSS_MAX_PEERS];
+    double* bary[CSS_MAX_PEERS];
+    unsigned long long* flags[CSS_MAX_PEERS];
+};
+void launchPeerWaitConsumed(cudaStream_t st, const PeerWin& pw, const unsigned long long* epoch, unsigned long long* counters);
+void launchPeerBarrier(cudaStream_t st, const PeerWin& pw, unsigned long long* epoch, unsigned long long* counters);
+void launchPeerCopy(cudaStream_t st, const PeerWin& pw, int nTotal, int lo, int hi, int* face, double* bary, const unsigned long long* epoch,
+                    unsigned* ticket);
 void launchWalk(cudaStream_t st, const MeshDev& m, int n, int minIdx, int* face, double* bary, double* disp, double* vel, double* frc,
-                int transportForce, int transportVelocity, int mode, double dt, int* flags, unsigned long long* counters);
+                int transportForce, int transportVelocity, int mode, double dt, int* flags, unsigned long long* counters, const PeerWin& pw);
 void launchTransportGeneric(cudaStream_t st, const MeshDev& m, int n, int* face, double* bary, double* disp, int nVec, double* vecs,
                             int* flags);
 void launchAxpy(cudaStream_t st, int op, int n, double a, double b, double* vel, const double* frc, double* disp);

@@ -141,6 +141,10 @@ int css_force_norm(css_ctx* ctx, double* forceNorm);
 int css_comm_unique_id(void* id128 /*128 bytes out*/);
 int css_comm_init(css_ctx* ctx, int rank, int nranks, const void* id128);
 int css_gather_positions(css_ctx* ctx); /* all-gather (face, bary) of every rank's block into the replicated arrays */
+/* peerExchange = 1 when the exchange after every move runs over peer memory (the walker stores new positions straight into
+ * every rank's CUDA-IPC-mapped window over NVLink, followed by a flag barrier) instead of the NCCL all-gather; decided
+ * collectively at the first move after css_comm_init (CSS_P2P=0 in the environment keeps NCCL) */
+int css_comm_info(css_ctx* ctx, int* rank, int* nranks, int* peerExchange);
 int css_reduce(css_ctx* ctx, int op, int k, double* data); /* gather per-rank partials, fold in rank order */
 
 /* ---- measurement / diagnostics ---- */

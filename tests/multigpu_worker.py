@@ -1,7 +1,7 @@
 """Worker of tests/test_gpu_parity.py::test_two_gpus_bitwise_equal_to_one.  Launched either directly
 (world 1) or under torch.distributed.run (world 2..8): every rank owns a block of particles
-(mpiModel::determineIndexBounds), the mesh is replicated, positions are all-gathered over NCCL after
-every move (css_gather_positions).  Dumps the final state per rank."""
+(mpiModel::determineIndexBounds), the mesh is replicated, positions are exchanged after every move: over peer
+memory (walker stores + flag barrier, the default) or the NCCL all-gather (CSS_P2P=0).  Dumps the final state per rank."""
 from __future__ import annotations
 
 import os
@@ -43,10 +43,18 @@ def main(out_dir):
         ctx.comm_init(rank, world, uid[0])
     ctx.set_state(face, bary, vel[lo:hi], None, n_local=hi - lo, min_idx=lo)
     ctx.compute_forces(kind, params)
-    ctx.step_nve(kind, params, 0.01, 25)
+    ctx.step_nve(kind, params, 0.01, 25)      # 2 plain steps, then CUDA-graph replays
     ke = ctx.reduce(binding.SUM, [0.5 * float((ctx.get_state()[2] ** 2).sum())])
     f, b, v, fr = ctx.get_state()
-    np.savez(os.path.join(out_dir, "world%d_rank%d.npz" % (world, rank)), face=f, bary=b, vel=v, frc=fr, lo=lo, hi=hi, ke=ke)
+    # a few Nose-Hoover steps (two moves + one force evaluation each; the kinetic-energy sum folds per-rank partials, so this
+    # part is compared between the two exchange transports at the same world size, not against world 1)
+    ctx.nvt_init(0.01, 0.2, 1.0, 2)
+    ctx.step_nvt(kind, params, 3)
+    ctx.step_nve(kind, params, 0.01, 5)
+    f2, b2, v2, fr2 = ctx.get_state()
+    tag = os.environ.get("CSS_TAG", "")
+    np.savez(os.path.join(out_dir, "world%d_rank%d%s.npz" % (world, rank, tag)), face=f, bary=b, vel=v, frc=fr, lo=lo, hi=hi, ke=ke,
+             face2=f2, bary2=b2, vel2=v2, frc2=fr2, peer=ctx.comm_info()[2], timeouts=ctx.counters()["peer_timeout"])
     ctx.close()
     if world > 1:
         dist.barrier()

@@ -661,12 +661,24 @@ def test_two_gpus_bitwise_equal_to_one(tmp_path):
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
     script = os.path.join(ROOT, "tests", "multigpu_worker.py")
     out = str(tmp_path)
-    subprocess.check_call([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-                           "--master-port", "29611", script, out])
-    subprocess.check_call([sys.executable, script, out])
+    world = min(torch.cuda.device_count(), 4)
+    # the exchange after every move: peer-memory stores fused into the walker (default) and the NCCL all-gather
+    for tag, p2p in (("_p2p", "1"), ("_nccl", "0")):
+        env = dict(os.environ, CSS_P2P=p2p, CSS_TAG=tag)
+        subprocess.check_call([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % world, "--master-addr",
+                               "127.0.0.1", "--master-port", "29611", script, out], env=env, timeout=600)
+    subprocess.check_call([sys.executable, script, out], timeout=600)
     one = np.load(os.path.join(out, "world1_rank0.npz"))
-    for r in range(2):
-        two = np.load(os.path.join(out, "world2_rank%d.npz" % r))
-        assert np.array_equal(two["face"], one["face"]) and np.array_equal(two["bary"], one["bary"])
-        lo, hi = int(two["lo"]), int(two["hi"])
-        assert np.array_equal(two["vel"], one["vel"][lo:hi]) and np.array_equal(two["frc"], one["frc"][lo:hi])
+    for tag in ("_p2p", "_nccl"):
+        for r in range(world):
+            two = np.load(os.path.join(out, "world%d_rank%d%s.npz" % (world, r, tag)))
+            assert bool(two["peer"]) == (tag == "_p2p"), "peer-memory exchange was not established"
+            assert int(two["timeouts"]) == 0
+            assert np.array_equal(two["face"], one["face"]) and np.array_equal(two["bary"], one["bary"])
+            lo, hi = int(two["lo"]), int(two["hi"])
+            assert np.array_equal(two["vel"], one["vel"][lo:hi]) and np.array_equal(two["frc"], one["frc"][lo:hi])
+    for r in range(world):  # NVT + NVE continuation: the two transports agree bit for bit
+        a = np.load(os.path.join(out, "world%d_rank%d_p2p.npz" % (world, r)))
+        b = np.load(os.path.join(out, "world%d_rank%d_nccl.npz" % (world, r)))
+        for k in ("face2", "bary2", "vel2", "frc2", "ke"):
+            assert np.array_equal(a[k], b[k]), k
