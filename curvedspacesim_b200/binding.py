@@ -29,7 +29,8 @@ NUM_COUNTERS = 32
 API_SYMBOLS = [
     "css_create", "css_destroy", "css_last_error", "css_set_mesh", "css_mesh_info", "css_set_submeshing", "css_set_cell_domain",
     "css_set_options", "css_set_boundary", "css_euclidean", "css_distance", "css_transport", "css_set_state", "css_get_state", "css_set_velocities",
-    "css_set_forces", "css_find_neighbors", "css_get_neighbors", "css_compute_forces", "css_compute_energy", "css_move",
+    "css_set_forces", "css_find_neighbors", "css_get_neighbors", "css_compute_forces", "css_compute_energy", "css_compute_stress",
+    "css_temperature", "css_move",
     "css_get_walk_flags", "css_step_nve", "css_step_gd", "css_nvt_init", "css_step_nvt", "css_nvt_state", "css_fire_init",
     "css_fire_minimize", "css_max_force", "css_force_norm", "css_comm_unique_id", "css_comm_init", "css_comm_info", "css_gather_positions",
     "css_reduce", "css_counters", "css_synchronize", "css_device_positions", "css_last_kernel_ms", "css_set_timing", "css_last_stage_ms",
@@ -231,6 +232,16 @@ class Context:
         e = C.c_double()
         self._ck(self.L.css_compute_energy(self.h, int(kind), _d(params), C.byref(e)))
         return e.value
+
+    def compute_stress(self, kind, params):
+        out = np.zeros(9)
+        self._ck(self.L.css_compute_stress(self.h, int(kind), _d(params), _d(out)))
+        return out.reshape(3, 3)
+
+    def temperature(self):
+        t = C.c_double()
+        self._ck(self.L.css_temperature(self.h, C.byref(t)))
+        return t.value
 
     def move(self, disp=None, transport_force=False, transport_velocity=True):
         d = None if disp is None else np.ascontiguousarray(disp, np.float64)

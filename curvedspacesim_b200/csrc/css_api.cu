@@ -269,8 +269,8 @@ int css_create(css_ctx** out, int device)
     cudaMalloc(&ctx->d_counters, NUM_COUNTERS * sizeof(unsigned long long));
     cudaMemset(ctx->d_counters, 0, NUM_COUNTERS * sizeof(unsigned long long));
     cudaMalloc(&ctx->d_work, 16 * sizeof(int));
-    cudaMalloc(&ctx->d_partial, REDUCE_MAX_BLOCKS * 5 * sizeof(double));
-    cudaMalloc(&ctx->d_red, 8 * sizeof(double));
+    cudaMalloc(&ctx->d_partial, REDUCE_MAX_BLOCKS * 18 * sizeof(double));
+    cudaMalloc(&ctx->d_red, 24 * sizeof(double));
     for (auto& e : ctx->ev) cudaEventCreate(&e);
     for (auto& e : ctx->evS) cudaEventCreate(&e);
     if (const char* tune = getenv("CSS_TUNE")) { // developer tuning: t0 maxF,maxV,ring,kt,warpsPerBlock, t1 ...
@@ -983,6 +983,42 @@ int css_compute_energy(css_ctx* ctx, int kind, const double* params, double* ene
     CU(cudaMemcpyAsync(energy, ctx->d_red, sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
     CU(cudaStreamSynchronize(ctx->st));
     return css_reduce(ctx, CSS_SUM, 1, energy);
+}
+
+static int reduceDevice(css_ctx* ctx, double out[5]);
+// simulation::computeMonodisperseStress (simulation.cpp:104-173) for one force computer: virial + kinetic parts of the
+// Euclidean 3x3 "stress" of the surface, density = N / area
+int css_compute_stress(css_ctx* ctx, int kind, const double* params, double stress[9])
+{
+    if (!ctx || !params || !stress) return CSS_EINVAL;
+    if (!ctx->nTotal) return fail(ctx, CSS_ESTATE, "state not set");
+    BIND();
+    double range;
+    ForceParams fp = mkForce(kind, params, &range);
+    int rc = css_find_neighbors(ctx, range, nullptr);
+    if (rc) return rc;
+    launchStress(ctx->st, ctx->nLocal, ctx->kmax, ctx->d_nbrCount, ctx->d_nbrDist, ctx->d_nbrTs, ctx->d_vel, fp, ctx->d_partial, ctx->d_red);
+    ctx->hostKernels += 2;
+    double h[24] = {0};
+    CU(cudaMemcpyAsync(h, ctx->d_red, sizeof(double) * 18, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    for (int o = 0; o < 18 && !rc; o += 8) rc = css_reduce(ctx, CSS_SUM, std::min(8, 18 - o), h + o);
+    if (rc) return rc;
+    const double N = ctx->nTotal, A = ctx->area, density = N / A;
+    for (int q = 0; q < 9; ++q) stress[q] = density * 1.0 * h[9 + q] / (2 * N) + h[q] / (2 * 2 * A * N);
+    return CSS_OK;
+}
+// noseHooverNVT::getTemperatureFromKE (noseHooverNVT.cpp:141-150): sum v.v / (2 Ndof)
+int css_temperature(css_ctx* ctx, double* temperature)
+{
+    if (!ctx || !temperature) return CSS_EINVAL;
+    if (!ctx->nTotal) return fail(ctx, CSS_ESTATE, "state not set");
+    BIND();
+    double r[5]; // {f.f, v.v, f.v, max f.f, KE}, already folded over the ranks
+    int rc = reduceDevice(ctx, r);
+    if (rc) return rc;
+    *temperature = r[1] / (2.0 * ctx->nTotal);
+    return CSS_OK;
 }
 
 static int moveImpl(css_ctx* ctx, int transportForce, int transportVelocity, int mode, double dt)

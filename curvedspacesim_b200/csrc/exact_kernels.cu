@@ -602,6 +602,64 @@ __global__ void k_energy_final(int nb, const double* __restrict__ partial, doubl
     out[0] = x;
 }
 
+// simulation::computeMonodisperseStress (src/simulation/simulation.cpp:104-173): sums over particles and their neighbours,
+// in list order, of force (x) separation and - counted once per NEIGHBOUR, as the reference's loop nest does - v (x) v.
+__device__ __forceinline__ d3 pairForceExact(const ForceParams& fp, const d3& sep, double d)
+{
+    if (fp.kind == 0) { // harmonicRepulsion.cpp:19-33
+        if (d <= fp.sigma) return (-fp.a * (fp.sigma - d)) * sep;
+        return d3{0, 0, 0};
+    }
+    const double sqrtTwoPi = 2.50662827463100050241576528481104525300698674061; // gaussianRepulsion.h:16-24
+    double twoSigmaSquared = 2.0 * fp.sigma * fp.sigma;
+    double pre = d * fp.a * exp(-d * d / twoSigmaSquared) / ((sqrtTwoPi * fp.sigma) * sqrt(fp.sigma));
+    return (-pre) * sep;
+}
+__global__ void k_stress_partial(int n, int kmax, const int* __restrict__ nbrCount, const double* __restrict__ nbrDist,
+                                 const double* __restrict__ nbrTs, const double* __restrict__ vel, ForceParams fp, double* __restrict__ partial)
+{
+    __shared__ double sm[8][18];
+    double acc[18];
+#pragma unroll
+    for (int q = 0; q < 18; ++q) acc[q] = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int K = nbrCount[i];
+        d3 v = ld3(vel, i);
+        double vv[3] = {v.x, v.y, v.z};
+        for (int j = 0; j < K; ++j) {
+            size_t o = (size_t)i * kmax + j;
+            d3 sep = ld3(nbrTs, o);
+            d3 f = pairForceExact(fp, sep, nbrDist[o]);
+            double ff[3] = {f.x, f.y, f.z}, ss[3] = {sep.x, sep.y, sep.z};
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int b = 0; b < 3; ++b) acc[3 * a + b] += ff[a] * ss[b], acc[9 + 3 * a + b] += vv[a] * vv[b];
+        }
+    }
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < 18; ++q) {
+        double x = acc[q];
+        for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0) sm[w][q] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < 18) {
+        double x = 0;
+        for (int ww = 0; ww < (int)(blockDim.x >> 5); ++ww) x += sm[ww][threadIdx.x];
+        partial[blockIdx.x * 18 + threadIdx.x] = x;
+    }
+}
+__global__ void k_stress_final(int nb, const double* __restrict__ partial, double* __restrict__ out)
+{
+    int q = threadIdx.x;
+    if (q >= 18) return;
+    double x = 0;
+    for (int b = 0; b < nb; ++b) x += partial[b * 18 + q];
+    out[q] = x;
+}
+
 // ---------------------------------------------------------------------------------- host launchers
 static inline int gridFor(int n, int b) { return (n + b - 1) / b; }
 
@@ -742,6 +800,14 @@ void launchEnergy(cudaStream_t st, int nLocal, int kmax, const int* nbrCount, co
     int nb = nLocal > 0 ? min(REDUCE_MAX_BLOCKS, gridFor(nLocal, 256)) : 1;
     k_energy_partial<<<nb, 256, 0, st>>>(nLocal, kmax, nbrCount, nbrDist, fp, partial);
     k_energy_final<<<1, 1, 0, st>>>(nb, partial, out);
+}
+
+void launchStress(cudaStream_t st, int nLocal, int kmax, const int* nbrCount, const double* nbrDist, const double* nbrTs, const double* vel,
+                  ForceParams fp, double* partial, double* out)
+{
+    int nb = nLocal > 0 ? min(REDUCE_MAX_BLOCKS, gridFor(nLocal, 256)) : 1;
+    k_stress_partial<<<nb, 256, 0, st>>>(nLocal, kmax, nbrCount, nbrDist, nbrTs, vel, fp, partial);
+    k_stress_final<<<1, 32, 0, st>>>(nb, partial, out);
 }
 
 } // namespace css

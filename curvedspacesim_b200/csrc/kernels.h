@@ -176,5 +176,7 @@ void launchAxpy(cudaStream_t st, int op, int n, double a, double b, double* vel,
 void launchReduce(cudaStream_t st, int n, const double* vel, const double* frc, double* partial, double* out);
 void launchEnergy(cudaStream_t st, int nLocal, int kmax, const int* nbrCount, const double* nbrDist, ForceParams fp, double* partial,
                   double* out);
+void launchStress(cudaStream_t st, int nLocal, int kmax, const int* nbrCount, const double* nbrDist, const double* nbrTs, const double* vel,
+                  ForceParams fp, double* partial, double* out); // out[18]: sum f (x) dr | sum v (x) v
 
 } // namespace css

@@ -464,14 +464,14 @@ template <class T, bool LEAN> __device__ int processRecord(const WinArgs& a, Win
                     tm &= tm - 1;
                     double b0 = w.tb0[t], b1 = w.tb1[t], b2 = w.tb2[t];
                     double bA = e == 0 ? b1 : (e == 1 ? b2 : b0), bB = e == 0 ? b2 : (e == 1 ? b0 : b1), bC = e == 0 ? b0 : (e == 1 ? b1 : b2);
-                    double rbs = 1.0 / (bA + bB + bC);
+                    double rbs = frcp(bA + bB + bC);
                     v2 Tq{(bA * A.x + bB * B.x + bC * C.x) * rbs, (bA * A.y + bB * B.y + bC * C.y) * rbs};
                     v2 d = Tq - S;
                     double den = cross2(AB, d);
                     if (den != 0) {
-                        double mu = cross2(S - A, d) / den;
+                        double mu = cross2(S - A, d) * frcp(den);
                         if (mu >= t0 - 1e-12 && mu <= t1 + 1e-12) {
-                            double c = sg + sqrt(d.x * d.x + d.y * d.y);
+                            double c = sg + fsqrt(d.x * d.x + d.y * d.y);
                             if (atomicMinD(&w.tbest[t], c)) improvedT = true, myT = t, cand = c, dT = d;
                         }
                     }
@@ -485,7 +485,7 @@ template <class T, bool LEAN> __device__ int processRecord(const WinArgs& a, Win
                         if (psv == NOPSV) w.tsx[myT] = dT.x, w.tsy[myT] = dT.y;
                         else w.tsx[myT] = w.dirx[psv], w.tsy[myT] = w.diry[psv];
                         w.tcode[myT] = 2 + 4 * (g | (e << 8));
-                        double rl = rsqrt(AB.x * AB.x + AB.y * AB.y);
+                        double rl = frcp(fsqrt(AB.x * AB.x + AB.y * AB.y));
                         w.tdu[myT] = (dT.x * AB.x + dT.y * AB.y) * rl;
                         w.tdw[myT] = (-dT.x * AB.y + dT.y * AB.x) * rl;
                     }

@@ -461,6 +461,9 @@ public:
     virtual void findNeighbors(double maximumInteractionRange) = 0;
     virtual void positionsChanged() {}
     void setVerbose(bool v) { verbose = v; }
+    //! simpleModel::fillEuclideanLocations (simpleModel.cpp:28-31)
+    virtual void fillEuclideanLocations() { space->meshPositionToEuclideanLocation(positions, euclideanLocations); }
+    vector<double3> euclideanLocations;
 
     shared_ptr<baseSpace> space;
     int N = 0;
@@ -550,6 +553,18 @@ public:
         double e = 0;
         cssHost::check(ctx(), css_compute_energy(ctx(), kind, params, &e), "css_compute_energy");
         return e;
+        }
+    void computeStressOnDevice(int kind, const double params[3], double stress[9])
+        {
+        pushState();
+        cssHost::check(ctx(), css_compute_stress(ctx(), kind, params, stress), "css_compute_stress");
+        }
+    double temperatureOnDevice()
+        {
+        pushState();
+        double t = 0;
+        cssHost::check(ctx(), css_temperature(ctx(), &t), "css_temperature");
+        return t;
         }
 
     //! upload positions / velocities / forces if the host copies are newer
@@ -1052,6 +1067,46 @@ public:
         }
     void clearForceComputers() { forceComputers.clear(); }
     void clearUpdaters() { updaters.clear(); }
+    //! virial + kinetic "stress" of a monodisperse system (simulation.cpp:104-173), flattened 3x3.  A stock pair potential on
+    //! a gpuModel is evaluated on the device; anything else runs the reference's double loop over the host neighbour lists.
+    void computeMonodisperseStress(vector<double>& stress)
+        {
+        auto conf = configuration.lock();
+        stress.assign(9, 0.0);
+        int kind = 0;
+        double p[3];
+        auto g = std::dynamic_pointer_cast<gpuModel>(conf);
+        if (g && forceComputers.size() == 1 && forceComputers[0].lock()->deviceKind(kind, p))
+            {
+            g->computeStressOnDevice(kind, p, stress.data());
+            return;
+            }
+        auto f0 = forceComputers[0].lock();
+        double area = conf->space->getArea();
+        int Ndof = conf->N;
+        double density = Ndof / area;
+        conf->findNeighbors(f0->maximumInteractionRange);
+        double fOuterDR[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, vOuterv[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        bool first = true;
+        for (auto& wf : forceComputers)
+            {
+            auto frc = wf.lock();
+            for (int ii = 0; ii < Ndof; ++ii)
+                for (size_t jj = 0; jj < conf->neighbors[ii].size(); ++jj)
+                    {
+                    vector3 sep = conf->neighborVectors[ii][jj];
+                    vector3 force = frc->pairwiseForce(sep, conf->neighborDistances[ii][jj]);
+                    for (int a = 0; a < 3; ++a)
+                        for (int b = 0; b < 3; ++b)
+                            {
+                            fOuterDR[3 * a + b] += force[a] * sep[b];
+                            if (first) vOuterv[3 * a + b] += conf->velocities[ii][a] * conf->velocities[ii][b];
+                            }
+                    }
+            first = false;
+            }
+        for (int q = 0; q < 9; ++q) stress[q] = density * vOuterv[q] / (2 * Ndof) + fOuterDR[q] / (2 * 2 * area * Ndof);
+        }
     void setIntegrationTimestep(double dt)
         {
         integrationTimestep = dt;

@@ -5,9 +5,11 @@
 //     programBranch: 0 FIRE, 1 gradient descent, 2 velocity-Verlet NVE, 3 Nose-Hoover NVT
 //     fused: 0 = host-driven updaters (reference control flow, one ABI call per moveParticles/computeForces)
 //            1 = gpuSimulation (device-resident fused step)
+//   CSS_EXAMPLE_DB=<dir> in the environment: the initial and final states are also written as two records of a
+//   simpleModelDatabase (host/css_database.hpp), as the reference's mains do with their HDF5 trajectory file.
 // The dump holds N, then the initial (face, bary, velocity) and the final (face, bary, velocity, force) arrays in raw
 // little-endian form; tests/test_gpu_parity.py replays the same initial state through the ctypes binding and the oracle.
-#include "css_host.hpp"
+#include "css_database.hpp"
 
 #include <chrono>
 #include <cstdlib>
@@ -76,6 +78,11 @@ int main(int argc, char** argv)
         fwrite(&N, sizeof(int), 1, f);
         dumpState(f, *configuration, false);
 
+        if (const char* dbDir = getenv("CSS_EXAMPLE_DB"))
+            {
+            simpleModelDatabase db(N, dbDir, fileMode::replace);
+            db.writeState(configuration, 0.0);
+            }
         auto t0 = std::chrono::steady_clock::now();
         for (int ii = 0; ii < maximumIterations; ++ii) simulator->performTimestep();
         if (fused) std::static_pointer_cast<gpuSimulation>(simulator)->syncHost();
@@ -83,6 +90,14 @@ int main(int argc, char** argv)
 
         dumpState(f, *configuration, true);
         fclose(f);
+        vector<double> stress;
+        simulator->computeMonodisperseStress(stress); // curvedSpaceNVTSim.cpp:113-118 prints the same observable
+        printf("stress trace %.17g temperature %.17g\n", stress[0] + stress[4] + stress[8], configuration->temperatureOnDevice());
+        if (const char* dbDir = getenv("CSS_EXAMPLE_DB"))
+            {
+            simpleModelDatabase db(N, dbDir, fileMode::readwrite);
+            db.writeState(configuration, simulator->Time);
+            }
         printf("%d particles, %d timesteps in %.4f s (%s): %.3e particle-timesteps/s; fN %g fM %g\n", N, maximumIterations, secs,
                fused ? "fused device step" : "host-driven updaters", N * (double)maximumIterations / secs, eom->getForceNorm(), eom->getMaxForce());
         }

@@ -20,6 +20,8 @@
  *   css_compute_forces      force::computeForces with harmonicRepulsion / gaussianRepulsion
  *                           (src/forces/baseForce.cpp:12-28, harmonicRepulsion.cpp:19-33, gaussianRepulsion.cpp:8-12)
  *   css_compute_energy      force::computeEnergy (baseForce.cpp:33-44)
+ *   css_compute_stress      simulation::computeMonodisperseStress (src/simulation/simulation.cpp:104-173)
+ *   css_temperature         noseHooverNVT::getTemperatureFromKE (src/updaters/noseHooverNVT.cpp:141-150)
  *   css_move                simpleModel::moveParticles (simpleModel.cpp:44-66)
  *   css_gather_positions    mpiSimulation::synchronizeAndTransferBuffers (src/simulation/mpiSimulation.cpp:11-42)
  *   css_reduce              mpiSimulation::manipulateUpdaterData (mpiSimulation.cpp:69-89)
@@ -120,6 +122,10 @@ int css_find_neighbors(css_ctx* ctx, double range, int64_t* totalNeighbors);
 int css_get_neighbors(css_ctx* ctx, int32_t* offsets, int32_t* idx, double* dist, double* startTan, double* endTan);
 int css_compute_forces(css_ctx* ctx, int kind, const double* params, int zero);
 int css_compute_energy(css_ctx* ctx, int kind, const double* params, double* energy);
+/* stress[3 a + b]: density kB <v_a v_b> / 2 + <f_a dr_b> / (2 d A), d = 2, density = N / A; v (x) v is accumulated once per
+ * neighbour, as the reference's loop nest does.  Runs find_neighbors at the force's range first (like the reference). */
+int css_compute_stress(css_ctx* ctx, int kind, const double* params, double stress[9]);
+int css_temperature(css_ctx* ctx, double* temperature); /* sum v.v / (2 N) over all ranks */
 int css_move(css_ctx* ctx, const double* disp /*nLocal, host; NULL = use the device displacement buffer*/, int transportForce,
              int transportVelocity);
 int css_get_walk_flags(css_ctx* ctx, int32_t* flags /*nLocal*/);

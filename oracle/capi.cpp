@@ -227,6 +227,12 @@ ORC_API double orc_compute_energy(void* h, int kind, const double* params)
     Sim* s = (Sim*)h;
     return s->computeEnergy(mkForce(kind, params));
 }
+ORC_API void orc_compute_stress(void* h, int kind, const double* params, double* stress9)
+{
+    Sim* s = (Sim*)h;
+    s->computeStress(mkForce(kind, params), s->mesh.area(), stress9);
+}
+ORC_API double orc_temperature(void* h) { return ((Sim*)h)->temperature(); }
 ORC_API void orc_move(void* h, double* disp, int transportForce, int transportVelocity)
 {
     Sim* s = (Sim*)h;

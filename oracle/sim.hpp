@@ -224,6 +224,29 @@ struct Sim {
         return e;
     }
 
+    // simulation::computeMonodisperseStress (simulation.cpp:104-173), one force computer.  NB v (x) v sits inside the
+    // neighbour loop there, so it is accumulated once per neighbour; kept as is.
+    void computeStress(const PairForce& pf, double area, double out[9])
+    {
+        findNeighbors(pf.range);
+        double fdr[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, vv[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        for (int i = 0; i < N; ++i)
+            for (size_t jj = 0; jj < nbr[i].size(); ++jj) {
+                const V3& sep = nbrStart[i][jj];
+                V3 f = pf.force(sep, nbrDist[i][jj]);
+                for (int a = 0; a < 3; ++a)
+                    for (int b = 0; b < 3; ++b) fdr[3 * a + b] += f[a] * sep[b], vv[3 * a + b] += vel[i][a] * vel[i][b];
+            }
+        double density = N / area;
+        for (int q = 0; q < 9; ++q) out[q] = density * 1.0 * vv[q] / (2 * N) + fdr[q] / (2 * 2 * area * N);
+    }
+    double temperature() const // noseHooverNVT::getTemperatureFromKE (noseHooverNVT.cpp:141-150)
+    {
+        double v2 = 0;
+        for (int i = 0; i < N; ++i) v2 = v2 + dot(vel[i], vel[i]);
+        return v2 / (2 * N);
+    }
+
     // simpleModel::moveParticles (simpleModel.cpp:44-66): transports = [force?][velocity?]
     void moveParticles(std::vector<V3>& disp)
     {

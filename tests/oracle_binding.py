@@ -32,7 +32,7 @@ def lib():
         L.orc_last_error.restype = C.c_char_p
         L.orc_candidates.restype = C.c_long
         L.orc_find_neighbors.restype = C.c_long
-        for n in ("orc_run_nve", "orc_run_gd", "orc_run_nvt", "orc_run_fire", "orc_compute_energy"):
+        for n in ("orc_run_nve", "orc_run_gd", "orc_run_nvt", "orc_run_fire", "orc_compute_energy", "orc_temperature"):
             getattr(L, n).restype = C.c_double
         _LIB = L
     return _LIB
@@ -191,6 +191,14 @@ class Oracle:
 
     def compute_energy(self, kind, params):
         return self.L.orc_compute_energy(self.h, kind, _d(params))
+
+    def compute_stress(self, kind, params):
+        out = np.zeros(9)
+        self.L.orc_compute_stress(self.h, kind, _d(params), _d(out))
+        return out.reshape(3, 3)
+
+    def temperature(self):
+        return self.L.orc_temperature(self.h)
 
     def move(self, disp, transport_force=False, transport_velocity=True):
         disp = np.array(disp, np.float64)

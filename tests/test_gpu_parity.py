@@ -330,6 +330,17 @@ def test_open_mesh_boundary_rules(mode, sheet, gpu_ctx_factory):
         compared += int(ok.sum())
     assert compared > 39 * N and orc.counters()["border"] > 100 and ctx.counters()["walk_border"] == orc.counters()["border"]
 
+# ------------------------------------------------------------------------------ observables
+@pytest.mark.parametrize("pot", ["harmonic", "gaussian"])
+def test_stress_tensor_and_temperature(pot, gpu_ctx_factory):
+    """simulation::computeMonodisperseStress (simulation.cpp:104-173), noseHooverNVT::getTemperatureFromKE."""
+    V, F = _case_mesh("icosphere40")
+    orc, ctx, corners, face, bary, vel, rc, kind, params = _pair(V, F, 3000, pot, gpu_ctx_factory, area_fraction=1.5)
+    So, Sg = orc.compute_stress(kind, params), ctx.compute_stress(kind, params)
+    assert np.abs(So).max() > 0 and np.max(np.abs(So - Sg)) < TOL_FORCE * np.abs(So).max()
+    assert abs(orc.temperature() - ctx.temperature()) < 1e-12 * orc.temperature()
+
+
 # ------------------------------------------------------------------------------ golden fixtures
 def test_golden_bruteforce_geodesics(gpu_ctx_factory):
     g = np.load(os.path.join(GOLDEN, "bruteforce_geodesics.npz"))
@@ -626,7 +637,9 @@ def test_cpp_host_layer_matches_the_oracle(branch, fused, tmp_path):
     meshes.save_off(off, V, F)
     N, iters, dt, T = 150, (30 if branch else 25), 0.01, 0.2
     dump = str(tmp_path / "d.bin")
-    out = subprocess.run([exe, off, str(N), str(iters), str(branch), str(fused), dump, str(dt), str(T)], capture_output=True, text=True)
+    dbdir = str(tmp_path / "traj.cssdb")
+    out = subprocess.run([exe, off, str(N), str(iters), str(branch), str(fused), dump, str(dt), str(T)], capture_output=True, text=True,
+                         env=dict(os.environ, CSS_EXAMPLE_DB=dbdir))
     assert out.returncode == 0, out.stderr
     n, (f0, b0, v0), (f1, b1, v1, fr1) = _read_dump(dump)
     corners = meshes.reference_corners(F)
@@ -651,6 +664,20 @@ def test_cpp_host_layer_matches_the_oracle(branch, fused, tmp_path):
     assert np.array_equal(of, f1)
     assert np.max(np.abs(ob - b1)) < 1e-9 and np.max(np.abs(ov - v1)) < 1e-9
     assert np.max(np.abs(ofr - fr1)) < TOL_FORCE * max(np.abs(ofr).max(), 1e-300) + 1e-12
+    # the trajectory database written by the program (host/css_database.hpp) holds the same two states
+    from curvedspacesim_b200 import trajectory
+
+    db = trajectory.SimpleModelDatabase(N, dbdir, "r")
+    assert db.current_number_of_records() == 2
+    first, last = db.read_state(0), db.read_state(1)
+    assert np.array_equal(first["faceIndex"], f0) and np.array_equal(first["barycentricPosition"], b0) and np.array_equal(first["velocity"], v0)
+    assert np.array_equal(last["faceIndex"], f1) and np.array_equal(last["barycentricPosition"], b1) and np.array_equal(last["force"], fr1)
+    assert np.array_equal(last["R3position"], orc.euclidean(f1, b1))
+    # observables printed by the program: simulation::computeMonodisperseStress, noseHooverNVT::getTemperatureFromKE
+    line = [ln for ln in out.stdout.splitlines() if ln.startswith("stress trace")][0].split()
+    orc.set_state(f1, b1, v1, fr1)
+    So = orc.compute_stress(kind, params)
+    assert abs(float(line[2]) - np.trace(So)) < 1e-8 * abs(np.trace(So)) and abs(float(line[4]) - orc.temperature()) < 1e-12
 
 
 # ------------------------------------------------------------------------------ multi-GPU

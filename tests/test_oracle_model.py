@@ -411,3 +411,35 @@ def test_tangential_boundary_slides_along_the_edge():
     c = orc.counters()
     assert c["nan"] == 0 and c["border"] > 100
     assert np.all(b3 >= 0) and np.all((P[:, :2] >= -1e-9) & (P[:, :2] <= 1 + 1e-9))
+
+
+# --------------------------------------------------------------------------------- observables
+def test_stress_and_temperature_match_a_literal_numpy_evaluation():
+    """simulation::computeMonodisperseStress (simulation.cpp:104-173) and noseHooverNVT::getTemperatureFromKE
+    (noseHooverNVT.cpp:141-150) restated with numpy loops over the oracle's own neighbour lists."""
+    V, F = meshes.icosphere(8)
+    N = 150
+    corners, face, bary, vel = make_state(V, F, N)
+    orc = Oracle(V, corners)
+    _, _, area = orc.mesh_info()
+    rc = interaction_range(area, N, 2.0)
+    orc.set_submeshing(True, rc)
+    orc.set_state(face, bary, vel)
+    for name, kw in (("harmonic", dict(k=1.0, sigma=rc)), ("gaussian", dict(alpha=1.0, sigma=0.5 * rc, range=rc))):
+        kind, params = force_params(name, **kw)
+        S = orc.compute_stress(kind, params)
+        off, idx, d, ts, _ = orc.find_neighbors(rc)
+        fdr, vv = np.zeros((3, 3)), np.zeros((3, 3))
+        for i in range(N):
+            for q in range(off[i], off[i + 1]):
+                if name == "harmonic":
+                    f = -1.0 * (rc - d[q]) * ts[q] if d[q] <= rc else np.zeros(3)
+                else:
+                    sg = 0.5 * rc
+                    f = -(d[q] * np.exp(-d[q] ** 2 / (2 * sg * sg)) / (np.sqrt(2 * np.pi) * sg * np.sqrt(sg))) * ts[q]
+                fdr += np.outer(f, ts[q])
+                vv += np.outer(vel[i], vel[i])
+        ref = (N / area) * vv / (2 * N) + fdr / (4 * area * N)
+        assert len(idx) > N and np.max(np.abs(S - ref)) < 1e-12 * np.abs(ref).max()
+        assert abs(np.trace(S)) > 0
+    assert abs(orc.temperature() - (vel ** 2).sum() / (2 * N)) < 1e-14
