@@ -557,11 +557,13 @@ public:
     void computeStressOnDevice(int kind, const double params[3], double stress[9])
         {
         pushState();
+        pushVectors(velocities, css_set_velocities, "css_set_velocities"); // host-driven updaters kick the host copy
         cssHost::check(ctx(), css_compute_stress(ctx(), kind, params, stress), "css_compute_stress");
         }
     double temperatureOnDevice()
         {
         pushState();
+        pushVectors(velocities, css_set_velocities, "css_set_velocities");
         double t = 0;
         cssHost::check(ctx(), css_temperature(ctx(), &t), "css_temperature");
         return t;
