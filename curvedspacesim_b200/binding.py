@@ -31,7 +31,7 @@ API_SYMBOLS = [
     "css_set_options", "css_set_boundary", "css_euclidean", "css_distance", "css_transport", "css_set_state", "css_get_state", "css_set_velocities",
     "css_set_forces", "css_find_neighbors", "css_get_neighbors", "css_compute_forces", "css_compute_energy", "css_compute_stress",
     "css_temperature", "css_move",
-    "css_get_walk_flags", "css_step_nve", "css_step_gd", "css_nvt_init", "css_step_nvt", "css_nvt_state", "css_fire_init",
+    "css_get_walk_flags", "css_step_nve", "css_step_nve_host", "css_step_gd", "css_nvt_init", "css_step_nvt", "css_nvt_state", "css_fire_init",
     "css_fire_minimize", "css_max_force", "css_force_norm", "css_comm_unique_id", "css_comm_init", "css_comm_info", "css_gather_positions",
     "css_reduce", "css_counters", "css_synchronize", "css_device_positions", "css_last_kernel_ms", "css_set_timing", "css_last_stage_ms",
     "css_timer_record", "css_timer_elapsed_ms",
@@ -253,6 +253,14 @@ class Context:
         return f
 
     # ---- updaters ----
+    def step_nve_host(self, kind, params, dt, face, bary, vel, frc):
+        """One NVE step of a host-resident state, in place (upload, step, download with the position download overlapped)."""
+        for a, n, dt_ in ((face, self.n_total, np.int32), (bary, 3 * self.n_total, np.float64), (vel, 3 * self.n_local, np.float64),
+                          (frc, 3 * self.n_local, np.float64)):
+            if a.dtype != dt_ or a.size != n or not a.flags["C_CONTIGUOUS"]:
+                raise ValueError("step_nve_host: wrong dtype / size / layout")
+        self._ck(self.L.css_step_nve_host(self.h, int(kind), _d(params), C.c_double(dt), _i(face), _d(bary), _d(vel), _d(frc)))
+
     def step_nve(self, kind, params, dt, nsteps=1):
         self._ck(self.L.css_step_nve(self.h, int(kind), _d(params), C.c_double(dt), int(nsteps)))
 

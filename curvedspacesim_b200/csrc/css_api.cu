@@ -109,6 +109,12 @@ struct css_ctx {
     uint64_t nveKey = 0;
     unsigned long long nveKernels = 0;
     int nveCalls = 0;
+    // host-buffer step (css_step_nve_host): positions are downloaded on a second stream while the neighbour / force phase runs
+    cudaStream_t stCopy = nullptr;
+    cudaEvent_t evFork = nullptr, evJoin = nullptr;
+    int32_t* ioFace = nullptr;
+    double* ioBary = nullptr;
+    bool ioNoGraph = false;
     // timing
     bool timing = false;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -316,6 +322,9 @@ int css_destroy(css_ctx* ctx)
         if (e) cudaEventDestroy(e);
     for (auto& e : ctx->evS)
         if (e) cudaEventDestroy(e);
+    if (ctx->evFork) cudaEventDestroy(ctx->evFork);
+    if (ctx->evJoin) cudaEventDestroy(ctx->evJoin);
+    if (ctx->stCopy) cudaStreamDestroy(ctx->stCopy);
     cudaStreamDestroy(ctx->st);
     delete ctx;
     return CSS_OK;
@@ -1072,7 +1081,16 @@ static int nveStepLaunches(css_ctx* ctx, const ForceParams& fp, double range, do
     // first half step fused into the walker; second half kick fused into the geodesic/force kernel
     int rc = moveImpl(ctx, 0, 1, 1, dt);
     if (rc) return rc;
-    return findNeighborsImpl(ctx, range, 1, fp, 1, 0.5 * dt);
+    if (ctx->ioFace) { // host-buffer step: the positions are final here, their download overlaps the neighbour / force phase
+        CU(cudaEventRecord(ctx->evFork, ctx->st));
+        CU(cudaStreamWaitEvent(ctx->stCopy, ctx->evFork, 0));
+        CU(cudaMemcpyAsync(ctx->ioFace, ctx->d_face, sizeof(int) * ctx->nTotal, cudaMemcpyDeviceToHost, ctx->stCopy));
+        CU(cudaMemcpyAsync(ctx->ioBary, ctx->d_bary, sizeof(double) * 3 * ctx->nTotal, cudaMemcpyDeviceToHost, ctx->stCopy));
+        CU(cudaEventRecord(ctx->evJoin, ctx->stCopy));
+    }
+    rc = findNeighborsImpl(ctx, range, 1, fp, 1, 0.5 * dt);
+    if (ctx->ioFace) CU(cudaStreamWaitEvent(ctx->st, ctx->evJoin, 0));
+    return rc;
 }
 
 // everything that decides what the captured launches look like: a change of any of these re-captures the graph
@@ -1094,22 +1112,18 @@ static uint64_t nveGraphKey(css_ctx* ctx, const ForceParams& fp, double range, d
                     ctx->winPeer[0], ctx->winPeer[1], ctx->winPeer[2], ctx->winPeer[3], ctx->winPeer[4], ctx->winPeer[5], ctx->winPeer[6],
                     ctx->winPeer[7]};
     MIX(ptrs);
+    MIX(ctx->ioFace), MIX(ctx->ioBary);
 #undef MIX
     return h ? h : 1;
 }
 
-int css_step_nve(css_ctx* ctx, int kind, const double* params, double dt, int nsteps)
+static int nveSteps(css_ctx* ctx, const ForceParams& fp, double range, double dt, int nsteps)
 {
-    if (!ctx || !params) return CSS_EINVAL;
-    if (!ctx->nTotal) return fail(ctx, CSS_ESTATE, "state not set");
-    BIND();
-    double range;
-    ForceParams fp = mkForce(kind, params, &range);
     int rc = CSS_OK;
     for (int s = 0; s < nsteps && !rc; ++s) {
         // The first two steps of a configuration run as plain launches (they size every buffer); after that the
         // step is replayed from a CUDA graph as long as nothing it captured has changed.
-        uint64_t key = ctx->useGraph && ctx->nveCalls >= 2 ? nveGraphKey(ctx, fp, range, dt) : 0;
+        uint64_t key = ctx->useGraph && !(ctx->ioFace && ctx->ioNoGraph) && ctx->nveCalls >= 2 ? nveGraphKey(ctx, fp, range, dt) : 0;
         if (key && key == ctx->nveKey && ctx->nveExec) {
             CU(cudaGraphLaunch(ctx->nveExec, ctx->st));
             ctx->hostKernels += ctx->nveKernels;
@@ -1152,11 +1166,23 @@ int css_step_nve(css_ctx* ctx, int kind, const double* params, double dt, int ns
                 ctx->nbrValid = true;
                 continue;
             }
-            ctx->useGraph = false; // capture is not possible in this configuration: plain launches from now on
+            if (ctx->ioFace) ctx->ioNoGraph = true; // e.g. pageable host buffers cannot be captured: the host-buffer step runs plain launches
+            else ctx->useGraph = false;             // capture is not possible in this configuration: plain launches from now on
         }
         rc = nveStepLaunches(ctx, fp, range, dt);
         ctx->nveCalls++;
     }
+    return rc;
+}
+
+int css_step_nve(css_ctx* ctx, int kind, const double* params, double dt, int nsteps)
+{
+    if (!ctx || !params) return CSS_EINVAL;
+    if (!ctx->nTotal) return fail(ctx, CSS_ESTATE, "state not set");
+    BIND();
+    double range;
+    ForceParams fp = mkForce(kind, params, &range);
+    int rc = nveSteps(ctx, fp, range, dt, nsteps);
     if (rc) return rc;
     rc = checkCapacity(ctx, nullptr);
     if (ctx->timing && nsteps > 0) {
@@ -1165,6 +1191,39 @@ int css_step_nve(css_ctx* ctx, int kind, const double* params, double dt, int ns
         cudaEventElapsedTime(&ctx->msWalk, ctx->ev[3], ctx->ev[4]);
     }
     return rc;
+}
+
+// One velocity-Verlet step of a HOST-resident state (the reference keeps positions / velocities / forces in std::vectors and
+// every performTimestep reads and writes them): upload, step, download in one call.  The positions are downloaded on a
+// second stream as soon as the walker and the exchange are done, overlapping the neighbour / force phase.  Buffers should
+// be page-locked for the copies to be asynchronous.  face/bary hold all nTotal particles, vel/frc this rank's block.
+int css_step_nve_host(css_ctx* ctx, int kind, const double* params, double dt, int32_t* face, double* bary, double* vel, double* frc)
+{
+    if (!ctx || !params || !face || !bary || !vel || !frc) return CSS_EINVAL;
+    if (!ctx->nTotal) return fail(ctx, CSS_ESTATE, "state not set (css_set_state fixes the sharding)");
+    BIND();
+    const int nT = ctx->nTotal, nL = ctx->nLocal;
+    int bad = 0;
+    for (int i = 0; i < nT; ++i) bad |= (face[i] < 0) | (face[i] >= ctx->nF);
+    if (bad) return fail(ctx, CSS_EINVAL, "css_step_nve_host: face index out of range");
+    if (!ctx->stCopy) {
+        CU(cudaStreamCreateWithFlags(&ctx->stCopy, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx->evJoin, cudaEventDisableTiming));
+    }
+    double range;
+    ForceParams fp = mkForce(kind, params, &range);
+    CU(cudaMemcpyAsync(ctx->d_face, face, sizeof(int) * nT, cudaMemcpyHostToDevice, ctx->st));
+    CU(cudaMemcpyAsync(ctx->d_bary, bary, sizeof(double) * 3 * nT, cudaMemcpyHostToDevice, ctx->st));
+    CU(cudaMemcpyAsync(ctx->d_vel, vel, sizeof(double) * 3 * nL, cudaMemcpyHostToDevice, ctx->st));
+    CU(cudaMemcpyAsync(ctx->d_frc, frc, sizeof(double) * 3 * nL, cudaMemcpyHostToDevice, ctx->st));
+    ctx->ioFace = face, ctx->ioBary = bary;
+    int rc = nveSteps(ctx, fp, range, dt, 1);
+    ctx->ioFace = nullptr, ctx->ioBary = nullptr;
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(vel, ctx->d_vel, sizeof(double) * 3 * nL, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaMemcpyAsync(frc, ctx->d_frc, sizeof(double) * 3 * nL, cudaMemcpyDeviceToHost, ctx->st));
+    return checkCapacity(ctx, nullptr); // synchronises the stream (which has joined the copy stream)
 }
 
 int css_step_gd(css_ctx* ctx, int kind, const double* params, double dt, int nsteps)

@@ -83,7 +83,13 @@ template <int F_, int V_, int K_, int RING_> struct GeoTier {
     static_assert(BYTES % 16 == 0 && OFF_FVERT % 16 == 0 && OFF_GFACE % 4 == 0, "record sections must stay aligned");
     static_assert(F_ < 255 && V_ < 256 && K_ <= 32 && (RING_ & (RING_ - 1)) == 0, "8-bit local ids, one target per lane");
 };
-using TierSmall = GeoTier<96, 64, 16, 64>;
+#ifndef CSS_T0_K
+#define CSS_T0_K 16
+#endif
+#ifndef CSS_T0_RING
+#define CSS_T0_RING 64
+#endif
+using TierSmall = GeoTier<96, 64, CSS_T0_K, CSS_T0_RING>;
 using TierLarge = GeoTier<240, 160, 32, 256>;
 #define REC_NONE 255
 #define PATCH_THREADS 256

@@ -25,6 +25,7 @@
  *   css_move                simpleModel::moveParticles (simpleModel.cpp:44-66)
  *   css_gather_positions    mpiSimulation::synchronizeAndTransferBuffers (src/simulation/mpiSimulation.cpp:11-42)
  *   css_reduce              mpiSimulation::manipulateUpdaterData (mpiSimulation.cpp:69-89)
+ *   css_step_nve_host       the same step with the model's host vectors as input and output (simpleModel.h:60-75 public arrays)
  *   css_step_nve            velocityVerletNVE::performUpdate (src/updaters/velocityVerletNVE.cpp:3-29)
  *   css_step_gd             gradientDescent::performUpdate (src/updaters/gradientDescent.cpp:6-18)
  *   css_nvt_init/step_nvt   noseHooverNVT ctor/setBathVariables/performUpdate (src/updaters/noseHooverNVT.cpp:3-139)
@@ -132,6 +133,10 @@ int css_get_walk_flags(css_ctx* ctx, int32_t* flags /*nLocal*/);
 
 /* ---- fused updaters ---- */
 int css_step_nve(css_ctx* ctx, int kind, const double* params, double dt, int nsteps);
+/* The same step for a HOST-resident state (simpleModel's public std::vectors): uploads face/bary [nTotal] and vel/frc
+ * [nLocal] (page-locked buffers recommended), steps once, downloads the new state into the same buffers; the positions
+ * come back on a second stream while the neighbour / force phase is still running.  Sharding as set by css_set_state. */
+int css_step_nve_host(css_ctx* ctx, int kind, const double* params, double dt, int32_t* face, double* bary, double* vel, double* frc);
 int css_step_gd(css_ctx* ctx, int kind, const double* params, double dt, int nsteps);
 int css_nvt_init(css_ctx* ctx, double dt, double T, double tau, int M);
 int css_step_nvt(css_ctx* ctx, int kind, const double* params, int nsteps);

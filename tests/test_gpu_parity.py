@@ -341,6 +341,40 @@ def test_stress_tensor_and_temperature(pot, gpu_ctx_factory):
     assert abs(orc.temperature() - ctx.temperature()) < 1e-12 * orc.temperature()
 
 
+@pytest.mark.parametrize("pinned", [False, True])
+def test_host_buffer_step_equals_the_device_resident_step(pinned, gpu_ctx_factory):
+    """css_step_nve_host (upload, step, download with the position download overlapped on a second stream) against
+    css_set_state + css_step_nve + css_get_state: bitwise, through the plain launches and the CUDA-graph replays."""
+    V, F = _case_mesh("icosphere40")
+    orc, ctx, corners, face, bary, vel, rc, kind, params = _pair(V, F, 3000, "harmonic", gpu_ctx_factory, want_end=False)
+    ctx.compute_forces(kind, params)
+    f0, b0, v0, fr0 = ctx.get_state()
+    ref = gpu_ctx_factory()
+    ref.set_mesh(V, corners)
+    ref.set_submeshing(True, rc)
+    ref.set_options(True, False)
+    ref.set_state(f0, b0, v0, fr0)
+    bufs = [f0.copy(), b0.copy(), v0.copy(), fr0.copy()]
+    if pinned:
+        import torch
+
+        bufs = [torch.from_numpy(a).pin_memory().numpy() for a in bufs]
+    for step in range(6):
+        ctx.step_nve_host(kind, params, 0.01, *bufs)
+        ref.step_nve(kind, params, 0.01, 1)
+        rf, rb, rv, rfr = ref.get_state()
+        assert np.array_equal(bufs[0], rf) and np.array_equal(bufs[1], rb), step
+        assert np.array_equal(bufs[2], rv) and np.array_equal(bufs[3], rfr), step
+        if step == 2:  # the host owns the state: a change made on the host is what the next step sees
+            bufs[2] *= 0.5
+            ref.set_velocities(bufs[2])
+    assert not np.array_equal(bufs[1], b0)
+    bad = bufs[0].copy()
+    bad[5] = len(F)
+    with pytest.raises(binding.CssError):
+        ctx.step_nve_host(kind, params, 0.01, bad, bufs[1], bufs[2], bufs[3])
+
+
 # ------------------------------------------------------------------------------ golden fixtures
 def test_golden_bruteforce_geodesics(gpu_ctx_factory):
     g = np.load(os.path.join(GOLDEN, "bruteforce_geodesics.npz"))
