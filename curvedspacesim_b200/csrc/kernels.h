@@ -60,8 +60,8 @@ cudaError_t launchGeodesic(cudaStream_t st, const GeoArgs& a, int warpsPerBlock,
 // ---- two-stage tier-0 path: patch records (patch_kernel.cu) -> window propagation (window_kernel.cu) ----
 // Fixed-capacity patch record, one per local source particle, REC_BYTES apart (all offsets 16-byte aligned):
 //   int   hdr[4]            nF, nV, K, status (1 = overflow: handled by the retry tiers, stage 2 skips it)
-//   int   tIdx[REC_MAXK]    ordered candidate particle indices (the neighbour list)
-//   u8    tFace[REC_MAXK]   local face of each target
+//   int   tIdx[RECK]        ordered candidate particle indices (the neighbour list)
+//   u8    tFace[RECK]       local face of each target
 //   u8    velig[REC_MAXV]   vertex may act as a pseudo-source (saddle of the mesh or on the patch border)
 //   int   gface[REC_MAXF]   local face -> global face
 //   int   gvert[REC_MAXV]   local vertex -> global vertex
@@ -69,11 +69,14 @@ cudaError_t launchGeodesic(cudaStream_t st, const GeoArgs& a, int warpsPerBlock,
 //   uchar4 fadj[REC_MAXF]   local face across the edge opposite corner k (REC_NONE = patch border)
 // Two capacity classes are instantiated: SMALL (tier 0, covers the design-point configs) and LARGE (tier 1: big patches
 // or many candidates; also the fast path of coarse meshes such as config 1).
-template <int F_, int V_, int K_, int RING_> struct GeoTier {
-    static constexpr int MAXF = F_, MAXV = V_, MAXK = K_, RING = RING_;      // faces < 255, K <= 32 (one target per lane)
+// K_ targets are propagated at a time (the per-target workspace of stage 2); a record holds up to RECK_ >= K_ candidates and
+// stage 2 runs one propagation per group of K_ (sources with more than K_ candidates are ~5e-6 of config 5, and a second
+// propagation inside the main launch is far cheaper than a lone warp in a retry launch).
+template <int F_, int V_, int K_, int RING_, int RECK_ = K_> struct GeoTier {
+    static constexpr int MAXF = F_, MAXV = V_, MAXK = K_, RING = RING_, RECK = RECK_; // faces < 255, RECK <= 32 (one target per lane in stage 1)
     static constexpr int OFF_TIDX = 16;
-    static constexpr int OFF_TFACE = OFF_TIDX + 4 * K_;
-    static constexpr int OFF_VELIG = OFF_TFACE + K_;
+    static constexpr int OFF_TFACE = OFF_TIDX + 4 * RECK_;
+    static constexpr int OFF_VELIG = OFF_TFACE + RECK_;
     static constexpr int OFF_GFACE = OFF_VELIG + V_;
     static constexpr int OFF_GVERT = OFF_GFACE + 4 * F_;
     static constexpr int OFF_FVERT = OFF_GVERT + 4 * V_;
@@ -81,7 +84,7 @@ template <int F_, int V_, int K_, int RING_> struct GeoTier {
     static constexpr int BYTES = OFF_FADJ + 4 * F_;
     static constexpr int HASHF = F_ <= 96 ? 256 : 512, HASHV = V_ <= 64 ? 256 : 512; // >= 2 x capacity + in-flight inserts
     static_assert(BYTES % 16 == 0 && OFF_FVERT % 16 == 0 && OFF_GFACE % 4 == 0, "record sections must stay aligned");
-    static_assert(F_ < 255 && V_ < 256 && K_ <= 32 && (RING_ & (RING_ - 1)) == 0, "8-bit local ids, one target per lane");
+    static_assert(F_ < 255 && V_ < 256 && K_ <= RECK_ && RECK_ <= 32 && (RING_ & (RING_ - 1)) == 0, "8-bit local ids, one target per lane");
 };
 #ifndef CSS_T0_K
 #define CSS_T0_K 16
@@ -89,7 +92,10 @@ template <int F_, int V_, int K_, int RING_> struct GeoTier {
 #ifndef CSS_T0_RING
 #define CSS_T0_RING 64
 #endif
-using TierSmall = GeoTier<96, 64, CSS_T0_K, CSS_T0_RING>;
+#ifndef CSS_T0_RECK
+#define CSS_T0_RECK 32
+#endif
+using TierSmall = GeoTier<96, 64, CSS_T0_K, CSS_T0_RING, CSS_T0_RECK>;
 using TierLarge = GeoTier<240, 160, 32, 256>;
 #define REC_NONE 255
 #define PATCH_THREADS 256

@@ -141,7 +141,7 @@ template <class T> __device__ int buildPatch(const PatchArgs& a, PatchSmem<T>& s
             if (lane == 0) atomicAdd(a.counters + C_KMAX_OVERFLOW, 1ull);
             return 1;
         }
-        if (K > T::MAXK) return 2; // 1 + reason (0 candidates, 1 faces, 2 vertices)
+        if (K > T::RECK) return 2; // 1 + reason (0 candidates, 1 faces, 2 vertices)
         maxd2 = warpMaxD(maxd2);
         R = xsqrt(maxd2);
         int pos = incl - mine;
@@ -188,7 +188,7 @@ template <class T> __device__ int buildPatch(const PatchArgs& a, PatchSmem<T>& s
                 s.misc[2] = 1;
         }
     };
-    int myTF = lane < K ? a.face[tIdx[lane]] : sf; // K <= T::MAXK <= 32: one target per lane
+    int myTF = lane < K ? a.face[tIdx[lane]] : sf; // K <= T::RECK <= 32: one target per lane
     if (lane == 0) addFace(sf);
     __syncwarp();
     if (__any_sync(FULL, myTF != sf)) {

@@ -45,7 +45,9 @@ template <class T, bool LEAN> struct WinSmem { // per-warp workspace
     double tbest[K], tb0[K], tb1[K], tb2[K], tsx[K], tsy[K], tdu[K], tdw[K];
     double tpx[K], tpy[K], tpz[K], tcd0[K], tcd1[K], tcd2[K];
     double root[6];
+    double fpart[3]; // pair forces of the earlier target groups of this source
     unsigned long long wcnt[16];
+    int grp[2];      // [0] first target of the group being propagated, [1] number of targets of the source
     int rmeta[R];
     int tIdx[K];
     int tcode[K];  // how the best path ends: 0 none, 1 chord in the source face, 2 + 4*(g | e << 8) window, 3 + 4*k corner k
@@ -254,18 +256,29 @@ template <class W> __device__ __noinline__ d3 liftEnd(const MeshDev& m, const W&
     return d3{rx / L, ry / L, rz / L};
 }
 
-enum { WS_OK = 0, WS_RING = 1 };
+enum { WS_OK = 0, WS_RING = 1, WS_GROUPS = 2 };
 
-template <class T, bool LEAN> __device__ int processRecord(const WinArgs& a, WinSmem<T, LEAN>& w, int li, int rslot, int lane)
+// One propagation for the targets [base, base + T::MAXK) of the record, base = w.grp[0].  The pair forces are summed in
+// neighbour order across the groups (the partial sum waits in w.fpart); force and kicked velocity are written by the last
+// group only, so a ring overflow in any group leaves the particle untouched for the retry tiers.  The group state lives in
+// shared memory and is re-read where it is needed: the common single-group path keeps no extra registers alive.
+template <class T, bool LEAN, bool GROUPED> __device__ int processRecord(const WinArgs& a, WinSmem<T, LEAN>& w, int li, int rslot, int lane)
 {
     constexpr int MASKR = T::RING - 1;
     unsigned long long* cnt = w.wcnt;
     const int gi = a.minIdx + li;
     const unsigned char* rec = a.records + (size_t)rslot * T::BYTES;
     const int4 hdr = *reinterpret_cast<const int4*>(rec);
-    const int nF = hdr.x, nV = hdr.y, K = hdr.z;
+    const int nF = hdr.x, nV = hdr.y;
     if (hdr.w) return WS_OK; // overflowed in stage 1: the retry tiers own this source
-    if (K == 0) {
+    int Kg = hdr.z;
+    if constexpr (GROUPED) {
+        Kg = min(T::MAXK, hdr.z - w.grp[0]);
+        if (lane == 0) w.grp[1] = hdr.z; // read back by the caller: are there more target groups?
+    } else if (hdr.z > T::MAXK)
+        return WS_GROUPS; // more candidates than one propagation takes: the caller switches to the grouped instantiation
+    const int K = Kg;
+    if (hdr.z == 0) {
         if (lane == 0) {
             cnt[C_SOURCES]++;
             a.nbrCount[li] = 0;
@@ -306,9 +319,10 @@ template <class T, bool LEAN> __device__ int processRecord(const WinArgs& a, Win
             w.vdirty[v] = 0;
         }
         if (lane < K) {
-            int j = reinterpret_cast<const int*>(rec + T::OFF_TIDX)[lane];
+            const int base = GROUPED ? w.grp[0] : 0;
+            int j = reinterpret_cast<const int*>(rec + T::OFF_TIDX)[base + lane];
             w.tIdx[lane] = j;
-            w.tFace[lane] = rec[T::OFF_TFACE + lane];
+            w.tFace[lane] = rec[T::OFF_TFACE + base + lane];
             w.tb0[lane] = a.bary[3 * j], w.tb1[lane] = a.bary[3 * j + 1], w.tb2[lane] = a.bary[3 * j + 2];
             w.tpx[lane] = a.eucl[3 * j], w.tpy[lane] = a.eucl[3 * j + 1], w.tpz[lane] = a.eucl[3 * j + 2];
             w.tbest[lane] = dinf();
@@ -615,6 +629,9 @@ template <class T, bool LEAN> __device__ int processRecord(const WinArgs& a, Win
     }
 
     // ---------------- results, pair forces ----------------
+    int base = 0, Ktot = K;
+    if constexpr (GROUPED) base = *reinterpret_cast<volatile int*>(&w.grp[0]), Ktot = *reinterpret_cast<volatile int*>(&w.grp[1]);
+    const bool firstGroup = base == 0, lastGroup = base + T::MAXK >= Ktot;
     unsigned long long nDis = 0;
     double dres = 0;
     d3 ts{0, 0, 1}, te{0, 0, 1};
@@ -650,7 +667,7 @@ template <class T, bool LEAN> __device__ int processRecord(const WinArgs& a, Win
                 }
             }
         }
-        size_t o = (size_t)li * a.kmax + t;
+        size_t o = (size_t)li * a.kmax + base + t;
         a.nbrIdx[o] = w.tIdx[t];
         a.nbrDist[o] = dres;
         if (a.nbrTs) a.nbrTs[3 * o] = ts.x, a.nbrTs[3 * o + 1] = ts.y, a.nbrTs[3 * o + 2] = ts.z;
@@ -662,7 +679,8 @@ template <class T, bool LEAN> __device__ int processRecord(const WinArgs& a, Win
     if (a.forceMode && lane < K) pf = pairForce(a.fp, ts, dres);
     d3 f{0, 0, 0};
     if (a.forceMode) {
-        if (lane == 0 && !a.zero) f = d3{a.frc[3 * li], a.frc[3 * li + 1], a.frc[3 * li + 2]};
+        if (!firstGroup) f = d3{w.fpart[0], w.fpart[1], w.fpart[2]};
+        else if (lane == 0 && !a.zero) f = d3{a.frc[3 * li], a.frc[3 * li + 1], a.frc[3 * li + 2]};
         for (int t = 0; t < K; ++t) {
             double x = __shfl_sync(FULL, pf.x, t), y = __shfl_sync(FULL, pf.y, t), z = __shfl_sync(FULL, pf.z, t);
             f.x += x, f.y += y, f.z += z;
@@ -680,25 +698,43 @@ template <class T, bool LEAN> __device__ int processRecord(const WinArgs& a, Win
         atomicAdd(a.counters + C_CLK_BATCH, (unsigned long long)nPass), atomicAdd(a.counters + C_CLK_FAN, (unsigned long long)nPass3);
         atomicAdd(a.counters + C_CLK_PROP, (unsigned long long)nPass8);
 #endif
-        cnt[C_SOURCES]++;
         cnt[C_QUERIES] += K;
-        cnt[C_PATCH_FACES] += nF;
-        cnt[C_PATCH_VERTS] += nV;
-        a.nbrCount[li] = K;
-        if (a.forceMode) {
-            a.frc[3 * li] = f.x, a.frc[3 * li + 1] = f.y, a.frc[3 * li + 2] = f.z;
-            if (a.kick != 0.0) a.vel[3 * li] += a.kick * f.x, a.vel[3 * li + 1] += a.kick * f.y, a.vel[3 * li + 2] += a.kick * f.z;
-        }
+        if (firstGroup) cnt[C_PATCH_FACES] += nF, cnt[C_PATCH_VERTS] += nV;
+        if (lastGroup) {
+            cnt[C_SOURCES]++;
+            a.nbrCount[li] = Ktot;
+            if (a.forceMode) {
+                a.frc[3 * li] = f.x, a.frc[3 * li + 1] = f.y, a.frc[3 * li + 2] = f.z;
+                if (a.kick != 0.0) a.vel[3 * li] += a.kick * f.x, a.vel[3 * li + 1] += a.kick * f.y, a.vel[3 * li + 2] += a.kick * f.z;
+            }
+        } else
+            w.fpart[0] = f.x, w.fpart[1] = f.y, w.fpart[2] = f.z;
     }
     return WS_OK;
 }
 
 } // namespace
 
+// rare path (~5e-6 of the sources of config 5): one propagation per group of T::MAXK targets, out of line so that the
+// common path compiles exactly as if it did not exist
+template <class T, bool LEAN> __device__ __noinline__ int processGroups(const WinArgs& a, WinSmem<T, LEAN>& w, int li, int rslot, int lane)
+{
+    int st = WS_OK;
+    for (int base = 0;; base += T::MAXK) {
+        if (lane == 0) w.grp[0] = base;
+        __syncwarp();
+        st = processRecord<T, LEAN, true>(a, w, li, rslot, lane);
+        st = __shfl_sync(FULL, st, 0);
+        __syncwarp();
+        if (st != WS_OK || base + T::MAXK >= w.grp[1]) break;
+    }
+    return st;
+}
+
 #ifndef CSS_LEAN_MINBLOCKS
 #define CSS_LEAN_MINBLOCKS 5
 #endif
-template <class T, bool LEAN> __global__ void __launch_bounds__(128, LEAN ? CSS_LEAN_MINBLOCKS : 4) k_windows(WinArgs a)
+template <class T, bool LEAN> __global__ void __launch_bounds__(128, LEAN ? CSS_LEAN_MINBLOCKS : 4) k_windows(const __grid_constant__ WinArgs a)
 {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -713,9 +749,11 @@ template <class T, bool LEAN> __global__ void __launch_bounds__(128, LEAN ? CSS_
         s = __shfl_sync(FULL, s, 0);
         if (s >= nWork) break;
         const int li = a.srcList ? a.srcList[s] : s;
-        int st = processRecord<T, LEAN>(a, w, li, s, lane);
+        int st = processRecord<T, LEAN, false>(a, w, li, s, lane);
         st = __shfl_sync(FULL, st, 0);
         __syncwarp();
+        if constexpr (T::RECK > T::MAXK)
+            if (st == WS_GROUPS) st = processGroups<T, LEAN>(a, w, li, s, lane);
         if (st != WS_OK && lane == 0) { // ring overflow: rerun on the next tier
             int r = atomicAdd(a.retryCount, 1);
             a.retryList[r] = li;
