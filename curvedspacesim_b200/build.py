@@ -12,7 +12,7 @@ LIB = os.path.join(HERE, "libcurvedspacesim_b200.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 # (source, extra flags).  exact_kernels.cu must not contract a*b+c into FMA (bit parity with the oracle).
-UNITS = [("exact_kernels.cu", ["-fmad=false"]), ("geodesic_kernel.cu", []), ("patch_kernel.cu", []), ("window_kernel.cu", []),
+UNITS = [("exact_kernels.cu", ["-fmad=false"]), ("geodesic_kernel.cu", []), ("patch_kernel.cu", []), ("window_kernel.cu", []), ("window_half_kernel.cu", []),
          ("css_api.cu", [])]
 
 
@@ -25,7 +25,7 @@ def _stale(target, deps):
 
 def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    hdrs = [os.path.join(CSRC, h) for h in ("common.cuh", "kernels.h")] + [os.path.join(HERE, "..", "include", "css_api.h")]
+    hdrs = [os.path.join(CSRC, h) for h in ("common.cuh", "kernels.h", "window_common.cuh")] + [os.path.join(HERE, "..", "include", "css_api.h")]
     objs = []
     for src, extra in UNITS:
         s = os.path.join(CSRC, src)

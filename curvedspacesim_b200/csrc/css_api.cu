@@ -61,9 +61,10 @@ struct css_ctx {
     int t2Warps = 32;
     int wpb0 = 4, wpb1 = 1;
     // two-stage tier 0: patch records (stage 1) -> window propagation (stage 2)
-    bool twoStage = true, winLean = true;
+    bool twoStage = true, winLean = true, winHalf = true;
     int winWpb = 2;
     unsigned char *d_records = nullptr, *d_recordsL = nullptr;
+    double* d_spill = nullptr; // window spill stacks of the two-sources-per-warp kernel (allocated once)
     size_t capRecords = 0, capRecordsL = 0;
     int numSMs = 148;
     // reductions / scratch
@@ -294,6 +295,7 @@ int css_create(css_ctx** out, int device)
     if (const char* v = getenv("CSS_LEGACY_TIER0")) ctx->twoStage = atoi(v) == 0; // developer switch: fused one-kernel tier 0
     if (const char* v = getenv("CSS_NO_GRAPH")) ctx->useGraph = atoi(v) == 0;
     if (const char* v = getenv("CSS_WIN_LEAN")) ctx->winLean = atoi(v) != 0;
+    if (const char* v = getenv("CSS_WIN_HALF")) ctx->winHalf = atoi(v) != 0; // 0: one warp per source in tier 0 (window_kernel.cu)
     if (const char* v = getenv("CSS_WIN_WPB")) ctx->winWpb = std::max(1, std::min(4, atoi(v)));
     if (const char* v = getenv("CSS_P2P")) ctx->p2pEnabled = atoi(v) != 0;
     *out = ctx;
@@ -313,7 +315,7 @@ int css_destroy(css_ctx* ctx)
                     ctx->d_blockSums, ctx->d_fill,   ctx->d_tmpItems, ctx->d_items,  ctx->d_nbrCount, ctx->d_nbrIdx,  ctx->d_nbrDist,
                     ctx->d_nbrTs,  ctx->d_nbrTe,     ctx->d_work,    ctx->d_retry[0], ctx->d_retry[1], ctx->d_retry[2], ctx->d_gws,
                     ctx->d_partial, ctx->d_red,      ctx->d_counters, ctx->d_sendI,  ctx->d_sendD,    ctx->d_recvI,   ctx->d_recvD,
-                    ctx->d_redBuf,  ctx->d_geo,       ctx->d_records, ctx->d_recordsL, ctx->d_epoch, ctx->d_ticket, ctx->d_ipcBuf};
+                    ctx->d_redBuf,  ctx->d_geo,       ctx->d_records, ctx->d_recordsL, ctx->d_epoch, ctx->d_ticket, ctx->d_ipcBuf, ctx->d_spill};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (auto& e : ctx->ev)
@@ -564,8 +566,9 @@ static int runGeodesicTiers(css_ctx* ctx, GeoArgs a, int nSrc)
         // Tier 0 = TierSmall over every local source; tier 1 = TierLarge over the sources tier 0 handed on.
         const int maxLarge = std::min(std::max(nSrc, 1), 65536);
         size_t needS = (size_t)std::max(nSrc, 1) * TierSmall::BYTES, needL = (size_t)maxLarge * TierLarge::BYTES;
-        if (needS > ctx->capRecords || needL > ctx->capRecordsL) {
+        if (needS > ctx->capRecords || needL > ctx->capRecordsL || (ctx->winHalf && !ctx->d_spill)) {
             CU(cudaStreamSynchronize(ctx->st));
+            if (ctx->winHalf && !ctx->d_spill) CU(regrow(ctx->d_spill, windowsHalfSpillBytes(ctx->numSMs) / sizeof(double)));
             if (needS > ctx->capRecords) {
                 CU(regrow(ctx->d_records, needS));
                 ctx->capRecords = needS;
@@ -586,7 +589,7 @@ static int runGeodesicTiers(css_ctx* ctx, GeoArgs a, int nSrc)
         w.submeshing = a.submeshing, w.maxDist = a.maxDist, w.kmax = a.kmax;
         w.nbrCount = a.nbrCount, w.nbrIdx = a.nbrIdx, w.nbrDist = a.nbrDist, w.nbrTs = a.nbrTs, w.nbrTe = a.nbrTe;
         w.forceMode = a.forceMode, w.fp = a.fp, w.zero = a.zero, w.frc = a.frc, w.kick = a.kick, w.vel = a.vel;
-        w.counters = ctx->d_counters;
+        w.counters = ctx->d_counters, w.spill = ctx->d_spill;
         // tier 0
         p.srcList = nullptr, p.srcCount = nullptr, p.maxRecords = std::max(nSrc, 1);
         p.workCounter = ctx->d_work + 0, p.retryList = ctx->d_retry[0], p.retryCount = ctx->d_work + 4, p.records = ctx->d_records;
@@ -595,7 +598,8 @@ static int runGeodesicTiers(css_ctx* ctx, GeoArgs a, int nSrc)
         if (ctx->timing) recordEvent(ctx, ctx->evS[0]);
         CU(launchPatch<TierSmall>(ctx->st, p, ctx->numSMs));
         if (ctx->timing) recordEvent(ctx, ctx->evS[1]);
-        CU(launchWindows<TierSmall>(ctx->st, w, ctx->winWpb, ctx->numSMs, ctx->winLean));
+        if (ctx->winHalf) CU(launchWindowsHalf<TierHalf>(ctx->st, w, ctx->numSMs));
+        else CU(launchWindows<TierSmall>(ctx->st, w, ctx->winWpb, ctx->numSMs, ctx->winLean));
         if (ctx->timing) recordEvent(ctx, ctx->evS[2]);
         // tier 1 (work list = tier 0's retry list; its length is only known on the device)
         p.srcList = ctx->d_retry[0], p.srcCount = ctx->d_work + 4, p.maxRecords = maxLarge;
@@ -1104,11 +1108,11 @@ static uint64_t nveGraphKey(css_ctx* ctx, const ForceParams& fp, double range, d
 #define MIX(x) mix(&(x), sizeof(x))
     MIX(fp.kind), MIX(fp.a), MIX(fp.sigma), MIX(range), MIX(dt);
     MIX(ctx->nLocal), MIX(ctx->nTotal), MIX(ctx->minIdx), MIX(ctx->kmax), MIX(ctx->nranks), MIX(ctx->timing), MIX(ctx->submeshing),
-        MIX(ctx->maxDist), MIX(ctx->boundaryMode), MIX(ctx->useCellList), MIX(ctx->wantEnd), MIX(ctx->twoStage), MIX(ctx->winWpb), MIX(ctx->winLean), MIX(ctx->grid), MIX(ctx->nCells);
+        MIX(ctx->maxDist), MIX(ctx->boundaryMode), MIX(ctx->useCellList), MIX(ctx->wantEnd), MIX(ctx->twoStage), MIX(ctx->winWpb), MIX(ctx->winLean), MIX(ctx->winHalf), MIX(ctx->grid), MIX(ctx->nCells);
     void* ptrs[] = {ctx->d_vert, ctx->d_corner, ctx->d_adj, ctx->d_geo, ctx->d_saddle, ctx->d_face, ctx->d_bary, ctx->d_eucl, ctx->d_vel, ctx->d_frc,
                     ctx->d_disp, ctx->d_walkFlags, ctx->d_cellOf, ctx->d_cellCount, ctx->d_cellStart, ctx->d_blockSums, ctx->d_fill, ctx->d_tmpItems,
                     ctx->d_items, ctx->d_nbrCount, ctx->d_nbrIdx, ctx->d_nbrDist, ctx->d_nbrTs, ctx->d_nbrTe, ctx->d_retry[0], ctx->d_retry[1],
-                    ctx->d_retry[2], ctx->d_gws, ctx->d_records, ctx->d_recordsL, ctx->d_recvI, ctx->d_recvD, (void*)ctx->comm, ctx->winLocal,
+                    ctx->d_retry[2], ctx->d_gws, ctx->d_records, ctx->d_recordsL, ctx->d_spill, ctx->d_recvI, ctx->d_recvD, (void*)ctx->comm, ctx->winLocal,
                     ctx->winPeer[0], ctx->winPeer[1], ctx->winPeer[2], ctx->winPeer[3], ctx->winPeer[4], ctx->winPeer[5], ctx->winPeer[6],
                     ctx->winPeer[7]};
     MIX(ptrs);

@@ -97,6 +97,16 @@ template <int F_, int V_, int K_, int RING_, int RECK_ = K_> struct GeoTier {
 #endif
 using TierSmall = GeoTier<96, 64, CSS_T0_K, CSS_T0_RING, CSS_T0_RECK>;
 using TierLarge = GeoTier<240, 160, 32, 256>;
+// Tier 0 as the two-sources-per-warp kernel sees it (window_half_kernel.cu): the SAME record layout as TierSmall, a slimmer
+// per-source workspace (8 targets per propagation, 32-window ring) so that twice as many sources are resident per SM.
+#ifndef CSS_TH_K
+#define CSS_TH_K 8
+#endif
+#ifndef CSS_TH_RING
+#define CSS_TH_RING 32
+#endif
+using TierHalf = GeoTier<96, 64, CSS_TH_K, CSS_TH_RING, CSS_T0_RECK>;
+static_assert(TierHalf::BYTES == TierSmall::BYTES && TierHalf::OFF_FVERT == TierSmall::OFF_FVERT, "TierHalf reads TierSmall records");
 #define REC_NONE 255
 #define PATCH_THREADS 256
 
@@ -151,8 +161,11 @@ struct WinArgs {
     int* retryList;
     int* retryCount;
     unsigned long long* counters;
+    double* spill; // launchWindowsHalf only: windowsHalfSpillBytes(numSMs) bytes of scratch
 };
 template <class Tier> cudaError_t launchWindows(cudaStream_t st, const WinArgs& a, int warpsPerBlock, int numSMs, bool lean);
+template <class Tier> cudaError_t launchWindowsHalf(cudaStream_t st, const WinArgs& a, int numSMs); // two sources per warp
+size_t windowsHalfSpillBytes(int numSMs);
 int geodesicMaxSmemPerBlock();
 
 void launchEuclidCell(cudaStream_t st, const MeshDev& m, const CellGrid& g, int n, const int* face, const double* bary, double* eucl,

@@ -541,6 +541,47 @@ np.savez(sys.argv[1], off=off, idx=idx, d=d, ts=ts, te=te, retry=c["tier_retry"]
     assert _rel(a["d"], b["d"]) < 1e-12 and np.max(np.abs(a["ts"] - b["ts"])) < 1e-10
 
 
+def test_half_warp_and_one_warp_tier0_agree():
+    """Tier 0 runs two sources per warp (window_half_kernel.cu, 8 targets per propagation, groups for K > 8);
+    CSS_WIN_HALF=0 selects the one-warp-per-source kernel.  Same neighbour lists, distances and tangents to round-off,
+    on a dense state (K up to ~30: several target groups per source) and through fused NVE steps."""
+    code = r"""
+import sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+from curvedspacesim_b200 import binding, meshes
+from helpers import make_state, interaction_range
+from oracle_binding import force_params
+V, F = meshes.torus(120, 40, R=3.0, r=1.0, jitter=0.2, seed=7)
+N = 3000
+corners, face, bary, vel = make_state(V, F, N)
+area = float(meshes.face_areas(V, F).sum()); rc = interaction_range(area, N, 4.0)
+kind, params = force_params("harmonic", k=1.0, sigma=rc)
+ctx = binding.Context(0); ctx.set_mesh(V, corners); ctx.set_submeshing(True, rc); ctx.set_options(True, True); ctx.set_state(face, bary, vel)
+off, idx, d, ts, te = ctx.find_neighbors(rc, want_end=True)
+c = ctx.counters()
+ctx.step_nve(kind, params, 0.002, 10)
+f2, b2, v2, fr2 = ctx.get_state()
+np.savez(sys.argv[1], off=off, idx=idx, d=d, ts=ts, te=te, retry=c["tier_retry"], overflow=c["overflow"], face=f2, bary=b2, vel=v2, frc=fr2,
+         kmean=len(idx) / N, kmax=int(np.diff(off).max()))
+""" % (ROOT, os.path.join(ROOT, "tests"))
+    import tempfile
+
+    outs = []
+    with tempfile.TemporaryDirectory() as td:
+        for i, half in enumerate(("1", "0")):
+            env = dict(os.environ, CSS_WIN_HALF=half)
+            out = os.path.join(td, "o%d.npz" % i)
+            subprocess.check_call([sys.executable, "-c", code, out], env=env, timeout=300)
+            outs.append(dict(np.load(out)))
+    a, b = outs
+    assert int(a["kmax"]) > 16 and float(a["kmean"]) > 8          # the grouped path is exercised
+    assert int(a["overflow"]) == 0 and int(b["overflow"]) == 0
+    assert np.array_equal(a["off"], b["off"]) and np.array_equal(a["idx"], b["idx"])
+    assert _rel(a["d"], b["d"]) < 1e-12 and np.max(np.abs(a["ts"] - b["ts"])) < 1e-10 and np.max(np.abs(a["te"] - b["te"])) < 1e-10
+    assert np.array_equal(a["face"], b["face"])
+    assert np.max(np.abs(a["bary"] - b["bary"])) < 1e-9 and np.max(np.abs(a["frc"] - b["frc"])) < 1e-8 * np.abs(a["frc"]).max()
+
+
 # ------------------------------------------------------------------------------ full size: properties
 @pytest.mark.parametrize("workload", ["cfg4_icosphere_250kfaces_N25k", "cfg5_torus_1Mfaces_N100k"])
 def test_full_size_properties(workload, gpu_ctx_factory):
