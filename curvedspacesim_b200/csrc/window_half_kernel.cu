@@ -37,19 +37,19 @@ template <class T> struct HalfSmem { // per-SOURCE workspace, two per warp (alwa
     using mask_t = typename MaskOf<(K <= 8 ? 8 : 16)>::type;
     static_assert(K <= 16 && R >= 32, "one target per lane of the half; a pass pushes up to 16 children");
     int gface[F], gvert[V];
-    double D[V], dirx[V], diry[V];
+    double D[V + 1], dirx[V], diry[V]; // D[V] = 0: the sigma of the real source
     double rax[R], ray[R], rbx[R], rby[R], rt0[R], rt1[R];
     double2 rcg[R];
     double tbest[K], tb0[K], tb1[K], tb2[K], tsx[K], tsy[K], tdu[K], tdw[K];
     double tpx[K], tpy[K], tpz[K], tcd0[K], tcd1[K], tcd2[K];
     double root[6];
     double fpart[3]; // pair forces of the earlier target groups of this source
-    double s2[2];    // the source in the root frame
     int rmeta[R];
     int tIdx[K];
     int tcode[K]; // how the best path ends: 0 none, 1 chord in the source face, 2 + 4*(g | e << 8) window, 3 + 4*k corner k
     int towner[K];
     unsigned wcnt[16];
+    float ub; // pruning bound: max over the targets of the best distance known, fp32 rounded up
     alignas(16) uchar4 fvert[F];
     uchar4 fadj[F];
     alignas(4) mask_t tmask[F]; // targets lying in each face (bit t)
@@ -59,10 +59,20 @@ template <class T> struct HalfSmem { // per-SOURCE workspace, two per warp (alwa
     unsigned char rpsv[R];
 };
 
-template <class W> __device__ __forceinline__ float halfBound(const W& w, int hl, unsigned hmask, int K)
-{ // upper bound max_t best[t] over this half's targets, fp32 rounded up
-    unsigned u = hl < K ? __float_as_uint(__double2float_ru(w.tbest[hl])) : 0u;
-    return __uint_as_float(__reduce_max_sync(hmask, u)) * (1.f + 2e-5f);
+// one lane refreshes the pruning bound of a source after its target distances changed
+template <class W> __device__ __forceinline__ void updateBound(W& w, int K)
+{
+    unsigned u = 0;
+    for (int t = 0; t < K; ++t) u = max(u, __float_as_uint(__double2float_ru(w.tbest[t])));
+    w.ub = __uint_as_float(u) * (1.f + 2e-5f);
+}
+// parameter on X + mu (Y - X) hit by the ray from the origin through P, clamped to the segment
+__device__ __forceinline__ double hitParam0(const v2& P, const v2& X, const v2& Y)
+{
+    double den = cross2(Y - X, P);
+    double mu = -cross2(X, P) * frcp(den);
+    if (!(mu == mu)) mu = 0.5;
+    return fmin(1.0, fmax(0.0, mu));
 }
 
 // push up to one window per lane into the ring of the lane's own half; false when that ring would overflow
@@ -187,7 +197,7 @@ template <class T> __global__ void __launch_bounds__(32 * CSS_HALF_WPB, CSS_HALF
 
         // ---------------- root frame, direct legs ----------------
         // source face = local face 0: corner 0 at the origin, corner 1 on +x, corner 2 above
-        v2 rq1{1, 0}, rq2{0, 1}, S2{0, 0};
+        v2 rq0{0, 0}, rq1{1, 0}, rq2{0, 1};
         if (live) {
             uchar4 fv = w.fvert[0];
             const d3 P0 = vpos(a.m, w, fv.x), P1 = vpos(a.m, w, fv.y), P2 = vpos(a.m, w, fv.z);
@@ -203,16 +213,19 @@ template <class T> __global__ void __launch_bounds__(32 * CSS_HALF_WPB, CSS_HALF
             rq1 = v2{L01, 0};
             rq2 = v2{x2, y2};
             double rbs = 1.0 / (sb0 + sb1 + sb2);
-            S2 = v2{(sb1 * rq1.x + sb2 * rq2.x) * rbs, (sb2 * rq2.y) * rbs};
-            if (hl == 0) w.s2[0] = S2.x, w.s2[1] = S2.y;
+            const v2 S2{(sb1 * rq1.x + sb2 * rq2.x) * rbs, (sb2 * rq2.y) * rbs};
+            // translate: the source becomes the origin of the root frame
+            rq0 = v2{-S2.x, -S2.y};
+            rq1 = rq1 - S2, rq2 = rq2 - S2;
+            if (hl == 0) w.D[W::V] = 0.0;
             if (hl == 0) w.root[0] = ex.x, w.root[1] = ex.y, w.root[2] = ex.z, w.root[3] = ey.x, w.root[4] = ey.y, w.root[5] = ey.z;
             if (hl < 3) { // straight legs to the three corners of the source face
                 int cv = hl == 0 ? fv.x : (hl == 1 ? fv.y : fv.z);
-                v2 q = hl == 0 ? v2{0, 0} : (hl == 1 ? rq1 : rq2);
+                v2 q = hl == 0 ? rq0 : (hl == 1 ? rq1 : rq2);
                 d3 P = hl == 0 ? P0 : (hl == 1 ? P1 : P2);
                 d3 d{P.x - sp.x, P.y - sp.y, P.z - sp.z};
                 w.D[cv] = sqrt(d.x * d.x + d.y * d.y + d.z * d.z);
-                w.dirx[cv] = q.x - S2.x, w.diry[cv] = q.y - S2.y;
+                w.dirx[cv] = q.x, w.diry[cv] = q.y;
                 w.vdirty[cv] = 1;
             }
             if (hl < K) {
@@ -251,13 +264,15 @@ template <class T> __global__ void __launch_bounds__(32 * CSS_HALF_WPB, CSS_HALF
                     valid = true;
                     meta = g | (kk << 16);
                     // edge k runs corner k+1 -> corner k+2; the neighbour sees it reversed
-                    A = hl == 0 ? rq2 : (hl == 1 ? v2{0, 0} : rq1);
-                    B = hl == 0 ? rq1 : (hl == 1 ? rq2 : v2{0, 0});
+                    A = hl == 0 ? rq2 : (hl == 1 ? rq0 : rq1);
+                    B = hl == 0 ? rq1 : (hl == 1 ? rq2 : rq0);
                     cg = edgeFrame(a.m, w, g, kk);
                 }
             }
             pushHalf(w, hl, hbase, head, tail, valid, A, B, 0.0, 1.0, meta, NOPSV, cg); // 3 <= ring
         }
+        __syncwarp();
+        if (hl == 0) updateBound(w, K);
         __syncwarp();
 
         unsigned nWin = 0, nPs = 0;
@@ -296,50 +311,41 @@ template <class T> __global__ void __launch_bounds__(32 * CSS_HALF_WPB, CSS_HALF
                 const int k = src ? slot - nb0 : slot;
                 bool active = src ? k < nb1 : true;
                 W& wp = wpair[src];
-                const float fUb = __shfl_sync(FULL, halfBound(w, hl, hmask, K), 16 * src);
+                const float fUb = wp.ub; // max over the source's targets of the best distance so far (kept by updateBound)
                 const int j = lane & 1; // which child edge this lane propagates into
 #ifdef CSS_PASS_STATS
                 nPass++, nPassIdle += (nb0 == 0 || nb1 == 0), nPass4 += nb0 + nb1 <= 8, nPop += nb0 + nb1;
 #endif
                 const int p = ((src ? head1 : head0) + k) & MASKR;
                 head += half ? nb1 : nb0;
-                v2 A{0, 0}, B{1, 0}, S{0, -1};
-                double t0 = 0, t1 = 1, sg = 0;
-                int meta = 0;
-                unsigned char psv = NOPSV;
-                double2 cg{0, 0};
-                if (active) {
-                    A = v2{wp.rax[p], wp.ray[p]}, B = v2{wp.rbx[p], wp.rby[p]};
-                    t0 = wp.rt0[p], t1 = wp.rt1[p], meta = wp.rmeta[p], psv = wp.rpsv[p];
-                    cg = wp.rcg[p];
-                    // a window family lives in the frame of its (pseudo-)source: the real source sits at S2 in the root frame,
-                    // a pseudo-source at the origin of its fan frame with sigma = its current vertex distance
-                    if (psv == NOPSV) S = v2{wp.s2[0], wp.s2[1]};
-                    else S = v2{0, 0}, sg = wp.D[psv];
-                }
-                __syncwarp(); // every slot of this pass is read before anybody pushes
+                // ---- pop.  Every lane reads its slot (the index is always inside the ring; lanes without a window compute on
+                // stale data and are masked at every side effect): straight-line code instead of divergent regions.
+                // Window families live in the frame of their (pseudo-)source, which sits at the ORIGIN of that frame (the root
+                // frame is translated so that the real source is at the origin too); sigma = D[pseudo-source], D[V] = 0 stands
+                // for the real source.
+                const v2 A{wp.rax[p], wp.ray[p]}, B{wp.rbx[p], wp.rby[p]};
+                const double t0 = wp.rt0[p], t1 = wp.rt1[p];
+                const double2 cg = wp.rcg[p];
+                const int meta = active ? wp.rmeta[p] : 0;
+                const unsigned char psv = wp.rpsv[p];
+                const double sg = wp.D[min((int)psv, W::V)];
                 const int g = meta & 0xFF, e = (meta >> 16) & 3;
                 const v2 AB = B - A;
                 const v2 P0 = lerp2(A, B, t0), P1 = lerp2(A, B, t1);
-                const f2 fS = tof2(S);
                 const float fsg = (float)sg;
-                if (active && fsg + fsegDist(fS, tof2(P0), tof2(P1)) * (1.f - 1e-5f) > fUb) active = false; // bound tightened since the push
-                // ---- unfold the entered face: apex C from the edge frame
-                int vA = 0, vB = 0, vC = 0, kkbits = 0;
-                uchar4 fa = make_uchar4(REC_NONE, REC_NONE, REC_NONE, 0);
-                v2 C{0, 1};
-                unsigned tm = 0;
-                if (active) {
-                    nWin += j == 0;
-                    uchar4 fv = wp.fvert[g];
-                    fa = wp.fadj[g];
-                    kkbits = fv.w;
-                    vA = e == 0 ? fv.y : (e == 1 ? fv.z : fv.x);
-                    vB = e == 0 ? fv.z : (e == 1 ? fv.x : fv.y);
-                    vC = e == 0 ? fv.x : (e == 1 ? fv.y : fv.z);
-                    C = v2{fma(cg.x, AB.x, fma(-cg.y, AB.y, A.x)), fma(cg.x, AB.y, fma(cg.y, AB.x, A.y))};
-                    if (j == 0) tm = wp.tmask[g]; // the even lane of the pair answers the queries
-                }
+                const f2 fO{0.f, 0.f};
+                if (fsg + fsegDist(fO, tof2(P0), tof2(P1)) * (1.f - 1e-5f) > fUb) active = false; // bound tightened since the push
+                // ---- unfold the entered face: apex C from the edge frame; corners / neighbours / edge indices rotated by e
+                const unsigned fvw = *reinterpret_cast<const unsigned*>(&wp.fvert[g]), faw = *reinterpret_cast<const unsigned*>(&wp.fadj[g]);
+                const unsigned fv3 = fvw & 0xFFFFFFu, fa3 = faw & 0xFFFFFFu, kb = (fvw >> 24) & 63u;
+                const unsigned rv = __funnelshift_r(fv3 | (fv3 << 24), fv3 >> 8, 8 * e);  // bytes: corner e, e+1, e+2
+                const unsigned ra = __funnelshift_r(fa3 | (fa3 << 24), fa3 >> 8, 8 * e);  // faces opposite corner e, e+1, e+2
+                const unsigned rk = (kb | (kb << 6)) >> (2 * e);                          // 2-bit edge indices, same rotation
+                const int vC = rv & 0xFF, vA = (rv >> 8) & 0xFF, vB = (rv >> 16) & 0xFF;
+                const v2 C{fma(cg.x, AB.x, fma(-cg.y, AB.y, A.x)), fma(cg.x, AB.y, fma(cg.y, AB.x, A.y))};
+                nWin += active && j == 0;
+                unsigned tm = (active && j == 0) ? wp.tmask[g] : 0u; // the even lane of the pair answers the queries
+                __syncwarp(); // every slot of this pass is read before anybody pushes
                 // ---- queries: targets inside the entered face (rare: ~K/nF of the windows enter a face that holds a target)
                 while (__any_sync(FULL, tm != 0)) {
                     bool improvedT = false;
@@ -352,11 +358,10 @@ template <class T> __global__ void __launch_bounds__(32 * CSS_HALF_WPB, CSS_HALF
                         double b0 = wp.tb0[t], b1 = wp.tb1[t], b2 = wp.tb2[t];
                         double bA = e == 0 ? b1 : (e == 1 ? b2 : b0), bB = e == 0 ? b2 : (e == 1 ? b0 : b1), bC = e == 0 ? b0 : (e == 1 ? b1 : b2);
                         double rbs = frcp(bA + bB + bC);
-                        v2 Tq{(bA * A.x + bB * B.x + bC * C.x) * rbs, (bA * A.y + bB * B.y + bC * C.y) * rbs};
-                        v2 d = Tq - S;
+                        v2 d{(bA * A.x + bB * B.x + bC * C.x) * rbs, (bA * A.y + bB * B.y + bC * C.y) * rbs}; // the target, seen from the source
                         double den = cross2(AB, d);
                         if (den != 0) {
-                            double mu = cross2(S - A, d) * frcp(den);
+                            double mu = -cross2(A, d) * frcp(den);
                             if (mu >= t0 - 1e-12 && mu <= t1 + 1e-12) {
                                 double c = sg + fsqrt(d.x * d.x + d.y * d.y);
                                 if (atomicMinD(&wp.tbest[t], c)) improvedT = true, myT = t, cand = c, dT = d;
@@ -367,6 +372,7 @@ template <class T> __global__ void __launch_bounds__(32 * CSS_HALF_WPB, CSS_HALF
                         __syncwarp();
                         bool win = improvedT && wp.tbest[myT] == cand;
                         if (win) atomicMin(&wp.towner[myT], lane);
+                        if (hl == 0) updateBound(w, K);
                         __syncwarp();
                         if (win && wp.towner[myT] == lane) {
                             if (psv == NOPSV) wp.tsx[myT] = dT.x, wp.tsy[myT] = dT.y;
@@ -382,30 +388,23 @@ template <class T> __global__ void __launch_bounds__(32 * CSS_HALF_WPB, CSS_HALF
                     }
                 }
                 // ---- children
-                bool improved = false, leftOpen = false, rightOpen = false, inside = false;
-                double dC = 0;
-                float fDA = 0.f, fDB = 0.f, fDC = 0.f;
-                if (active) {
-                    const v2 dL = P0 - S, dR = P1 - S, dCv = C - S;
-                    const double sideL = cross2(dL, dCv), sideR = cross2(dR, dCv);
-                    const double lc2 = dCv.x * dCv.x + dCv.y * dCv.y;
-                    // |side| <= 1e-12 |d| |dC| counts as "on the ray" (squared form: no square roots)
-                    leftOpen = !(sideL > 0 && sideL * sideL > 1e-24 * (dL.x * dL.x + dL.y * dL.y) * lc2);
-                    rightOpen = !(sideR < 0 && sideR * sideR > 1e-24 * (dR.x * dR.x + dR.y * dR.y) * lc2);
-                    inside = leftOpen && rightOpen;
-                    double DC = wp.D[vC];
-                    if (inside) {
-                        dC = sg + fsqrt(lc2);
-                        if (dC < DC) {
-                            if (j == 0) improved = atomicMinD(&wp.D[vC], dC);
-                            DC = fmin(DC, dC);
-                        }
-                    }
-                    fDA = (float)wp.D[vA], fDB = (float)wp.D[vB], fDC = (float)DC;
+                const double sideL = cross2(P0, C), sideR = cross2(P1, C);
+                const double lc2 = C.x * C.x + C.y * C.y;
+                // |side| <= 1e-12 |d| |dC| counts as "on the ray" (squared form: no square roots)
+                const bool leftOpen = !(sideL > 0 && sideL * sideL > 1e-24 * (P0.x * P0.x + P0.y * P0.y) * lc2);
+                const bool rightOpen = !(sideR < 0 && sideR * sideR > 1e-24 * (P1.x * P1.x + P1.y * P1.y) * lc2);
+                const bool inside = leftOpen && rightOpen;
+                double DC = wp.D[vC];
+                const double dC = sg + fsqrt(lc2);
+                bool improved = false;
+                if (active && inside && dC < DC) {
+                    if (j == 0) improved = atomicMinD(&wp.D[vC], dC);
+                    DC = dC;
                 }
+                const float fDA = (float)wp.D[vA], fDB = (float)wp.D[vB], fDC = (float)DC;
                 __syncwarp();
                 if (improved && dC == wp.D[vC]) { // the winner writes the start direction carried to this vertex
-                    if (psv == NOPSV) wp.dirx[vC] = C.x - S.x, wp.diry[vC] = C.y - S.y;
+                    if (psv == NOPSV) wp.dirx[vC] = C.x, wp.diry[vC] = C.y;
                     else wp.dirx[vC] = wp.dirx[psv], wp.diry[vC] = wp.diry[psv];
                     wp.vdirty[vC] = 1;
                 }
@@ -413,34 +412,32 @@ template <class T> __global__ void __launch_bounds__(32 * CSS_HALF_WPB, CSS_HALF
                 // child j = 1: edge B->C of this face (opposite corner A), entered by the neighbour as C->B
                 // Xin-Wang filter and bound test in fp32 with a conservative margin: a window is dropped only when it is
                 // dominated by clearly more than the rounding of the approximation.
-                const f2 fA = tof2(A), fB = tof2(B), fC = tof2(C);
                 {
                     const v2 X = j ? C : A, Y = j ? B : C;
                     bool valid = false;
                     double m0 = 0, m1 = 1;
                     int cmeta = 0;
                     double2 ccg{0, 0};
-                    if (active && (j ? rightOpen : leftOpen)) {
-                        const int io = j ? (e == 2 ? 0 : e + 1) : (e == 0 ? 2 : e - 1); // corner opposite the child edge: iA / iB
-                        const int g2 = io == 0 ? fa.x : (io == 1 ? fa.y : fa.z);
-                        if (g2 != REC_NONE) {
-                            const int kk = (kkbits >> (2 * io)) & 3;
-                            ccg = edgeFrame(a.m, wp, g2, kk); // needed by the child at the next pass: issued here, stored with the push
-                            if (!(j == 1 && inside)) m0 = hitParam(S, P0, X, Y);
-                            if (!(j == 0 && inside)) m1 = hitParam(S, P1, X, Y);
-                            if (m1 - m0 > 1e-13) {
-                                const f2 fX = j ? fC : fA, fY = j ? fB : fC, fO = j ? fA : fB;
-                                const float dX = j ? fDC : fDA, dY = j ? fDB : fDC, dO = j ? fDA : fDB;
-                                const f2 X0 = flerp(fX, fY, (float)m0), X1 = flerp(fX, fY, (float)m1);
-                                if (fsg + fsegDist(fS, X0, X1) <= fUb) {
-                                    const float keep = 1.f - 2e-5f;
-                                    const float s0 = (fsg + fdist(fS, X0)) * keep, s1 = (fsg + fdist(fS, X1)) * keep;
-                                    const f2 Xn = j ? X1 : X0; // the end of the child interval next to the parent edge
-                                    const float sn = j ? s1 : s0;
-                                    const bool dom = (dX + fdist(fX, X1) < s1) || (dY + fdist(fY, X0) < s0) || (dO + fdist(fO, Xn) < sn);
-                                    valid = !dom;
-                                    cmeta = g2 | (kk << 16);
-                                }
+                    // corner opposite the child edge: B = corner e+2 for j = 0, A = corner e+1 for j = 1
+                    const int g2 = (ra >> (j ? 8 : 16)) & 0xFF;
+                    if (active && (j ? rightOpen : leftOpen) && g2 != REC_NONE) {
+                        const int kk = (rk >> (j ? 2 : 4)) & 3;
+                        ccg = edgeFrame(a.m, wp, g2, kk); // needed by the child at the next pass: issued here, stored with the push
+                        if (!(j == 1 && inside)) m0 = hitParam0(P0, X, Y);
+                        if (!(j == 0 && inside)) m1 = hitParam0(P1, X, Y);
+                        if (m1 - m0 > 1e-13) {
+                            const f2 fA = tof2(A), fB = tof2(B), fC = tof2(C);
+                            const f2 fX = j ? fC : fA, fY = j ? fB : fC, fO2 = j ? fA : fB;
+                            const float dX = j ? fDC : fDA, dY = j ? fDB : fDC, dO = j ? fDA : fDB;
+                            const f2 X0 = flerp(fX, fY, (float)m0), X1 = flerp(fX, fY, (float)m1);
+                            if (fsg + fsegDist(fO, X0, X1) <= fUb) {
+                                const float keep = 1.f - 2e-5f;
+                                const float s0 = (fsg + flen(X0.x, X0.y)) * keep, s1 = (fsg + flen(X1.x, X1.y)) * keep;
+                                const f2 Xn = j ? X1 : X0; // the end of the child interval next to the parent edge
+                                const float sn = j ? s1 : s0;
+                                const bool dom = (dX + fdist(fX, X1) < s1) || (dY + fdist(fY, X0) < s0) || (dO + fdist(fO2, Xn) < sn);
+                                valid = !dom;
+                                cmeta = g2 | (kk << 16);
                             }
                         }
                     }
@@ -496,7 +493,9 @@ template <class T> __global__ void __launch_bounds__(32 * CSS_HALF_WPB, CSS_HALF
                 }
             }
             __syncwarp();
-            const float fUb = halfBound(w, hl, hmask, K);
+            if (hl == 0) updateBound(w, K);
+            __syncwarp();
+            const float fUb = w.ub;
             // A vertex v can lie on a shortest path to target t only if D[v] + |x_v - x_t| (Euclidean lower bound of the
             // remaining leg) beats the best path known to t.
             bool spawned = false;
