@@ -315,7 +315,7 @@ def main():
     h2d = N * (4 + 24) + nloc * 48
     d2h = N * (4 + 24) + nloc * 48
 
-    # ---- roofline of the dominant kernel (k_windows, stage 2): algorithmic bytes per launch / measured duration.
+    # ---- roofline of the dominant kernel (k_windows_half, stage 2): algorithmic bytes per launch / measured duration.
     # Per source it must read its patch record (header 16, tIdx 4K, tFace K, velig P_v, gface 4 P_f, gvert 4 P_v,
     # fvert 4 P_f, fadj 4 P_f), the edge frames of the patch faces (48 P_f), the patch vertices (24 P_v), the targets'
     # barycentric + Euclidean positions (48 K), its own (52), and write idx/dist/start tangent (36 K), the force (24)
@@ -336,7 +336,7 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
                 "traffic": traffic,
                 "peak_source": pk_kind + " (MEASURED_PEAKS.json hbm_gbs, burst copy)" if pk_kind == "measured" else "fallback 6650 GB/s",
-                "kernel": "k_windows (stage 2: window propagation + queries + pair forces)",
+                "kernel": "k_windows_half (stage 2, two sources per warp: window propagation + queries + pair forces + half kick)",
                 "algorithmic_bytes_per_source": bytes_per_source, "kernel_ms_per_launch": win_ms_per_launch,
                 "kernel_share_of_step": max_over_ranks(float(np.sum(win_ms))) / inst_total_ms,
                 "ms_per_step_with_phase_events": inst_total_ms / args.steps,

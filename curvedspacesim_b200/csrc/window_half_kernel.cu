@@ -71,8 +71,9 @@ __device__ __forceinline__ double hitParam0(const v2& P, const v2& X, const v2& 
 {
     double den = cross2(Y - X, P);
     double mu = -cross2(X, P) * frcp(den);
-    if (!(mu == mu)) mu = 0.5;
-    return fmin(1.0, fmax(0.0, mu));
+    mu = mu == mu ? mu : 0.5; // plain compares and selects: fmin / fmax carry IEEE NaN handling that costs ~8 instructions each
+    mu = mu < 0.0 ? 0.0 : mu;
+    return mu > 1.0 ? 1.0 : mu;
 }
 
 // push up to one window per lane into the ring of the lane's own half; false when that ring would overflow
