@@ -28,7 +28,7 @@ NUM_COUNTERS = 32
 # every symbol include/css_api.h declares (tests check that the library exports all of them)
 API_SYMBOLS = [
     "css_create", "css_destroy", "css_last_error", "css_set_mesh", "css_mesh_info", "css_set_submeshing", "css_set_cell_domain",
-    "css_set_options", "css_set_boundary", "css_euclidean", "css_distance", "css_transport", "css_set_state", "css_get_state", "css_set_velocities",
+    "css_set_options", "css_set_boundary", "css_euclidean", "css_locate", "css_distance", "css_transport", "css_set_state", "css_get_state", "css_set_velocities",
     "css_set_forces", "css_find_neighbors", "css_get_neighbors", "css_compute_forces", "css_compute_energy", "css_compute_stress",
     "css_temperature", "css_move",
     "css_get_walk_flags", "css_step_nve", "css_step_nve_host", "css_step_gd", "css_nvt_init", "css_step_nvt", "css_nvt_state", "css_fire_init",
@@ -157,6 +157,14 @@ class Context:
         out = np.zeros((len(face), 3))
         self._ck(self.L.css_euclidean(self.h, len(face), _i(face), _d(bary), _d(out)))
         return out
+
+    def locate(self, xyz, clamp_tol=1e-14):
+        """simpleModel::R3PositionsToMeshPositions: closest mesh position (face, clamped barycentric weights) of points of R^3."""
+        xyz = np.ascontiguousarray(xyz, np.float64).reshape(-1, 3)
+        face = np.zeros(len(xyz), np.int32)
+        bary = np.zeros((len(xyz), 3))
+        self._ck(self.L.css_locate(self.h, len(xyz), _d(xyz), C.c_double(clamp_tol), _i(face), _d(bary)))
+        return face, bary
 
     def distance(self, src_face, src_bary, tgt_face, tgt_bary, threshold=1e20):
         sb = np.ascontiguousarray(src_bary, np.float64)

@@ -65,6 +65,11 @@ struct css_ctx {
     int winWpb = 2;
     unsigned char *d_records = nullptr, *d_recordsL = nullptr;
     double* d_spill = nullptr; // window spill stacks of the two-sources-per-warp kernel (allocated once)
+    // face grid of css_locate (built at the first call after css_set_mesh)
+    int *d_fgStart = nullptr, *d_fgFaces = nullptr;
+    double fgMin[3] = {0, 0, 0}, fgH = 0;
+    int fgN[3] = {0, 0, 0};
+    bool fgValid = false;
     size_t capRecords = 0, capRecordsL = 0;
     int numSMs = 148;
     // reductions / scratch
@@ -315,7 +320,7 @@ int css_destroy(css_ctx* ctx)
                     ctx->d_blockSums, ctx->d_fill,   ctx->d_tmpItems, ctx->d_items,  ctx->d_nbrCount, ctx->d_nbrIdx,  ctx->d_nbrDist,
                     ctx->d_nbrTs,  ctx->d_nbrTe,     ctx->d_work,    ctx->d_retry[0], ctx->d_retry[1], ctx->d_retry[2], ctx->d_gws,
                     ctx->d_partial, ctx->d_red,      ctx->d_counters, ctx->d_sendI,  ctx->d_sendD,    ctx->d_recvI,   ctx->d_recvD,
-                    ctx->d_redBuf,  ctx->d_geo,       ctx->d_records, ctx->d_recordsL, ctx->d_epoch, ctx->d_ticket, ctx->d_ipcBuf, ctx->d_spill};
+                    ctx->d_redBuf,  ctx->d_geo,       ctx->d_records, ctx->d_recordsL, ctx->d_epoch, ctx->d_ticket, ctx->d_ipcBuf, ctx->d_spill, ctx->d_fgStart, ctx->d_fgFaces};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (auto& e : ctx->ev)
@@ -420,6 +425,7 @@ int css_set_mesh(css_ctx* ctx, int nV, const double* xyz, int nF, const int32_t*
     CU(cudaMemcpy(ctx->d_saddle, sad.data(), nV, cudaMemcpyHostToDevice));
     ctx->nV = nV;
     ctx->nF = nF;
+    ctx->fgValid = false;
     ctx->nbrValid = false;
     ctx->nveCalls = 0;
     // last-resort tier: the whole mesh fits (local ids are 16 bit)
@@ -500,6 +506,103 @@ int css_euclidean(css_ctx* ctx, int n, const int32_t* face, const double* bary, 
     CU(cudaMemcpyAsync(xyz, dx, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, ctx->st));
     CU(cudaStreamSynchronize(ctx->st));
     cudaFree(df), cudaFree(db), cudaFree(dx);
+    return CSS_OK;
+}
+
+// simpleModel::R3PositionsToMeshPositions (src/models/simpleModel.cpp:136-154).  The reference builds a CGAL AABB tree per call;
+// here a uniform grid over the faces' bounding boxes is built once per mesh on the host (cell edge = twice the mean mesh edge,
+// at most 2^24 cells) and searched on the device shell by shell (exact_kernels.cu k_locate).
+static int buildFaceGrid(css_ctx* ctx)
+{
+    const int nV = ctx->nV, nF = ctx->nF;
+    std::vector<double4> hv(nV);
+    std::vector<int4> hc(nF);
+    CU(cudaMemcpy(hv.data(), ctx->d_vert, sizeof(double4) * nV, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(hc.data(), ctx->d_corner, sizeof(int4) * nF, cudaMemcpyDeviceToHost));
+    double mn[3] = {hv[0].x, hv[0].y, hv[0].z}, mx[3] = {hv[0].x, hv[0].y, hv[0].z};
+    for (int i = 1; i < nV; ++i) {
+        const double q[3] = {hv[i].x, hv[i].y, hv[i].z};
+        for (int d = 0; d < 3; ++d) mn[d] = std::min(mn[d], q[d]), mx[d] = std::max(mx[d], q[d]);
+    }
+    double esum = 0;
+    for (int f = 0; f < nF; ++f) {
+        const int c[3] = {hc[f].x, hc[f].y, hc[f].z};
+        for (int k = 0; k < 3; ++k) {
+            const double4 &a = hv[c[k]], &b = hv[c[(k + 1) % 3]];
+            esum += std::sqrt((a.x - b.x) * (a.x - b.x) + (a.y - b.y) * (a.y - b.y) + (a.z - b.z) * (a.z - b.z));
+        }
+    }
+    double ext = std::max(mx[0] - mn[0], std::max(mx[1] - mn[1], mx[2] - mn[2]));
+    double h = 2.0 * esum / (3.0 * nF);
+    if (!(h > 0)) h = ext > 0 ? ext : 1.0;
+    int n[3];
+    for (;;) {
+        double cells = 1;
+        for (int d = 0; d < 3; ++d) n[d] = (int)std::floor((mx[d] - mn[d]) / h) + 1, cells *= n[d];
+        if (cells <= (double)(1 << 24)) break;
+        h *= 1.26; // halves the cell count
+    }
+    const size_t ncell = (size_t)n[0] * n[1] * n[2];
+    auto cellRange = [&](int f, int lo[3], int hi[3]) {
+        const int c[3] = {hc[f].x, hc[f].y, hc[f].z};
+        for (int d = 0; d < 3; ++d) {
+            double a = 1e300, b = -1e300;
+            for (int k = 0; k < 3; ++k) {
+                const double q = d == 0 ? hv[c[k]].x : (d == 1 ? hv[c[k]].y : hv[c[k]].z);
+                a = std::min(a, q), b = std::max(b, q);
+            }
+            // one cell of slack on both sides: the device bins the query with its own rounding of the same division
+            lo[d] = std::max(0, (int)std::floor((a - mn[d]) / h) - 1), hi[d] = std::min(n[d] - 1, (int)std::floor((b - mn[d]) / h) + 1);
+        }
+    };
+    std::vector<int> start(ncell + 1, 0);
+    int lo[3], hi[3];
+    for (int f = 0; f < nF; ++f) {
+        cellRange(f, lo, hi);
+        for (int z = lo[2]; z <= hi[2]; ++z)
+            for (int y = lo[1]; y <= hi[1]; ++y)
+                for (int x = lo[0]; x <= hi[0]; ++x) start[((size_t)z * n[1] + y) * n[0] + x + 1]++;
+    }
+    for (size_t c = 0; c < ncell; ++c) start[c + 1] += start[c];
+    std::vector<int> faces((size_t)start[ncell]), fill(start.begin(), start.end() - 1);
+    for (int f = 0; f < nF; ++f) {
+        cellRange(f, lo, hi);
+        for (int z = lo[2]; z <= hi[2]; ++z)
+            for (int y = lo[1]; y <= hi[1]; ++y)
+                for (int x = lo[0]; x <= hi[0]; ++x) faces[fill[((size_t)z * n[1] + y) * n[0] + x]++] = f;
+    }
+    CU(regrow(ctx->d_fgStart, ncell + 1));
+    CU(regrow(ctx->d_fgFaces, faces.size()));
+    CU(cudaMemcpy(ctx->d_fgStart, start.data(), sizeof(int) * (ncell + 1), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ctx->d_fgFaces, faces.data(), sizeof(int) * faces.size(), cudaMemcpyHostToDevice));
+    for (int d = 0; d < 3; ++d) ctx->fgMin[d] = mn[d], ctx->fgN[d] = n[d];
+    ctx->fgH = h;
+    ctx->fgValid = true;
+    return CSS_OK;
+}
+
+int css_locate(css_ctx* ctx, int n, const double* xyz, double clampTol, int32_t* face, double* bary)
+{
+    if (!ctx || !ctx->nF) return fail(ctx, CSS_ESTATE, "mesh not set");
+    if (n < 0 || (n > 0 && (!xyz || !face || !bary))) return fail(ctx, CSS_EINVAL, "css_locate: bad arguments");
+    if (n == 0) return CSS_OK;
+    BIND();
+    if (!ctx->fgValid)
+        if (int rc = buildFaceGrid(ctx)) return rc;
+    int* df = nullptr;
+    double *dx = nullptr, *db = nullptr;
+    CU(cudaMalloc(&df, sizeof(int) * n));
+    CU(cudaMalloc(&dx, sizeof(double) * 3 * n));
+    CU(cudaMalloc(&db, sizeof(double) * 3 * n));
+    CU(cudaMemcpyAsync(dx, xyz, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, ctx->st));
+    launchLocate(ctx->st, meshDev(ctx), ctx->fgMin, ctx->fgH, ctx->fgN, ctx->d_fgStart, ctx->d_fgFaces, n, dx, clampTol, df, db);
+    ctx->hostKernels++;
+    CU(cudaMemcpyAsync(face, df, sizeof(int) * n, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaMemcpyAsync(bary, db, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    cudaFree(df), cudaFree(dx), cudaFree(db);
+    for (int i = 0; i < n; ++i)
+        if (face[i] < 0) return fail(ctx, CSS_EINVAL, "css_locate: point %d has no closest face (coordinates are not finite)", i);
     return CSS_OK;
 }
 

@@ -8,6 +8,7 @@
 //   k_walk          triangulatedMeshSpace::transportParticleAndVectors (:448-658), one thread per particle,
 //                   optionally fused with the velocity-Verlet first half step (velocityVerletNVE.cpp:14-21)
 //   k_axpy-type     updater arithmetic (src/updaters/*.cpp) and reductions
+//   k_locate        simpleModel::R3PositionsToMeshPositions (simpleModel.cpp:136-154): closest face + clamped weights
 #include "common.cuh"
 #include "kernels.h"
 
@@ -661,6 +662,147 @@ __global__ void k_stress_final(int nb, const double* __restrict__ partial, doubl
 }
 
 // ---------------------------------------------------------------------------------- host launchers
+// ---------------------------------------------------------------------------------------------------------------------
+// R^3 point -> mesh position: simpleModel::R3PositionsToMeshPositions (src/models/simpleModel.cpp:136-154), i.e.
+// PMP::locate_with_AABB_tree + simpleModel::clampBarycentricCoordinatesToFace (:114-134).  One thread per point.  The AABB
+// tree is replaced by a uniform grid over the faces' bounding boxes (built once per mesh, css_api.cu): the thread visits the
+// cells around its point shell by shell and stops when the next shell cannot hold anything closer.  The per-face arithmetic
+// (closest point by Voronoi region, squared distance, barycentric weights, snap, clamp) is the oracle's, operation for
+// operation, so face index and weights are bit-identical to the CPU restatement the tests check against; exact ties go to the lowest face index.
+struct FaceGrid {
+    double mn[3], h;
+    int n[3];
+    const int* cellStart; // [ncells + 1]
+    const int* cellFaces; // face ids, every face listed in each cell its bounding box overlaps
+};
+
+__device__ __forceinline__ d3 closestPointOnTriangle(const d3& p, const d3& a, const d3& b, const d3& c)
+{
+    const d3 ab = b - a, ac = c - a, ap = p - a;
+    const double d1 = dot(ab, ap), d2 = dot(ac, ap);
+    if (d1 <= 0.0 && d2 <= 0.0) return a;
+    const d3 bp = p - b;
+    const double d3_ = dot(ab, bp), d4 = dot(ac, bp);
+    if (d3_ >= 0.0 && d4 <= d3_) return b;
+    const double vc = d1 * d4 - d3_ * d2;
+    if (vc <= 0.0 && d1 >= 0.0 && d3_ <= 0.0) {
+        const double v = d1 / (d1 - d3_);
+        return a + v * ab;
+    }
+    const d3 cp = p - c;
+    const double d5 = dot(ab, cp), d6 = dot(ac, cp);
+    if (d6 >= 0.0 && d5 <= d6) return c;
+    const double vb = d5 * d2 - d1 * d6;
+    if (vb <= 0.0 && d2 >= 0.0 && d6 <= 0.0) {
+        const double w = d2 / (d2 - d6);
+        return a + w * ac;
+    }
+    const double va = d3_ * d6 - d5 * d4;
+    if (va <= 0.0 && (d4 - d3_) >= 0.0 && (d5 - d6) >= 0.0) {
+        const double w = (d4 - d3_) / ((d4 - d3_) + (d5 - d6));
+        return b + w * (c - b);
+    }
+    const double denom = 1.0 / (va + vb + vc);
+    const double v = vb * denom, w = vc * denom;
+    return (a + v * ab) + w * ac;
+}
+
+__device__ __forceinline__ void locateWeights(const d3& q, const d3& p0, const d3& p1, const d3& p2, double clampTol, double* out)
+{
+    const d3 v0 = p1 - p0, v1 = p2 - p0, v2 = q - p0;
+    const double d00 = dot(v0, v0), d01 = dot(v0, v1), d11 = dot(v1, v1), d20 = dot(v2, v0), d21 = dot(v2, v1);
+    const double den = d00 * d11 - d01 * d01;
+    const double v = (d11 * d20 - d01 * d21) / den, w = (d00 * d21 - d01 * d20) / den;
+    double co[3] = {(1.0 - v) - w, v, w};
+    if (co[0] < 0.0 || co[0] > 1.0 || co[1] < 0.0 || co[1] > 1.0 || co[2] < 0.0 || co[2] > 1.0) {
+        const double eps = 2.220446049250313e-16;
+        double residue = 0.0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            if (fabs(co[i]) <= eps) residue = residue + co[i], co[i] = 0.0;
+            else if (fabs(1.0 - co[i]) <= eps) residue = residue - (1.0 - co[i]), co[i] = 1.0;
+        }
+        bool dumped = false;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+            if (!dumped && co[i] != 0.0 && co[i] != 1.0) co[i] = co[i] + residue, dumped = true;
+    }
+    double w1 = co[0], w2 = co[1], w3 = co[2];
+    if (fabs(w1) < clampTol) w1 = clampTol;
+    if (fabs(w2) < clampTol) w2 = clampTol;
+    if (fabs(w3) < clampTol) w3 = clampTol;
+    w1 = w1 / ((w1 + w2) + w3);
+    w2 = w2 / ((w1 + w2) + w3);
+    w3 = w3 / ((w1 + w2) + w3);
+    out[0] = w1, out[1] = w2, out[2] = w3;
+}
+
+__global__ void __launch_bounds__(128) k_locate(MeshDev m, FaceGrid g, int n, const double* __restrict__ xyz, double clampTol,
+                                                int* __restrict__ face, double* __restrict__ bary)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const d3 p = ld3(xyz, i);
+    if (!(isfinite(p.x) && isfinite(p.y) && isfinite(p.z))) { // nothing is closest to such a point: reported by the host
+        face[i] = -1;
+        bary[3 * i] = bary[3 * i + 1] = bary[3 * i + 2] = 0.0;
+        return;
+    }
+    int c0[3];
+    {
+        const double q[3] = {p.x, p.y, p.z};
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            double t = floor((q[d] - g.mn[d]) / g.h);
+            t = t < 0.0 ? 0.0 : t;
+            c0[d] = min(g.n[d] - 1, (int)fmin(t, 2.0e9));
+        }
+    }
+    const int rmax = max(g.n[0], max(g.n[1], g.n[2]));
+    double best = __longlong_as_double(0x7ff0000000000000LL);
+    int bf = -1;
+    for (int r = 0; r <= rmax; ++r) {
+        const int x0 = max(0, c0[0] - r), x1 = min(g.n[0] - 1, c0[0] + r);
+        const int y0 = max(0, c0[1] - r), y1 = min(g.n[1] - 1, c0[1] + r);
+        const int z0 = max(0, c0[2] - r), z1 = min(g.n[2] - 1, c0[2] + r);
+        for (int z = z0; z <= z1; ++z)
+            for (int y = y0; y <= y1; ++y) {
+                const bool edge = abs(z - c0[2]) == r || abs(y - c0[1]) == r;
+                for (int x = x0; x <= x1; x += (edge || r == 0) ? 1 : max(1, x1 - x0)) { // interior rows: only the two end cells
+                    if (!edge && abs(x - c0[0]) != r) continue;
+                    const size_t cell = ((size_t)z * g.n[1] + y) * g.n[0] + x;
+                    for (int k = g.cellStart[cell], ke = g.cellStart[cell + 1]; k < ke; ++k) {
+                        const int f = g.cellFaces[k];
+                        const int4 c = __ldg(m.corner + f);
+                        const d3 q = closestPointOnTriangle(p, ldvert(m, c.x), ldvert(m, c.y), ldvert(m, c.z));
+                        const double d2 = sqlen(p - q);
+                        if (d2 < best || (d2 == best && f < bf)) best = d2, bf = f;
+                    }
+                }
+            }
+        // every cell of shell r + 1 is at least r h away from a point inside (or clamped into) the centre cell
+        const double lb = (double)r * g.h;
+        if (bf >= 0 && best < lb * lb * (1.0 - 1e-9)) break;
+    }
+    face[i] = bf;
+    if (bf >= 0) {
+        const int4 c = __ldg(m.corner + bf);
+        const d3 p0 = ldvert(m, c.x), p1 = ldvert(m, c.y), p2 = ldvert(m, c.z);
+        locateWeights(closestPointOnTriangle(p, p0, p1, p2), p0, p1, p2, clampTol, bary + 3 * i);
+    } else
+        bary[3 * i] = bary[3 * i + 1] = bary[3 * i + 2] = 0.0;
+}
+
+void launchLocate(cudaStream_t st, const MeshDev& m, const double gmn[3], double h, const int gn[3], const int* cellStart, const int* cellFaces,
+                  int n, const double* xyz, double clampTol, int* face, double* bary)
+{
+    if (n <= 0) return;
+    FaceGrid g;
+    for (int d = 0; d < 3; ++d) g.mn[d] = gmn[d], g.n[d] = gn[d];
+    g.h = h, g.cellStart = cellStart, g.cellFaces = cellFaces;
+    k_locate<<<(n + 127) / 128, 128, 0, st>>>(m, g, n, xyz, clampTol, face, bary);
+}
+
 static inline int gridFor(int n, int b) { return (n + b - 1) / b; }
 
 void launchEuclidCell(cudaStream_t st, const MeshDev& m, const CellGrid& g, int n, const int* face, const double* bary, double* eucl,

@@ -197,6 +197,8 @@ void launchWalk(cudaStream_t st, const MeshDev& m, int n, int minIdx, int* face,
                 int transportForce, int transportVelocity, int mode, double dt, int* flags, unsigned long long* counters, const PeerWin& pw);
 void launchTransportGeneric(cudaStream_t st, const MeshDev& m, int n, int* face, double* bary, double* disp, int nVec, double* vecs,
                             int* flags);
+void launchLocate(cudaStream_t st, const MeshDev& m, const double gmn[3], double h, const int gn[3], const int* cellStart, const int* cellFaces,
+                  int n, const double* xyz, double clampTol, int* face, double* bary);
 void launchAxpy(cudaStream_t st, int op, int n, double a, double b, double* vel, const double* frc, double* disp);
 void launchReduce(cudaStream_t st, int n, const double* vel, const double* frc, double* partial, double* out);
 void launchEnergy(cudaStream_t st, int nLocal, int kmax, const int* nbrCount, const double* nbrDist, ForceParams fp, double* partial,

@@ -171,6 +171,12 @@ public:
                           vector<vector3>& endPathTangent, double distanceThreshold) = 0;
     virtual void meshPositionToEuclideanLocation(vector<meshPosition>& p1, vector<double3>& result) = 0;
     virtual void meshPositionToEuclideanLocation(vector<meshPosition>& p1, vector<meshPosition>& result) = 0;
+    //! closest mesh positions of points of R^3 (the mesh half of simpleModel::R3PositionsToMeshPositions, simpleModel.cpp:136-154)
+    virtual void R3PositionsToMeshPositions(vector<point3>& r3positions, vector<meshPosition>& simPositions, double clampTolerance)
+        {
+        (void)r3positions, (void)simPositions, (void)clampTolerance;
+        ERRORERROR("this space cannot locate R3 positions");
+        }
     virtual double getArea() = 0;
     bool positionsAreEuclidean = true;
     virtual void randomPosition(meshPosition& p, noiseSource& noise) = 0;
@@ -278,6 +284,17 @@ public:
             startPathTangent[i] = vector3(ts[3 * i], ts[3 * i + 1], ts[3 * i + 2]);
             endPathTangent[i] = vector3(te[3 * i], te[3 * i + 1], te[3 * i + 2]);
             }
+        }
+    //! PMP::locate_with_AABB_tree + simpleModel::clampBarycentricCoordinatesToFace on the device (css_locate)
+    virtual void R3PositionsToMeshPositions(vector<point3>& r3positions, vector<meshPosition>& simPositions, double clampTolerance)
+        {
+        size_t n = r3positions.size();
+        vector<double> xyz(3 * n), b(3 * n);
+        vector<int32_t> f(n);
+        for (size_t i = 0; i < n; ++i)
+            for (int k = 0; k < 3; ++k) xyz[3 * i + k] = r3positions[i][k];
+        if (n) cssHost::check(ctx(), css_locate(ctx(), (int)n, xyz.data(), clampTolerance, f.data(), b.data()), "css_locate");
+        for (size_t i = 0; i < n; ++i) simPositions.push_back(meshPosition(point3(b[3 * i], b[3 * i + 1], b[3 * i + 2]), f[i]));
         }
     virtual void meshPositionToEuclideanLocation(vector<meshPosition>& p1, vector<double3>& result)
         {
@@ -436,6 +453,42 @@ public:
         for (int pp = 0; pp < N; ++pp) space->randomPosition(positions[pp], noise);
         positionsChanged();
         }
+    //! simpleModel::R3PositionsToMeshPositions (simpleModel.cpp:136-154); the mesh is the one the space was loaded with
+    virtual void R3PositionsToMeshPositions(vector<point3> r3positions, vector<meshPosition>& simPositions)
+        {
+        space->R3PositionsToMeshPositions(r3positions, simPositions, clampTolerance);
+        }
+    //! simpleModel::setMeshPositionsFromR3File (simpleModel.cpp:156-203): one "x,y,z" per line, malformed lines are skipped
+    virtual void setMeshPositionsFromR3File(string filename)
+        {
+        std::ifstream file(filename);
+        if (!file.is_open()) std::cerr << "Failed to open position file." << std::endl;
+        vector<point3> points;
+        string line;
+        while (std::getline(file, line))
+            {
+            std::stringstream ss(line);
+            string entry;
+            vector<double> entries;
+            while (std::getline(ss, entry, ','))
+                {
+                double value = 0;
+                std::istringstream(entry) >> value;
+                entries.push_back(value);
+                }
+            if (entries.size() != 3)
+                {
+                std::cerr << "Error: input file had invalid number of entries on a line. Skipping line." << std::endl;
+                continue;
+                }
+            points.push_back(point3(entries[0], entries[1], entries[2]));
+            }
+        vector<meshPosition> simPositions;
+        simPositions.reserve(points.size());
+        R3PositionsToMeshPositions(points, simPositions);
+        setParticlePositions(simPositions);
+        }
+    double clampTolerance = 0.00000000000001; // simpleModel.h:101
     virtual void setMaxwellBoltzmannVelocities(noiseSource& noise, double T)
         {
         for (int pp = 0; pp < N; ++pp)

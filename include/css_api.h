@@ -9,6 +9,8 @@
  *   css_set_boundary        openMeshSpace / absorbingOpenMeshSpace / tangentialOpenMeshSpace (src/models/openMeshSpace.cpp:114-238)
  *   css_set_cell_domain     cellListNeighborStructure ctor (src/utility/cellListNeighborStructure.cpp:4-20)
  *   css_euclidean           triangulatedMeshSpace::meshPositionToEuclideanLocation (.cpp:82-106)
+ *   css_locate              simpleModel::R3PositionsToMeshPositions + clampBarycentricCoordinatesToFace
+ *                           (src/models/simpleModel.cpp:114-154: PMP::locate_with_AABB_tree, then the clamp)
  *   css_distance            baseSpace::distance / triangulatedMeshSpace::distance (src/models/baseSpace.h:36-39,
  *                           triangulatedMeshSpace.cpp:155-238)
  *   css_transport           baseSpace::transportParticleAndVectors / displaceParticle (baseSpace.h:29-32,
@@ -106,6 +108,9 @@ int css_set_options(css_ctx* ctx, int useCellList, int wantEndTangents);
 
 /* ---- per-call API parity with baseSpace ---- */
 int css_euclidean(css_ctx* ctx, int n, const int32_t* face, const double* bary, double* xyz);
+/* closest mesh position of n points of R^3: face index and clamped barycentric weights (clampTol = simpleModel::clampTolerance,
+ * 1e-14 in the reference); among faces at exactly the same distance the lowest index wins */
+int css_locate(css_ctx* ctx, int n, const double* xyz, double clampTol, int32_t* face, double* bary);
 int css_distance(css_ctx* ctx, int srcFace, const double srcBary[3], int K, const int32_t* tgtFace, const double* tgtBary,
                  double threshold, double* dist, double* startTan, double* endTan);
 /* vecs is [n][nVec][3] (may be NULL when nVec==0); flags may be NULL */

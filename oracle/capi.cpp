@@ -1,5 +1,6 @@
 // ORACLE (test infrastructure only): C entry points so tests/ and bench.py's cpu_baseline leg can
 // drive the CPU restatement through ctypes.  Nothing in curvedspacesim_b200/ may link or call this.
+#include "locate.hpp"
 #include "sim.hpp"
 #include <chrono>
 #include <cstring>
@@ -44,6 +45,13 @@ ORC_API void orc_get_saddle(void* h, char* out)
 {
     Sim* s = (Sim*)h;
     std::memcpy(out, s->saddle.data(), s->saddle.size());
+}
+
+// simpleModel::R3PositionsToMeshPositions (src/models/simpleModel.cpp:136-154), brute force over the faces
+ORC_API void orc_locate(void* h, int n, const double* xyz, double clampTol, int* face, double* bary)
+{
+    Sim* s = (Sim*)h;
+    for (int i = 0; i < n; ++i) locatePoint(s->mesh, V3{xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]}, clampTol, face[i], bary + 3 * i);
 }
 
 ORC_API void orc_set_submeshing(void* h, int enabled, double maxDist)

@@ -125,6 +125,14 @@ class Oracle:
         self.L.orc_euclidean(self.h, len(face), _i(face), _d(bary), _d(out))
         return out
 
+    def locate(self, xyz, clamp_tol=1e-14):
+        """simpleModel::R3PositionsToMeshPositions (brute force over the faces)."""
+        xyz = np.ascontiguousarray(xyz, np.float64).reshape(-1, 3)
+        face = np.zeros(len(xyz), np.int32)
+        bary = np.zeros((len(xyz), 3))
+        self.L.orc_locate(self.h, len(xyz), _d(xyz), C.c_double(clamp_tol), _i(face), _d(bary))
+        return face, bary
+
     def candidates(self, rng):
         off = np.zeros(self.N + 1, np.int32)
         maxd = np.zeros(self.N)

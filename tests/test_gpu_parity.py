@@ -230,6 +230,38 @@ def test_distance_per_call_global_and_submeshed(gpu_ctx_factory):
     assert ctx.counters()["overflow"] == 0
 
 
+@pytest.mark.parametrize("name", ["torus60x24", "icosphere16"])
+def test_locate_r3_positions_is_bit_exact(name, gpu_ctx_factory):
+    """css_locate = simpleModel::R3PositionsToMeshPositions (simpleModel.cpp:136-154): the grid search on the device returns the
+    face and the clamped weights of the oracle's brute-force scan bit for bit (exact ties: lowest face index)."""
+    V, F = _mesh(name)
+    corners = meshes.reference_corners(F)
+    orc = Oracle(V, corners)
+    ctx = gpu_ctx_factory()
+    ctx.set_mesh(V, corners)
+    rng = np.random.default_rng(3)
+    face0, bary0 = random_positions(len(F), 2000, rng)
+    on = orc.euclidean(face0, bary0)
+    ext = float(np.abs(V).max())
+    P = np.concatenate([on + 1e-9 * rng.standard_normal((2000, 3)),        # slightly off the surface (the reference's use)
+                        on + 0.05 * ext * rng.standard_normal((2000, 3)),  # clearly off
+                        4.0 * ext * rng.standard_normal((200, 3)),         # far away, outside the grid
+                        V[:200],                                           # on vertices: distance-0 ties between faces
+                        0.5 * (V[corners[:200, 1]] + V[corners[:200, 2]]), # on edges
+                        np.zeros((1, 3))])                                 # deep inside
+    of, ob = orc.locate(P)
+    gf, gb = ctx.locate(P)
+    assert np.array_equal(of, gf)
+    assert np.array_equal(ob, gb)
+    assert np.array_equal(gf[:2000], face0)
+    gf2, gb2 = ctx.locate(P[:10], clamp_tol=1e-6)                           # the tolerance is the caller's
+    of2, ob2 = orc.locate(P[:10], clamp_tol=1e-6)
+    assert np.array_equal(of2, gf2) and np.array_equal(ob2, gb2)
+    assert ctx.locate(np.zeros((0, 3)))[0].shape == (0,)
+    with pytest.raises(binding.CssError):
+        ctx.locate(np.array([[np.nan, 0.0, 0.0]]))
+
+
 def test_disconnected_sentinel_and_unreachable(gpu_ctx_factory):
     V1, F1 = meshes.plane_grid(2, 2)
     V = np.concatenate([V1, V1 + [3.0, 0, 0]])

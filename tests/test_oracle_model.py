@@ -443,3 +443,66 @@ def test_stress_and_temperature_match_a_literal_numpy_evaluation():
         assert len(idx) > N and np.max(np.abs(S - ref)) < 1e-12 * np.abs(ref).max()
         assert abs(np.trace(S)) > 0
     assert abs(orc.temperature() - (vel ** 2).sum() / (2 * N)) < 1e-14
+
+
+# --------------------------------------------------------------------------------- R^3 -> mesh positions
+def _closest_point_distances_numpy(P, V, corners):
+    """Independent restatement (no Voronoi regions): the closest point of a triangle is the projection onto its plane when
+    that lies inside, otherwise the closest point of one of its three edges.  Returns [n_points, n_faces] distances."""
+    a, b, c = V[corners[:, 0]], V[corners[:, 1]], V[corners[:, 2]]
+    out = np.empty((len(P), len(corners)))
+    nrm = np.cross(b - a, c - a)
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+
+    def seg(p, s0, s1):
+        d = s1 - s0
+        t = np.clip(np.einsum("ij,ij->i", p - s0, d) / np.einsum("ij,ij->i", d, d), 0, 1)
+        return np.linalg.norm(p - (s0 + t[:, None] * d), axis=1)
+
+    for i, p in enumerate(P):
+        pp = np.broadcast_to(p, a.shape)
+        h = np.einsum("ij,ij->i", pp - a, nrm)
+        q = pp - h[:, None] * nrm
+        inside = np.ones(len(a), bool)
+        for s0, s1 in ((a, b), (b, c), (c, a)):
+            inside &= np.einsum("ij,ij->i", np.cross(s1 - s0, q - s0), nrm) >= 0
+        de = np.minimum(np.minimum(seg(pp, a, b), seg(pp, b, c)), seg(pp, c, a))
+        out[i] = np.where(inside, np.abs(h), de)
+    return out
+
+
+def test_locate_finds_the_closest_face_and_clamps_like_the_reference():
+    # simpleModel::R3PositionsToMeshPositions (simpleModel.cpp:136-154) + clampBarycentricCoordinatesToFace (:114-134)
+    V, F = meshes.torus(24, 12, R=3.0, r=1.0, jitter=0.2, seed=5)
+    corners = meshes.reference_corners(F)
+    orc = Oracle(V, corners)
+    rng = np.random.default_rng(11)
+    face0, bary0 = random_positions(len(F), 150, rng)
+    on = orc.euclidean(face0, bary0)
+    nrm = np.cross(V[corners[face0, 1]] - V[corners[face0, 0]], V[corners[face0, 2]] - V[corners[face0, 0]])
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    slightly_off = on + 1e-9 * rng.standard_normal((150, 1)) * nrm          # what the reference expects as input
+    far = 6.0 * rng.standard_normal((40, 3))                                 # anywhere, incl. outside the bounding box
+    P = np.concatenate([slightly_off, far, V[:20], 0.5 * (V[corners[:10, 0]] + V[corners[:10, 1]])])
+    f, b = orc.locate(P)
+    D = _closest_point_distances_numpy(P, V, corners)
+    x = orc.euclidean(f, b)
+    d_found = np.linalg.norm(P - x, axis=1)
+    assert np.all(np.abs(d_found - D.min(axis=1)) < 1e-10)                   # nothing on the mesh is closer
+    assert np.all(np.abs(D[np.arange(len(P)), f] - D.min(axis=1)) < 1e-10)   # and the face returned attains it
+    assert np.array_equal(f[:150], face0)                                    # interior points come back to their face
+    assert np.max(np.abs(b[:150] - bary0)) < 1e-7
+    # weights: all >= the clamp tolerance, and the reference's sequential renormalisation (sum == 1 only to ~1e-14)
+    assert b.min() >= 1e-14 * (1 - 1e-12) and np.max(np.abs(b.sum(axis=1) - 1)) < 1e-12
+    # a mesh vertex lies on several faces at distance 0: the lowest face index wins (documented tie rule)
+    for k in range(20):
+        incident = np.where((corners == k).any(axis=1))[0]
+        assert f[190 + k] == incident.min()
+    # literal clamp arithmetic on a corner point: weights (1, 0, 0) -> (1, tol, tol) divided one after the other
+    fv, bv = orc.locate(V[corners[7, 0]][None, :])
+    w = [1.0, 1e-14, 1e-14] if fv[0] == 7 else None
+    if w is not None:
+        w[0] = w[0] / (w[0] + w[1] + w[2])
+        w[1] = w[1] / (w[0] + w[1] + w[2])
+        w[2] = w[2] / (w[0] + w[1] + w[2])
+        assert np.array_equal(bv[0], np.array(w))
