@@ -19,6 +19,7 @@
 // Results are order-independent minima with the lowest lane winning ties, so runs are bitwise repeatable and the values
 // agree with the one-warp kernel and the oracle to round-off (~1e-15).
 #include "window_common.cuh"
+#include <cuda_pipeline.h>
 
 namespace css {
 
@@ -35,6 +36,7 @@ template <class T> struct HalfSmem { // per-SOURCE workspace, two per warp (alwa
     static constexpr int F = T::MAXF, V = T::MAXV, K = T::MAXK, R = T::RING;
     static constexpr bool lean = true;
     using mask_t = typename MaskOf<(K <= 8 ? 8 : 16)>::type;
+    static_assert(T::OFF_VELIG % 4 == 0 && V % 4 == 0, "velig is copied in 4-byte pieces");
     static_assert(K <= 16 && R >= 32, "one target per lane of the half; a pass pushes up to 16 children");
     int gface[F], gvert[V];
     double D[V + 1], dirx[V], diry[V]; // D[V] = 0: the sigma of the real source
@@ -54,17 +56,20 @@ template <class T> struct HalfSmem { // per-SOURCE workspace, two per warp (alwa
     uchar4 fadj[F];
     alignas(4) mask_t tmask[F]; // targets lying in each face (bit t)
     alignas(4) unsigned char tFace[K];
-    unsigned char velig[V];
+    alignas(4) unsigned char velig[V];
     unsigned char vdirty[V];
     unsigned char rpsv[R];
 };
 
-// one lane refreshes the pruning bound of a source after its target distances changed
-template <class W> __device__ __forceinline__ void updateBound(W& w, int K)
+// refresh the pruning bound of both sources of the warp after target distances changed: max over the half's targets of the
+// best distance known, fp32 rounded up (non-negative floats order like their bit patterns; +inf stays +inf).  Called by the
+// whole warp from warp-uniform code; the xor offsets stay inside a half.
+template <class W> __device__ __forceinline__ void updateBound(W& w, int hl, int K)
 {
-    unsigned u = 0;
-    for (int t = 0; t < K; ++t) u = max(u, __float_as_uint(__double2float_ru(w.tbest[t])));
-    w.ub = __uint_as_float(u) * (1.f + 2e-5f);
+    unsigned u = hl < K ? __float_as_uint(__double2float_ru(w.tbest[hl])) : 0u;
+#pragma unroll
+    for (int o = 8; o; o >>= 1) u = max(u, __shfl_xor_sync(FULL, u, o));
+    if (hl == 0) w.ub = __uint_as_float(u) * (1.f + 2e-5f);
 }
 // parameter on X + mu (Y - X) hit by the ray from the origin through P, clamped to the segment
 __device__ __forceinline__ double hitParam0(const v2& P, const v2& X, const v2& Y)
@@ -136,8 +141,8 @@ template <class T> __global__ void __launch_bounds__(32 * CSS_HALF_WPB, CSS_HALF
                     done = true;
                     break;
                 }
-                li = a.srcList ? a.srcList[s] : s;
                 const int4 hdr = *reinterpret_cast<const int4*>(a.records + (size_t)s * T::BYTES);
+                li = a.srcList ? a.srcList[s] : s;
                 if (hdr.w) continue; // overflowed in stage 1: the retry tiers own this source
                 if (hdr.z == 0) {    // no candidates: nothing to propagate
                     if (hl == 0) {
@@ -166,20 +171,23 @@ template <class T> __global__ void __launch_bounds__(32 * CSS_HALF_WPB, CSS_HALF
         d3 sp{0, 0, 0};
         double sb0 = 1, sb1 = 0, sb2 = 0;
         if (live) {
+            // the record sections go global -> shared as asynchronous copies (cp.async): all of them are in flight at once and
+            // overlap the dependent target fetches below, instead of one L2 round trip per section
             const int4* src = reinterpret_cast<const int4*>(rec + T::OFF_FVERT); // fvert | fadj are contiguous in the record and here
             int4* dst = reinterpret_cast<int4*>(w.fvert);
-            for (int q = hl; q * 4 < nF; q += 16) dst[q] = src[q], dst[q + T::MAXF / 4] = src[q + T::MAXF / 4];
+            for (int q = hl; q * 4 < nF; q += 16) {
+                __pipeline_memcpy_async(dst + q, src + q, 16);
+                __pipeline_memcpy_async(dst + q + T::MAXF / 4, src + q + T::MAXF / 4, 16);
+            }
             const int* gface = reinterpret_cast<const int*>(rec + T::OFF_GFACE);
-            for (int f = hl; f < nF; f += 16) w.gface[f] = gface[f];
+            for (int f = hl; f < nF; f += 16) __pipeline_memcpy_async(w.gface + f, gface + f, 4);
+            const int* gvert = reinterpret_cast<const int*>(rec + T::OFF_GVERT);
+            for (int v = hl; v < nV; v += 16) __pipeline_memcpy_async(w.gvert + v, gvert + v, 4);
+            for (int q = hl; q * 4 < nV; q += 16) __pipeline_memcpy_async(w.velig + 4 * q, rec + T::OFF_VELIG + 4 * q, 4);
+            __pipeline_commit();
             unsigned* tmw = reinterpret_cast<unsigned*>(w.tmask);
             for (int q = hl; q * 4 < nF * (int)sizeof(typename W::mask_t); q += 16) tmw[q] = 0;
-            const int* gvert = reinterpret_cast<const int*>(rec + T::OFF_GVERT);
-            for (int v = hl; v < nV; v += 16) {
-                w.gvert[v] = gvert[v];
-                w.D[v] = dinf();
-                w.velig[v] = rec[T::OFF_VELIG + v];
-                w.vdirty[v] = 0;
-            }
+            for (int v = hl; v < nV; v += 16) w.D[v] = dinf(), w.vdirty[v] = 0;
             if (hl < K) {
                 int j = reinterpret_cast<const int*>(rec + T::OFF_TIDX)[base + hl];
                 w.tIdx[hl] = j;
@@ -193,6 +201,7 @@ template <class T> __global__ void __launch_bounds__(32 * CSS_HALF_WPB, CSS_HALF
             }
             sp = d3{a.eucl[3 * gi], a.eucl[3 * gi + 1], a.eucl[3 * gi + 2]};
             sb0 = a.bary[3 * gi], sb1 = a.bary[3 * gi + 1], sb2 = a.bary[3 * gi + 2];
+            __pipeline_wait_prior(0);
         }
         __syncwarp();
 
@@ -273,7 +282,7 @@ template <class T> __global__ void __launch_bounds__(32 * CSS_HALF_WPB, CSS_HALF
             pushHalf(w, hl, hbase, head, tail, valid, A, B, 0.0, 1.0, meta, NOPSV, cg); // 3 <= ring
         }
         __syncwarp();
-        if (hl == 0) updateBound(w, K);
+        updateBound(w, hl, K);
         __syncwarp();
 
         unsigned nWin = 0, nPs = 0;
@@ -373,7 +382,7 @@ template <class T> __global__ void __launch_bounds__(32 * CSS_HALF_WPB, CSS_HALF
                         __syncwarp();
                         bool win = improvedT && wp.tbest[myT] == cand;
                         if (win) atomicMin(&wp.towner[myT], lane);
-                        if (hl == 0) updateBound(w, K);
+                        updateBound(w, hl, K);
                         __syncwarp();
                         if (win && wp.towner[myT] == lane) {
                             if (psv == NOPSV) wp.tsx[myT] = dT.x, wp.tsy[myT] = dT.y;
@@ -494,7 +503,7 @@ template <class T> __global__ void __launch_bounds__(32 * CSS_HALF_WPB, CSS_HALF
                 }
             }
             __syncwarp();
-            if (hl == 0) updateBound(w, K);
+            updateBound(w, hl, K);
             __syncwarp();
             const float fUb = w.ub;
             // A vertex v can lie on a shortest path to target t only if D[v] + |x_v - x_t| (Euclidean lower bound of the
