@@ -43,7 +43,7 @@ struct css_ctx {
     CellGrid grid{};
     double gridRange = -1;
     int nCells = 0, capCells = 0;
-    int *d_cellOf = nullptr, *d_cellCount = nullptr, *d_cellStart = nullptr, *d_blockSums = nullptr, *d_fill = nullptr, *d_tmpItems = nullptr,
+    int *d_cellOf = nullptr, *d_cellCount = nullptr, *d_cellStart = nullptr, *d_blockSums = nullptr, *d_fill = nullptr /* (unused) */, *d_cellSlot = nullptr, *d_tmpItems = nullptr,
         *d_items = nullptr;
     // neighbours (fixed stride kmax)
     int kmax = 32, capNbr = 0;
@@ -317,7 +317,7 @@ int css_destroy(css_ctx* ctx)
     if (ctx->comm) ncclCommDestroy(ctx->comm);
     void* ptrs[] = {ctx->d_vert,   ctx->d_corner,    ctx->d_adj,     ctx->d_saddle,  ctx->d_face,     ctx->d_bary,    ctx->d_eucl,
                     ctx->d_vel,    ctx->d_frc,       ctx->d_disp,    ctx->d_walkFlags, ctx->d_cellOf, ctx->d_cellCount, ctx->d_cellStart,
-                    ctx->d_blockSums, ctx->d_fill,   ctx->d_tmpItems, ctx->d_items,  ctx->d_nbrCount, ctx->d_nbrIdx,  ctx->d_nbrDist,
+                    ctx->d_blockSums, ctx->d_fill,   ctx->d_cellSlot, ctx->d_tmpItems, ctx->d_items,  ctx->d_nbrCount, ctx->d_nbrIdx,  ctx->d_nbrDist,
                     ctx->d_nbrTs,  ctx->d_nbrTe,     ctx->d_work,    ctx->d_retry[0], ctx->d_retry[1], ctx->d_retry[2], ctx->d_gws,
                     ctx->d_partial, ctx->d_red,      ctx->d_counters, ctx->d_sendI,  ctx->d_sendD,    ctx->d_recvI,   ctx->d_recvD,
                     ctx->d_redBuf,  ctx->d_geo,       ctx->d_records, ctx->d_recordsL, ctx->d_epoch, ctx->d_ticket, ctx->d_ipcBuf, ctx->d_spill, ctx->d_fgStart, ctx->d_fgFaces};
@@ -501,7 +501,7 @@ int css_euclidean(css_ctx* ctx, int n, const int32_t* face, const double* bary, 
     CU(cudaMalloc(&dx, sizeof(double) * 3 * n));
     CU(cudaMemcpyAsync(df, face, sizeof(int) * n, cudaMemcpyHostToDevice, ctx->st));
     CU(cudaMemcpyAsync(db, bary, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, ctx->st));
-    launchEuclidCell(ctx->st, meshDev(ctx), ctx->grid, n, df, db, dx, nullptr, nullptr);
+    launchEuclidCell(ctx->st, meshDev(ctx), ctx->grid, n, df, db, dx, nullptr, nullptr, nullptr);
     ctx->hostKernels++;
     CU(cudaMemcpyAsync(xyz, dx, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, ctx->st));
     CU(cudaStreamSynchronize(ctx->st));
@@ -683,7 +683,7 @@ static int runGeodesicTiers(css_ctx* ctx, GeoArgs a, int nSrc)
         }
         PatchArgs p{};
         p.m = a.m, p.grid = a.grid, p.nLocal = a.nLocal, p.minIdx = a.minIdx;
-        p.face = a.face, p.eucl = a.eucl, p.cellStart = a.cellStart, p.cellItems = a.cellItems;
+        p.face = a.face, p.eucl = a.eucl, p.cellStart = a.cellStart, p.cellCount = a.cellCount, p.cellItems = a.cellItems;
         p.submeshing = a.submeshing, p.maxDist = a.maxDist, p.kmax = a.kmax;
         p.counters = ctx->d_counters;
         WinArgs w{};
@@ -807,6 +807,7 @@ static int ensureParticles(css_ctx* ctx, int nLocal, int nTotal)
         CU(regrow(ctx->d_bary, 3 * (size_t)nTotal));
         CU(regrow(ctx->d_eucl, 3 * (size_t)nTotal));
         CU(regrow(ctx->d_cellOf, nTotal));
+        CU(regrow(ctx->d_cellSlot, nTotal));
         CU(regrow(ctx->d_tmpItems, nTotal));
         CU(regrow(ctx->d_items, nTotal));
         ctx->capTotal = nTotal;
@@ -908,8 +909,6 @@ static int setupGrid(css_ctx* ctx, double range)
     if (ctx->nCells > ctx->capCells) {
         CU(regrow(ctx->d_cellCount, (size_t)ctx->nCells + 1));
         CU(regrow(ctx->d_cellStart, (size_t)ctx->nCells + 1));
-        CU(regrow(ctx->d_fill, (size_t)ctx->nCells + 1));
-        CU(regrow(ctx->d_blockSums, (size_t)scanBlocks(ctx->nCells) + 1));
         ctx->capCells = ctx->nCells;
     }
     return CSS_OK;
@@ -925,12 +924,12 @@ static int findNeighborsImpl(css_ctx* ctx, double range, int forceMode, ForcePar
     if (ctx->useCellList) {
         if ((rc = setupGrid(ctx, range))) return rc;
         CU(cudaMemsetAsync(ctx->d_cellCount, 0, sizeof(int) * ((size_t)ctx->nCells + 1), ctx->st));
-        launchEuclidCell(ctx->st, m, ctx->grid, ctx->nTotal, ctx->d_face, ctx->d_bary, ctx->d_eucl, ctx->d_cellOf, ctx->d_cellCount);
-        launchCellBuild(ctx->st, ctx->nTotal, ctx->nCells, ctx->d_cellOf, ctx->d_cellCount, ctx->d_cellStart, ctx->d_blockSums, ctx->d_fill,
-                        ctx->d_tmpItems, ctx->d_items);
-        ctx->hostKernels += 6;
+        launchEuclidCell(ctx->st, m, ctx->grid, ctx->nTotal, ctx->d_face, ctx->d_bary, ctx->d_eucl, ctx->d_cellOf, ctx->d_cellCount, ctx->d_cellSlot);
+        launchCellBuild(ctx->st, ctx->nTotal, ctx->nCells, ctx->d_cellOf, ctx->d_cellSlot, ctx->d_cellCount, ctx->d_cellStart, ctx->d_tmpItems,
+                        ctx->d_items);
+        ctx->hostKernels += 4;
     } else {
-        launchEuclidCell(ctx->st, m, ctx->grid, ctx->nTotal, ctx->d_face, ctx->d_bary, ctx->d_eucl, nullptr, nullptr);
+        launchEuclidCell(ctx->st, m, ctx->grid, ctx->nTotal, ctx->d_face, ctx->d_bary, ctx->d_eucl, nullptr, nullptr, nullptr);
         ctx->hostKernels += 1;
         if (ctx->nTotal - 1 > ctx->kmax) {
             ctx->kmax = ctx->nTotal - 1;
@@ -945,6 +944,7 @@ static int findNeighborsImpl(css_ctx* ctx, double range, int forceMode, ForcePar
     a.nTotal = ctx->nTotal, a.nLocal = ctx->nLocal, a.minIdx = ctx->minIdx;
     a.face = ctx->d_face, a.bary = ctx->d_bary, a.eucl = ctx->d_eucl;
     a.cellStart = ctx->useCellList ? ctx->d_cellStart : nullptr;
+    a.cellCount = ctx->d_cellCount;
     a.cellItems = ctx->d_items;
     a.submeshing = ctx->submeshing, a.maxDist = ctx->maxDist;
     a.xK = -1;
@@ -1213,7 +1213,7 @@ static uint64_t nveGraphKey(css_ctx* ctx, const ForceParams& fp, double range, d
     MIX(ctx->nLocal), MIX(ctx->nTotal), MIX(ctx->minIdx), MIX(ctx->kmax), MIX(ctx->nranks), MIX(ctx->timing), MIX(ctx->submeshing),
         MIX(ctx->maxDist), MIX(ctx->boundaryMode), MIX(ctx->useCellList), MIX(ctx->wantEnd), MIX(ctx->twoStage), MIX(ctx->winWpb), MIX(ctx->winLean), MIX(ctx->winHalf), MIX(ctx->grid), MIX(ctx->nCells);
     void* ptrs[] = {ctx->d_vert, ctx->d_corner, ctx->d_adj, ctx->d_geo, ctx->d_saddle, ctx->d_face, ctx->d_bary, ctx->d_eucl, ctx->d_vel, ctx->d_frc,
-                    ctx->d_disp, ctx->d_walkFlags, ctx->d_cellOf, ctx->d_cellCount, ctx->d_cellStart, ctx->d_blockSums, ctx->d_fill, ctx->d_tmpItems,
+                    ctx->d_disp, ctx->d_walkFlags, ctx->d_cellOf, ctx->d_cellCount, ctx->d_cellStart, ctx->d_blockSums, ctx->d_fill, ctx->d_cellSlot, ctx->d_tmpItems,
                     ctx->d_items, ctx->d_nbrCount, ctx->d_nbrIdx, ctx->d_nbrDist, ctx->d_nbrTs, ctx->d_nbrTe, ctx->d_retry[0], ctx->d_retry[1],
                     ctx->d_retry[2], ctx->d_gws, ctx->d_records, ctx->d_recordsL, ctx->d_spill, ctx->d_recvI, ctx->d_recvD, (void*)ctx->comm, ctx->winLocal,
                     ctx->winPeer[0], ctx->winPeer[1], ctx->winPeer[2], ctx->winPeer[3], ctx->winPeer[4], ctx->winPeer[5], ctx->winPeer[6],

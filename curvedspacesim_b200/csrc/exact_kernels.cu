@@ -3,8 +3,7 @@
 //
 //   k_euclid_cell   meshPositionToEuclideanLocation (triangulatedMeshSpace.cpp:82-106) fused with the
 //                   cell binning of hyperRectangularCellList::positionToCellIndex/sort (:71-125)
-//   k_scan_*        exclusive scan of the per-cell counts
-//   k_cell_fill / k_cell_rank   deterministic (ascending particle index) cell contents
+//   k_cell_place / k_cell_fill / k_cell_rank   scan-free, deterministic (ascending particle index) cell contents
 //   k_walk          triangulatedMeshSpace::transportParticleAndVectors (:448-658), one thread per particle,
 //                   optionally fused with the velocity-Verlet first half step (velocityVerletNVE.cpp:14-21)
 //   k_axpy-type     updater arithmetic (src/updaters/*.cpp) and reductions
@@ -105,7 +104,7 @@ __device__ __forceinline__ d3 rotateAboutAxis(const d3& p, const d3& base, const
 
 // ------------------------------------------------------------------------------------------------
 __global__ void k_euclid_cell(MeshDev m, CellGrid g, int n, const int* __restrict__ face, const double* __restrict__ bary,
-                              double* __restrict__ eucl, int* __restrict__ cellOf, int* __restrict__ cellCount)
+                              double* __restrict__ eucl, int* __restrict__ cellOf, int* __restrict__ cellCount, int* __restrict__ cellSlot)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -117,106 +116,50 @@ __global__ void k_euclid_cell(MeshDev m, CellGrid g, int n, const int* __restric
         int ix = cellCoord(g, p.x, 0), iy = cellCoord(g, p.y, 1), iz = cellCoord(g, p.z, 2);
         int c = ix + iy * g.n[0] + iz * g.n[0] * g.n[1];
         cellOf[i] = c;
-        atomicAdd(cellCount + c, 1);
+        cellSlot[i] = atomicAdd(cellCount + c, 1); // arrival order inside the cell; the first arrival places the cell (k_cell_place)
     }
 }
 
-// exclusive scan, 3 passes; each block handles SCAN_ITEMS consecutive counts
-#define SCAN_THREADS 1024
-#define SCAN_PER_THREAD 4
-#define SCAN_ITEMS (SCAN_THREADS * SCAN_PER_THREAD)
-__device__ __forceinline__ int blockExclusiveScan(int v, int* total)
+// Cell contents without a scan over the grid (the grid of config 5 has 2.5 M cells for 100 k particles; a scan costs more than
+// everything else in the cell list).  The particle that arrived first in a cell reserves the cell's range with one atomic bump
+// (cellStart[c]; ranges are contiguous and disjoint but in no particular order, empty cells keep stale starts and are never
+// read because their count is 0), every particle drops itself at start + arrival slot, and the members are then put in
+// ascending particle order, as hyperRectangularCellList::sort produces by inserting particles in index order (:96-112).
+// Consumers read a cell as items[cellStart[c] .. cellStart[c] + cellCount[c]).
+__global__ void k_cell_place(int n, const int* __restrict__ cellOf, const int* __restrict__ cellSlot, const int* __restrict__ cellCount,
+                             int* __restrict__ cellStart, int* __restrict__ bump)
 {
-    __shared__ int warpSums[32];
-    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    int x = v;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+    const bool first = i < n && cellSlot[i] == 0;
+    const int c = first ? cellOf[i] : 0;
+    const int cnt = first ? cellCount[c] : 0;
+    int incl = cnt; // one bump per warp: the ranges of the warp's cells are carved out of it by a prefix sum
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        int y = __shfl_up_sync(0xffffffffu, x, o);
-        if (lane >= o) x += y;
+        int y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
     }
-    if (lane == 31) warpSums[w] = x;
-    __syncthreads();
-    if (w == 0) {
-        int s = warpSums[lane];
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            int y = __shfl_up_sync(0xffffffffu, s, o);
-            if (lane >= o) s += y;
-        }
-        warpSums[lane] = s;
-    }
-    __syncthreads();
-    int base = w ? warpSums[w - 1] : 0;
-    if (total) *total = warpSums[31];
-    __syncthreads();
-    return base + x - v;
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    int base = 0;
+    if (lane == 31 && total > 0) base = atomicAdd(bump, total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    if (first) cellStart[c] = base + incl - cnt;
 }
-__global__ void k_scan_local(const int* __restrict__ in, int* __restrict__ out, int* __restrict__ blockSums, int n)
-{
-    int base = blockIdx.x * SCAN_ITEMS + threadIdx.x * SCAN_PER_THREAD;
-    int v[SCAN_PER_THREAD], s = 0;
-#pragma unroll
-    for (int k = 0; k < SCAN_PER_THREAD; ++k) {
-        v[k] = (base + k < n) ? in[base + k] : 0;
-        s += v[k];
-    }
-    int tot;
-    int ex = blockExclusiveScan(s, &tot);
-#pragma unroll
-    for (int k = 0; k < SCAN_PER_THREAD; ++k) {
-        if (base + k < n) out[base + k] = ex;
-        ex += v[k];
-    }
-    if (threadIdx.x == 0) blockSums[blockIdx.x] = tot;
-}
-__global__ void k_scan_blocks(int* blockSums, int nb) // single block; nb <= SCAN_ITEMS * many via loop
-{
-    __shared__ int carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    for (int start = 0; start < nb; start += SCAN_THREADS) {
-        int i = start + threadIdx.x;
-        int v = i < nb ? blockSums[i] : 0;
-        int tot;
-        int ex = blockExclusiveScan(v, &tot);
-        int c = carry;
-        if (i < nb) blockSums[i] = ex + c;
-        __syncthreads();
-        if (threadIdx.x == 0) carry = c + tot;
-        __syncthreads();
-    }
-}
-__global__ void k_scan_add(int* __restrict__ out, const int* __restrict__ blockSums, int n, int* __restrict__ fill, int total)
-{
-    int base = blockIdx.x * SCAN_ITEMS + threadIdx.x * SCAN_PER_THREAD;
-    int add = blockSums[blockIdx.x];
-#pragma unroll
-    for (int k = 0; k < SCAN_PER_THREAD; ++k)
-        if (base + k < n) {
-            out[base + k] += add;
-            fill[base + k] = 0;
-        }
-    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) out[n] = total;
-}
-__global__ void k_cell_fill(int n, const int* __restrict__ cellOf, const int* __restrict__ cellStart, int* __restrict__ fill,
+__global__ void k_cell_fill(int n, const int* __restrict__ cellOf, const int* __restrict__ cellSlot, const int* __restrict__ cellStart,
                             int* __restrict__ tmpItems)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    int c = cellOf[i];
-    int s = atomicAdd(fill + c, 1);
-    tmpItems[cellStart[c] + s] = i;
+    tmpItems[cellStart[cellOf[i]] + cellSlot[i]] = i;
 }
-// rank of particle i inside its cell = number of members with a smaller index -> ascending order, as
-// hyperRectangularCellList::sort produces by inserting particles in index order (:96-112)
-__global__ void k_cell_rank(int n, const int* __restrict__ cellOf, const int* __restrict__ cellStart, const int* __restrict__ fill,
+// rank of particle i inside its cell = number of members with a smaller index
+__global__ void k_cell_rank(int n, const int* __restrict__ cellOf, const int* __restrict__ cellStart, const int* __restrict__ cellCount,
                             const int* __restrict__ tmpItems, int* __restrict__ items)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int c = cellOf[i];
-    int s0 = cellStart[c], cnt = fill[c];
+    int s0 = cellStart[c], cnt = cellCount[c];
     int r = 0;
     for (int s = 0; s < cnt; ++s) r += (tmpItems[s0 + s] < i);
     items[s0 + r] = i;
@@ -806,22 +749,18 @@ void launchLocate(cudaStream_t st, const MeshDev& m, const double gmn[3], double
 static inline int gridFor(int n, int b) { return (n + b - 1) / b; }
 
 void launchEuclidCell(cudaStream_t st, const MeshDev& m, const CellGrid& g, int n, const int* face, const double* bary, double* eucl,
-                      int* cellOf, int* cellCount)
+                      int* cellOf, int* cellCount, int* cellSlot)
 {
-    if (n > 0) k_euclid_cell<<<gridFor(n, 256), 256, 0, st>>>(m, g, n, face, bary, eucl, cellOf, cellCount);
+    if (n > 0) k_euclid_cell<<<gridFor(n, 256), 256, 0, st>>>(m, g, n, face, bary, eucl, cellOf, cellCount, cellSlot);
 }
-int scanBlocks(int nCells) { return (nCells + SCAN_ITEMS - 1) / SCAN_ITEMS; }
-void launchCellBuild(cudaStream_t st, int n, int nCells, const int* cellOf, const int* cellCount, int* cellStart, int* blockSums,
-                     int* fill, int* tmpItems, int* items)
+// cellCount[nCells] is the bump counter (cleared with the counts)
+void launchCellBuild(cudaStream_t st, int n, int nCells, const int* cellOf, const int* cellSlot, int* cellCount, int* cellStart, int* tmpItems,
+                     int* items)
 {
-    int nb = scanBlocks(nCells);
-    k_scan_local<<<nb, SCAN_THREADS, 0, st>>>(cellCount, cellStart, blockSums, nCells);
-    k_scan_blocks<<<1, SCAN_THREADS, 0, st>>>(blockSums, nb);
-    k_scan_add<<<nb, SCAN_THREADS, 0, st>>>(cellStart, blockSums, nCells, fill, n);
-    if (n > 0) {
-        k_cell_fill<<<gridFor(n, 256), 256, 0, st>>>(n, cellOf, cellStart, fill, tmpItems);
-        k_cell_rank<<<gridFor(n, 256), 256, 0, st>>>(n, cellOf, cellStart, fill, tmpItems, items);
-    }
+    if (n <= 0) return;
+    k_cell_place<<<gridFor(n, 256), 256, 0, st>>>(n, cellOf, cellSlot, cellCount, cellStart, cellCount + nCells);
+    k_cell_fill<<<gridFor(n, 256), 256, 0, st>>>(n, cellOf, cellSlot, cellStart, tmpItems);
+    k_cell_rank<<<gridFor(n, 256), 256, 0, st>>>(n, cellOf, cellStart, cellCount, tmpItems, items);
 }
 void launchWalk(cudaStream_t st, const MeshDev& m, int n, int minIdx, int* face, double* bary, double* disp, double* vel, double* frc,
                 int transportForce, int transportVelocity, int mode, double dt, int* flags, unsigned long long* counters, const PeerWin& pw)

@@ -273,7 +273,7 @@ __device__ int processSource(const GeoArgs& a, const WS& w, int li, int lane)
             int yy = y0 + rem / nz, zz = z0 + rem % nz;
             int c = xx + yy * g.n[0] + zz * g.n[0] * g.n[1];
             s0 = a.cellStart[c];
-            s1 = a.cellStart[c + 1];
+            s1 = s0 + a.cellCount[c];
         }
         int mine = 0;
         double maxd2 = 0;

@@ -20,6 +20,7 @@ struct GeoArgs {
     const double* bary;    // [3 nTotal]
     const double* eucl;    // [3 nTotal]
     const int* cellStart;  // nullptr -> all-to-all candidates (baseNeighborStructure)
+    const int* cellCount;  // cell c holds cellItems[cellStart[c] .. cellStart[c] + cellCount[c])
     const int* cellItems;
     int submeshing;
     double maxDist;
@@ -117,6 +118,7 @@ struct PatchArgs {
     const int* face;      // [nTotal]
     const double* eucl;   // [3 nTotal]
     const int* cellStart;
+    const int* cellCount;
     const int* cellItems;
     int submeshing;
     double maxDist;
@@ -169,10 +171,9 @@ size_t windowsHalfSpillBytes(int numSMs);
 int geodesicMaxSmemPerBlock();
 
 void launchEuclidCell(cudaStream_t st, const MeshDev& m, const CellGrid& g, int n, const int* face, const double* bary, double* eucl,
-                      int* cellOf, int* cellCount);
-int scanBlocks(int nCells);
-void launchCellBuild(cudaStream_t st, int n, int nCells, const int* cellOf, const int* cellCount, int* cellStart, int* blockSums,
-                     int* fill, int* tmpItems, int* items);
+                      int* cellOf, int* cellCount, int* cellSlot);
+void launchCellBuild(cudaStream_t st, int n, int nCells, const int* cellOf, const int* cellSlot, int* cellCount, int* cellStart, int* tmpItems,
+                     int* items);
 // ---- peer-memory position exchange, fused with the walker (replaces the all-gather after every move:
 // mpiSimulation::synchronizeAndTransferBuffers, src/simulation/mpiSimulation.cpp:11-42).  Every rank owns an exchange
 // window (cudaMalloc + CUDA IPC, mapped by all peers over NVLink/NVSwitch): a staging copy of the replicated position

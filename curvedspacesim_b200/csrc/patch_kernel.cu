@@ -115,7 +115,7 @@ template <class T> __device__ int buildPatch(const PatchArgs& a, PatchSmem<T>& s
             int yy = y0 + rem / nz, zz = z0 + rem % nz;
             int c = xx + yy * g.n[0] + zz * g.n[0] * g.n[1];
             s0 = a.cellStart[c];
-            s1 = a.cellStart[c + 1];
+            s1 = s0 + a.cellCount[c];
         }
         // one pass: each lane keeps the first few hits of its cell in registers (cells hold ~0.3 particles
         // on average at the target densities); a second pass over the cell is taken only when it has more
