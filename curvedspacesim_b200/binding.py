@@ -22,7 +22,7 @@ SUM, MAX = 0, 1
 COUNTER_NAMES = ["walk_vertex", "walk_nohit", "walk_itercap", "walk_nan", "walk_border", "disconnected", "ties", "crossings",
                  "windows", "pseudo_sources", "patch_faces", "patch_verts", "queries", "sources", "tier_retry", "overflow",
                  "kernels", "kmax_overflow", "ovf_candidates", "ovf_faces", "ovf_verts", "ovf_ring", "clk_batch", "clk_fan", "clk_prop",
-                 "clk_patch", "clk_total", "peer_timeout"]
+                 "clk_patch", "clk_total", "peer_timeout", "spilled"]
 NUM_COUNTERS = 32
 
 # every symbol include/css_api.h declares (tests check that the library exports all of them)

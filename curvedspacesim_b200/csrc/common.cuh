@@ -90,6 +90,7 @@ enum {
     C_OVF_REASON /* 18..21: candidates, faces, vertices, ring */,
     C_CLK_BATCH = 22, C_CLK_FAN = 23, C_CLK_PROP = 24, C_CLK_PATCH = 25, C_CLK_TOTAL = 26, /* summed per-warp clock64 cycles */
     C_PEER_TIMEOUT = 27, /* a peer-exchange flag wait gave up (a rank died or left the collective sequence) */
+    C_SPILLED = 28,      /* windows pushed to a global spill stack by k_windows_half */
     NUM_COUNTERS = 32
 };
 #define CSS_WALK_MAX_CROSSINGS 100000

@@ -476,7 +476,10 @@ template <class T> __global__ void __launch_bounds__(32 * CSS_HALF_WPB, CSS_HALF
                     const int toth = half ? tot1 : tot0;
                     if (half ? ovf1 : ovf0) {
                         if (spillN + toth > SPILL_CAP) failed = true, live = false, K = nF = nV = 0, head = tail = 0, spillN = 0; // next tier
-                        else spillN += toth;
+                        else {
+                            spillN += toth;
+                            if (hl == 0) atomicAdd(a.counters + C_SPILLED, (unsigned long long)toth);
+                        }
                     } else
                         tail += toth;
                 }

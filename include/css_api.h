@@ -88,7 +88,9 @@ enum css_counter {
     CSS_C_KERNELS = 16,      /* kernels launched by this context (host-side count) */
     CSS_C_KMAX_OVERFLOW = 17, /* neighbour stride too small (handled by regrowing and rerunning) */
     CSS_C_OVF_CANDIDATES = 18, CSS_C_OVF_FACES = 19, CSS_C_OVF_VERTS = 20, CSS_C_OVF_RING = 21, /* tier overflow reasons */
-    CSS_C_CLK_BATCH = 22, CSS_C_CLK_FAN = 23, CSS_C_CLK_PROP = 24, CSS_C_CLK_PATCH = 25, CSS_C_CLK_TOTAL = 26, /* per-warp cycles */
+    CSS_C_CLK_BATCH = 22, CSS_C_CLK_FAN = 23, CSS_C_CLK_PROP = 24, CSS_C_CLK_PATCH = 25, CSS_C_CLK_TOTAL = 26, /* developer statistics */
+    CSS_C_PEER_TIMEOUT = 27, /* a peer-exchange flag wait gave up */
+    CSS_C_SPILLED = 28,      /* windows that left a full shared-memory ring for the global spill stack (and came back) */
     CSS_NUM_COUNTERS = 32
 };
 

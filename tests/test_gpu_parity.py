@@ -594,7 +594,7 @@ c = ctx.counters()
 ctx.step_nve(kind, params, 0.002, 10)
 f2, b2, v2, fr2 = ctx.get_state()
 np.savez(sys.argv[1], off=off, idx=idx, d=d, ts=ts, te=te, retry=c["tier_retry"], overflow=c["overflow"], face=f2, bary=b2, vel=v2, frc=fr2,
-         kmean=len(idx) / N, kmax=int(np.diff(off).max()))
+         kmean=len(idx) / N, kmax=int(np.diff(off).max()), spilled=c["spilled"])
 """ % (ROOT, os.path.join(ROOT, "tests"))
     import tempfile
 
@@ -607,6 +607,7 @@ np.savez(sys.argv[1], off=off, idx=idx, d=d, ts=ts, te=te, retry=c["tier_retry"]
             outs.append(dict(np.load(out)))
     a, b = outs
     assert int(a["kmax"]) > 16 and float(a["kmean"]) > 8          # the grouped path is exercised
+    assert int(a["spilled"]) > 0 and int(b["spilled"]) == 0         # and so are the global spill stacks of the half-warp kernel
     assert int(a["overflow"]) == 0 and int(b["overflow"]) == 0
     assert np.array_equal(a["off"], b["off"]) and np.array_equal(a["idx"], b["idx"])
     assert _rel(a["d"], b["d"]) < 1e-12 and np.max(np.abs(a["ts"] - b["ts"])) < 1e-10 and np.max(np.abs(a["te"] - b["te"])) < 1e-10
