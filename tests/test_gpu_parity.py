@@ -796,7 +796,7 @@ def test_two_gpus_bitwise_equal_to_one(tmp_path):
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
     script = os.path.join(ROOT, "tests", "multigpu_worker.py")
     out = str(tmp_path)
-    world = min(torch.cuda.device_count(), 4)
+    world = min(torch.cuda.device_count(), 8)
     # the exchange after every move: peer-memory stores fused into the walker (default) and the NCCL all-gather
     for tag, p2p in (("_p2p", "1"), ("_nccl", "0")):
         env = dict(os.environ, CSS_P2P=p2p, CSS_TAG=tag)
