@@ -43,7 +43,7 @@ struct css_ctx {
     CellGrid grid{};
     double gridRange = -1;
     int nCells = 0, capCells = 0;
-    int *d_cellOf = nullptr, *d_cellCount = nullptr, *d_cellStart = nullptr, *d_blockSums = nullptr, *d_fill = nullptr /* (unused) */, *d_cellSlot = nullptr, *d_tmpItems = nullptr,
+    int *d_cellOf = nullptr, *d_cellCount = nullptr, *d_cellStart = nullptr, *d_cellSlot = nullptr, *d_tmpItems = nullptr,
         *d_items = nullptr;
     // neighbours (fixed stride kmax)
     int kmax = 32, capNbr = 0;
@@ -317,7 +317,7 @@ int css_destroy(css_ctx* ctx)
     if (ctx->comm) ncclCommDestroy(ctx->comm);
     void* ptrs[] = {ctx->d_vert,   ctx->d_corner,    ctx->d_adj,     ctx->d_saddle,  ctx->d_face,     ctx->d_bary,    ctx->d_eucl,
                     ctx->d_vel,    ctx->d_frc,       ctx->d_disp,    ctx->d_walkFlags, ctx->d_cellOf, ctx->d_cellCount, ctx->d_cellStart,
-                    ctx->d_blockSums, ctx->d_fill,   ctx->d_cellSlot, ctx->d_tmpItems, ctx->d_items,  ctx->d_nbrCount, ctx->d_nbrIdx,  ctx->d_nbrDist,
+                    ctx->d_cellSlot, ctx->d_tmpItems, ctx->d_items,  ctx->d_nbrCount, ctx->d_nbrIdx,  ctx->d_nbrDist,
                     ctx->d_nbrTs,  ctx->d_nbrTe,     ctx->d_work,    ctx->d_retry[0], ctx->d_retry[1], ctx->d_retry[2], ctx->d_gws,
                     ctx->d_partial, ctx->d_red,      ctx->d_counters, ctx->d_sendI,  ctx->d_sendD,    ctx->d_recvI,   ctx->d_recvD,
                     ctx->d_redBuf,  ctx->d_geo,       ctx->d_records, ctx->d_recordsL, ctx->d_epoch, ctx->d_ticket, ctx->d_ipcBuf, ctx->d_spill, ctx->d_fgStart, ctx->d_fgFaces};
@@ -1213,7 +1213,7 @@ static uint64_t nveGraphKey(css_ctx* ctx, const ForceParams& fp, double range, d
     MIX(ctx->nLocal), MIX(ctx->nTotal), MIX(ctx->minIdx), MIX(ctx->kmax), MIX(ctx->nranks), MIX(ctx->timing), MIX(ctx->submeshing),
         MIX(ctx->maxDist), MIX(ctx->boundaryMode), MIX(ctx->useCellList), MIX(ctx->wantEnd), MIX(ctx->twoStage), MIX(ctx->winWpb), MIX(ctx->winLean), MIX(ctx->winHalf), MIX(ctx->grid), MIX(ctx->nCells);
     void* ptrs[] = {ctx->d_vert, ctx->d_corner, ctx->d_adj, ctx->d_geo, ctx->d_saddle, ctx->d_face, ctx->d_bary, ctx->d_eucl, ctx->d_vel, ctx->d_frc,
-                    ctx->d_disp, ctx->d_walkFlags, ctx->d_cellOf, ctx->d_cellCount, ctx->d_cellStart, ctx->d_blockSums, ctx->d_fill, ctx->d_cellSlot, ctx->d_tmpItems,
+                    ctx->d_disp, ctx->d_walkFlags, ctx->d_cellOf, ctx->d_cellCount, ctx->d_cellStart, ctx->d_cellSlot, ctx->d_tmpItems,
                     ctx->d_items, ctx->d_nbrCount, ctx->d_nbrIdx, ctx->d_nbrDist, ctx->d_nbrTs, ctx->d_nbrTe, ctx->d_retry[0], ctx->d_retry[1],
                     ctx->d_retry[2], ctx->d_gws, ctx->d_records, ctx->d_recordsL, ctx->d_spill, ctx->d_recvI, ctx->d_recvD, (void*)ctx->comm, ctx->winLocal,
                     ctx->winPeer[0], ctx->winPeer[1], ctx->winPeer[2], ctx->winPeer[3], ctx->winPeer[4], ctx->winPeer[5], ctx->winPeer[6],
