@@ -423,34 +423,28 @@ template <class T> __global__ void __launch_bounds__(32 * CSS_HALF_WPB, CSS_HALF
                 // Xin-Wang filter and bound test in fp32 with a conservative margin: a window is dropped only when it is
                 // dominated by clearly more than the rounding of the approximation.
                 {
+                    // Straight-line, evaluated by every lane and masked at the end: some lane of the warp needs every one of these
+                    // steps in almost every pass, so nested early-outs only add branch and re-convergence instructions.
                     const v2 X = j ? C : A, Y = j ? B : C;
-                    bool valid = false;
-                    double m0 = 0, m1 = 1;
-                    int cmeta = 0;
-                    double2 ccg{0, 0};
                     // corner opposite the child edge: B = corner e+2 for j = 0, A = corner e+1 for j = 1
-                    const int g2 = (ra >> (j ? 8 : 16)) & 0xFF;
-                    if (active && (j ? rightOpen : leftOpen) && g2 != REC_NONE) {
-                        const int kk = (rk >> (j ? 2 : 4)) & 3;
-                        ccg = edgeFrame(a.m, wp, g2, kk); // needed by the child at the next pass: issued here, stored with the push
-                        if (!(j == 1 && inside)) m0 = hitParam0(P0, X, Y);
-                        if (!(j == 0 && inside)) m1 = hitParam0(P1, X, Y);
-                        if (m1 - m0 > 1e-13) {
-                            const f2 fA = tof2(A), fB = tof2(B), fC = tof2(C);
-                            const f2 fX = j ? fC : fA, fY = j ? fB : fC, fO2 = j ? fA : fB;
-                            const float dX = j ? fDC : fDA, dY = j ? fDB : fDC, dO = j ? fDA : fDB;
-                            const f2 X0 = flerp(fX, fY, (float)m0), X1 = flerp(fX, fY, (float)m1);
-                            if (fsg + fsegDist(fO, X0, X1) <= fUb) {
-                                const float keep = 1.f - 2e-5f;
-                                const float s0 = (fsg + flen(X0.x, X0.y)) * keep, s1 = (fsg + flen(X1.x, X1.y)) * keep;
-                                const f2 Xn = j ? X1 : X0; // the end of the child interval next to the parent edge
-                                const float sn = j ? s1 : s0;
-                                const bool dom = (dX + fdist(fX, X1) < s1) || (dY + fdist(fY, X0) < s0) || (dO + fdist(fO2, Xn) < sn);
-                                valid = !dom;
-                                cmeta = g2 | (kk << 16);
-                            }
-                        }
-                    }
+                    const int g2 = (ra >> (j ? 8 : 16)) & 0xFF, kk = (rk >> (j ? 2 : 4)) & 3;
+                    const bool open = active && (j ? rightOpen : leftOpen) && g2 != REC_NONE;
+                    double2 ccg{0, 0};
+                    if (open) ccg = edgeFrame(a.m, wp, g2, kk); // needed by the child at the next pass: issued here, stored with the push
+                    const double h0 = hitParam0(P0, X, Y), h1 = hitParam0(P1, X, Y);
+                    const double m0 = (j == 1 && inside) ? 0.0 : h0, m1 = (j == 0 && inside) ? 1.0 : h1;
+                    const f2 fA = tof2(A), fB = tof2(B), fC = tof2(C);
+                    const f2 fX = j ? fC : fA, fY = j ? fB : fC, fO2 = j ? fA : fB;
+                    const float dX = j ? fDC : fDA, dY = j ? fDB : fDC, dO = j ? fDA : fDB;
+                    const f2 X0 = flerp(fX, fY, (float)m0), X1 = flerp(fX, fY, (float)m1);
+                    const bool reach = fsg + fsegDist(fO, X0, X1) <= fUb;
+                    const float keep = 1.f - 2e-5f;
+                    const float s0 = (fsg + flen(X0.x, X0.y)) * keep, s1 = (fsg + flen(X1.x, X1.y)) * keep;
+                    const f2 Xn = j ? X1 : X0; // the end of the child interval next to the parent edge
+                    const float sn = j ? s1 : s0;
+                    const bool dom = (dX + fdist(fX, X1) < s1) | (dY + fdist(fY, X0) < s0) | (dO + fdist(fO2, Xn) < sn);
+                    const bool valid = open & (m1 - m0 > 1e-13) & reach & !dom;
+                    const int cmeta = g2 | (kk << 16);
                     // push the children into the ring of the source they belong to
                     const unsigned bal = __ballot_sync(FULL, valid);
                     const unsigned lanes0 = nb0 >= 16 ? FULL : (1u << (2 * nb0)) - 1u; // the lanes that worked for source 0
