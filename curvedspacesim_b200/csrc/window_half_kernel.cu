@@ -369,14 +369,10 @@ template <class T> __global__ void __launch_bounds__(32 * CSS_HALF_WPB, CSS_HALF
                         double bA = e == 0 ? b1 : (e == 1 ? b2 : b0), bB = e == 0 ? b2 : (e == 1 ? b0 : b1), bC = e == 0 ? b0 : (e == 1 ? b1 : b2);
                         double rbs = frcp(bA + bB + bC);
                         v2 d{(bA * A.x + bB * B.x + bC * C.x) * rbs, (bA * A.y + bB * B.y + bC * C.y) * rbs}; // the target, seen from the source
-                        double den = cross2(AB, d);
-                        if (den != 0) {
-                            double mu = -cross2(A, d) * frcp(den);
-                            if (mu >= t0 - 1e-12 && mu <= t1 + 1e-12) {
-                                double c = sg + fsqrt(d.x * d.x + d.y * d.y);
-                                if (atomicMinD(&wp.tbest[t], c)) improvedT = true, myT = t, cand = c, dT = d;
-                            }
-                        }
+                        const double den = cross2(AB, d);
+                        const double mu = -cross2(A, d) * frcp(den); // (den = 0: mu is inf or NaN and fails the range test)
+                        const double c = sg + fsqrt(d.x * d.x + d.y * d.y);
+                        if (den != 0 && mu >= t0 - 1e-12 && mu <= t1 + 1e-12 && atomicMinD(&wp.tbest[t], c)) improvedT = true, myT = t, cand = c, dT = d;
                     }
                     if (__any_sync(FULL, improvedT)) { // the winner (lowest lane among equal candidates) records how its path starts and ends
                         __syncwarp();
@@ -406,17 +402,17 @@ template <class T> __global__ void __launch_bounds__(32 * CSS_HALF_WPB, CSS_HALF
                 const bool inside = leftOpen && rightOpen;
                 double DC = wp.D[vC];
                 const double dC = sg + fsqrt(lc2);
+                const bool upd = active && inside && dC < DC;
                 bool improved = false;
-                if (active && inside && dC < DC) {
-                    if (j == 0) improved = atomicMinD(&wp.D[vC], dC);
-                    DC = dC;
-                }
+                if (upd && j == 0) improved = atomicMinD(&wp.D[vC], dC);
+                DC = upd ? dC : DC;
                 const float fDA = (float)wp.D[vA], fDB = (float)wp.D[vB], fDC = (float)DC;
                 __syncwarp();
-                if (improved && dC == wp.D[vC]) { // the winner writes the start direction carried to this vertex
-                    if (psv == NOPSV) wp.dirx[vC] = C.x, wp.diry[vC] = C.y;
-                    else wp.dirx[vC] = wp.dirx[psv], wp.diry[vC] = wp.diry[psv];
-                    wp.vdirty[vC] = 1;
+                { // the winner writes the start direction carried to this vertex (its own for the real source, the pseudo-source's else)
+                    const bool winner = improved && dC == wp.D[vC];
+                    const int pq = min((int)psv, W::V - 1);
+                    const double ndx = psv == NOPSV ? C.x : wp.dirx[pq], ndy = psv == NOPSV ? C.y : wp.diry[pq];
+                    if (winner) wp.dirx[vC] = ndx, wp.diry[vC] = ndy, wp.vdirty[vC] = 1;
                 }
                 // child j = 0: edge C->A of this face (opposite corner B), entered by the neighbour as A->C
                 // child j = 1: edge B->C of this face (opposite corner A), entered by the neighbour as C->B
@@ -453,29 +449,39 @@ template <class T> __global__ void __launch_bounds__(32 * CSS_HALF_WPB, CSS_HALF
                     // (all children of the pass, so a ring never holds a partial pass); the windows come back when the ring runs
                     // dry.  Order does not matter for the result, every update is a minimum.  ~1e-3 of the sources of config 5.
                     const bool ovf0 = tail0 + tot0 - (head0 + nb0) > T::RING, ovf1 = tail1 + tot1 - (head1 + nb1) > T::RING;
-                    const int sp0 = __shfl_sync(FULL, spillN, 0), sp1 = __shfl_sync(FULL, spillN, 16);
-                    if (valid) {
-                        const int rank = __popc(bal & (src ? ~lanes0 : lanes0) & ((1u << lane) - 1u));
-                        if (!(src ? ovf1 : ovf0)) {
+                    const int rank = __popc(bal & (src ? ~lanes0 : lanes0) & ((1u << lane) - 1u));
+                    const int toth = half ? tot1 : tot0;
+                    if (!(ovf0 | ovf1)) { // the common case: everything fits
+                        if (valid) {
                             const int q = ((src ? tail1 : tail0) + rank) & MASKR;
                             wp.rax[q] = X.x, wp.ray[q] = X.y, wp.rbx[q] = Y.x, wp.rby[q] = Y.y;
                             wp.rt0[q] = m0, wp.rt1[q] = m1, wp.rmeta[q] = cmeta, wp.rpsv[q] = psv;
                             wp.rcg[q] = ccg;
-                        } else if ((src ? sp1 : sp0) + rank < SPILL_CAP) {
-                            double* e = spillPair + ((size_t)src * SPILL_CAP + (src ? sp1 : sp0) + rank) * SPILL_DOUBLES;
-                            e[0] = X.x, e[1] = X.y, e[2] = Y.x, e[3] = Y.y, e[4] = m0, e[5] = m1, e[6] = ccg.x, e[7] = ccg.y;
-                            e[8] = __longlong_as_double((long long)(unsigned)cmeta | ((long long)psv << 32));
                         }
-                    }
-                    const int toth = half ? tot1 : tot0;
-                    if (half ? ovf1 : ovf0) {
-                        if (spillN + toth > SPILL_CAP) failed = true, live = false, K = nF = nV = 0, head = tail = 0, spillN = 0; // next tier
-                        else {
-                            spillN += toth;
-                            if (hl == 0) atomicAdd(a.counters + C_SPILLED, (unsigned long long)toth);
-                        }
-                    } else
                         tail += toth;
+                    } else {
+                        const int sp0 = __shfl_sync(FULL, spillN, 0), sp1 = __shfl_sync(FULL, spillN, 16);
+                        if (valid) {
+                            if (!(src ? ovf1 : ovf0)) {
+                                const int q = ((src ? tail1 : tail0) + rank) & MASKR;
+                                wp.rax[q] = X.x, wp.ray[q] = X.y, wp.rbx[q] = Y.x, wp.rby[q] = Y.y;
+                                wp.rt0[q] = m0, wp.rt1[q] = m1, wp.rmeta[q] = cmeta, wp.rpsv[q] = psv;
+                                wp.rcg[q] = ccg;
+                            } else if ((src ? sp1 : sp0) + rank < SPILL_CAP) {
+                                double* e = spillPair + ((size_t)src * SPILL_CAP + (src ? sp1 : sp0) + rank) * SPILL_DOUBLES;
+                                e[0] = X.x, e[1] = X.y, e[2] = Y.x, e[3] = Y.y, e[4] = m0, e[5] = m1, e[6] = ccg.x, e[7] = ccg.y;
+                                e[8] = __longlong_as_double((long long)(unsigned)cmeta | ((long long)psv << 32));
+                            }
+                        }
+                        if (half ? ovf1 : ovf0) {
+                            if (spillN + toth > SPILL_CAP) failed = true, live = false, K = nF = nV = 0, head = tail = 0, spillN = 0; // next tier
+                            else {
+                                spillN += toth;
+                                if (hl == 0) atomicAdd(a.counters + C_SPILLED, (unsigned long long)toth);
+                            }
+                        } else
+                            tail += toth;
+                    }
                 }
                 __syncwarp();
             }
