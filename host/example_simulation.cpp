@@ -7,6 +7,7 @@
 //            1 = gpuSimulation (device-resident fused step)
 //   CSS_EXAMPLE_DB=<dir> in the environment: the initial and final states are also written as two records of a
 //   simpleModelDatabase (host/css_database.hpp), as the reference's mains do with their HDF5 trajectory file.
+//   CSS_EXAMPLE_R3=<file>: the final R^3 coordinates are written to <file> and imported again (setMeshPositionsFromR3File).
 // The dump holds N, then the initial (face, bary, velocity) and the final (face, bary, velocity, force) arrays in raw
 // little-endian form; tests/test_gpu_parity.py replays the same initial state through the ctypes binding and the oracle.
 #include "css_database.hpp"
@@ -97,6 +98,29 @@ int main(int argc, char** argv)
             {
             simpleModelDatabase db(N, dbDir, fileMode::readwrite);
             db.writeState(configuration, simulator->Time);
+            }
+        if (const char* r3file = getenv("CSS_EXAMPLE_R3"))
+            { // simpleModel::setMeshPositionsFromR3File: write the final R^3 coordinates as "x,y,z" lines, import them into a second
+              // model on the same space and compare with the mesh positions they came from
+            configuration->fillEuclideanLocations();
+            FILE* r3 = fopen(r3file, "w");
+            if (!r3) ERRORERROR("cannot open the R3 file");
+            for (int i = 0; i < N; ++i)
+                fprintf(r3, "%.17g,%.17g,%.17g\n", configuration->euclideanLocations[i].x, configuration->euclideanLocations[i].y,
+                        configuration->euclideanLocations[i].z);
+            fclose(r3);
+            shared_ptr<gpuModel> imported = make_shared<gpuModel>(1);
+            imported->setSpace(meshSpace);
+            imported->setMeshPositionsFromR3File(r3file);
+            int sameFace = 0;
+            double maxDiff = 0;
+            for (int i = 0; i < N && imported->N == N; ++i)
+                if (imported->positions[i].faceIndex == configuration->positions[i].faceIndex)
+                    {
+                    sameFace++;
+                    for (int k = 0; k < 3; ++k) maxDiff = std::max(maxDiff, std::fabs(imported->positions[i].x[k] - configuration->positions[i].x[k]));
+                    }
+            printf("R3 import: %d positions, %d on the same face, max weight difference %.3e\n", imported->N, sameFace, maxDiff);
             }
         printf("%d particles, %d timesteps in %.4f s (%s): %.3e particle-timesteps/s; fN %g fM %g\n", N, maximumIterations, secs,
                fused ? "fused device step" : "host-driven updaters", N * (double)maximumIterations / secs, eom->getForceNorm(), eom->getMaxForce());

@@ -789,6 +789,23 @@ def test_cpp_host_layer_matches_the_oracle(branch, fused, tmp_path):
 
 
 # ------------------------------------------------------------------------------ multi-GPU
+def test_cpp_host_layer_imports_r3_positions(tmp_path):
+    """simpleModel::setMeshPositionsFromR3File / R3PositionsToMeshPositions of the C++ host layer (css_locate underneath): the final
+    R^3 coordinates of a short run, written as a text file, come back as the mesh positions they were computed from."""
+    from curvedspacesim_b200 import build
+
+    exe = build.build_host_example()
+    V, F = _mesh("icosphere16")
+    off = str(tmp_path / "m.off")
+    meshes.save_off(off, V, F)
+    out = subprocess.run([exe, off, "120", "5", "2", "1", str(tmp_path / "d.bin")], capture_output=True, text=True,
+                         env=dict(os.environ, CSS_EXAMPLE_R3=str(tmp_path / "r3.csv")))
+    assert out.returncode == 0, out.stderr
+    line = [l for l in out.stdout.splitlines() if l.startswith("R3 import:")][0].split()
+    n, same, diff = int(line[2]), int(line[4]), float(line[-1])
+    assert n == 120 and same >= 118 and diff < 1e-9      # (a point on an edge may legitimately come back on the neighbour)
+
+
 def test_two_gpus_bitwise_equal_to_one(tmp_path):
     import torch
 
