@@ -114,7 +114,7 @@ template <class W> __device__ __forceinline__ double2 edgeFrame(const MeshDev& m
 
 // push up to one window per lane; returns false when the ring would overflow
 template <class W> __device__ __forceinline__ bool pushWindows(W& w, int lane, int head, int& tail, bool valid, const v2& A, const v2& B,
-                                            double t0, double t1, int meta, unsigned char psv, const double2& cg)
+                                            double t0, double t1, int meta, unsigned char psv, const double2& cg, float lb = 0.f)
 {
     unsigned bal = __ballot_sync(FULL, valid);
     int tot = __popc(bal);
@@ -124,6 +124,7 @@ template <class W> __device__ __forceinline__ bool pushWindows(W& w, int lane, i
         w.rax[q] = A.x, w.ray[q] = A.y, w.rbx[q] = B.x, w.rby[q] = B.y;
         w.rt0[q] = t0, w.rt1[q] = t1, w.rmeta[q] = meta, w.rpsv[q] = psv;
         if constexpr (W::lean) w.rcg[q] = cg;
+        if constexpr (W::ringLb) w.rlb[q] = lb; // lower bound of every path through the window (checked again at pop time)
     }
     tail += tot;
     return true;
@@ -141,6 +142,7 @@ template <class W> __device__ __noinline__ bool spawnFan(const MeshDev& m, W& w,
         bool valid = false;
         v2 A{0, 0}, B{0, 0};
         int meta = 0;
+        float lb = 0.f;
         if (f < nF) {
             uchar4 fv = w.fvert[f];
             int i = fv.x == pv ? 0 : (fv.y == pv ? 1 : (fv.z == pv ? 2 : -1));
@@ -162,7 +164,8 @@ template <class W> __device__ __noinline__ bool spawnFan(const MeshDev& m, W& w,
                     meta = g2 | (kk << 16);
                     A = v2{qx, qy};
                     B = v2{lp, 0};
-                    valid = !((float)Dv + fsegDist(f2{0.f, 0.f}, tof2(A), tof2(B)) * (1.f - 1e-5f) > fUb);
+                    lb = (float)Dv + fsegDist(f2{0.f, 0.f}, tof2(A), tof2(B)) * (1.f - 1e-5f);
+                    valid = !(lb > fUb);
                 }
             }
         }
@@ -183,7 +186,7 @@ template <class W> __device__ __noinline__ bool spawnFan(const MeshDev& m, W& w,
         double2 cg{0, 0};
         if constexpr (W::lean)
             if (valid) cg = edgeFrame(m, w, meta & 0xFF, (meta >> 16) & 3);
-        if (ok) ok = pushWindows(w, lane, head, tail, valid, A, B, 0.0, 1.0, meta, (unsigned char)pv, cg);
+        if (ok) ok = pushWindows(w, lane, head, tail, valid, A, B, 0.0, 1.0, meta, (unsigned char)pv, cg, lb);
         __syncwarp();
     }
     return ok;

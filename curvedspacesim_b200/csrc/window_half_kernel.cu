@@ -35,6 +35,7 @@ template <> struct MaskOf<8> {
 template <class T> struct HalfSmem { // per-SOURCE workspace, two per warp (always the lean layout: frames / vertices from L2)
     static constexpr int F = T::MAXF, V = T::MAXV, K = T::MAXK, R = T::RING;
     static constexpr bool lean = true;
+    static constexpr bool ringLb = true;
     using mask_t = typename MaskOf<(K <= 8 ? 8 : 16)>::type;
     static_assert(T::OFF_VELIG % 4 == 0 && V % 4 == 0, "velig is copied in 4-byte pieces");
     static_assert(K <= 16 && R >= 32, "one target per lane of the half; a pass pushes up to 16 children");
@@ -47,6 +48,7 @@ template <class T> struct HalfSmem { // per-SOURCE workspace, two per warp (alwa
     double root[6];
     double fpart[3]; // pair forces of the earlier target groups of this source
     int rmeta[R];
+    float rlb[R]; // ring: lower bound (fp32, rounded down by the margin) of every path through the window, computed at push time
     int tIdx[K];
     int tcode[K]; // how the best path ends: 0 none, 1 chord in the source face, 2 + 4*(g | e << 8) window, 3 + 4*k corner k
     int towner[K];
@@ -83,7 +85,7 @@ __device__ __forceinline__ double hitParam0(const v2& P, const v2& X, const v2& 
 
 // push up to one window per lane into the ring of the lane's own half; false when that ring would overflow
 template <class W> __device__ __forceinline__ bool pushHalf(W& w, int hl, int hbase, int head, int& tail, bool valid, const v2& A, const v2& B,
-                                                           double t0, double t1, int meta, unsigned char psv, const double2& cg)
+                                                           double t0, double t1, int meta, unsigned char psv, const double2& cg, float lb)
 {
     const unsigned bal = (__ballot_sync(FULL, valid) >> hbase) & 0xFFFFu;
     const int tot = __popc(bal);
@@ -93,6 +95,7 @@ template <class W> __device__ __forceinline__ bool pushHalf(W& w, int hl, int hb
         w.rax[q] = A.x, w.ray[q] = A.y, w.rbx[q] = B.x, w.rby[q] = B.y;
         w.rt0[q] = t0, w.rt1[q] = t1, w.rmeta[q] = meta, w.rpsv[q] = psv;
         w.rcg[q] = cg;
+        w.rlb[q] = lb;
     }
     tail += tot;
     return true;
@@ -266,6 +269,7 @@ template <class T> __global__ void __launch_bounds__(32 * CSS_HALF_WPB, CSS_HALF
             v2 A{0, 0}, B{0, 0};
             int meta = 0;
             double2 cg{0, 0};
+            float lb0 = 0.f;
             if (live && hl < 3) {
                 uchar4 fa = w.fadj[0];
                 int g = hl == 0 ? fa.x : (hl == 1 ? fa.y : fa.z);
@@ -277,9 +281,10 @@ template <class T> __global__ void __launch_bounds__(32 * CSS_HALF_WPB, CSS_HALF
                     A = hl == 0 ? rq2 : (hl == 1 ? rq0 : rq1);
                     B = hl == 0 ? rq1 : (hl == 1 ? rq2 : rq0);
                     cg = edgeFrame(a.m, w, g, kk);
+                    lb0 = fsegDist(f2{0.f, 0.f}, tof2(A), tof2(B)) * (1.f - 1e-5f);
                 }
             }
-            pushHalf(w, hl, hbase, head, tail, valid, A, B, 0.0, 1.0, meta, NOPSV, cg); // 3 <= ring
+            pushHalf(w, hl, hbase, head, tail, valid, A, B, 0.0, 1.0, meta, NOPSV, cg, lb0); // 3 <= ring
         }
         __syncwarp();
         updateBound(w, hl, K);
@@ -306,7 +311,10 @@ template <class T> __global__ void __launch_bounds__(32 * CSS_HALF_WPB, CSS_HALF
                         w.rax[q] = e[0], w.ray[q] = e[1], w.rbx[q] = e[2], w.rby[q] = e[3], w.rt0[q] = e[4], w.rt1[q] = e[5];
                         w.rcg[q] = double2{e[6], e[7]};
                         const long long mp = __double_as_longlong(e[8]);
-                        w.rmeta[q] = (int)(mp & 0xFFFFFFFFll), w.rpsv[q] = (unsigned char)(mp >> 32);
+                        const int psvr = (int)(mp >> 32) & 0xFF;
+                        w.rmeta[q] = (int)(mp & 0xFFFFFFFFll), w.rpsv[q] = (unsigned char)psvr;
+                        const v2 Ar{e[0], e[1]}, Br{e[2], e[3]};
+                        w.rlb[q] = (float)w.D[min(psvr, W::V)] + fsegDist(f2{0.f, 0.f}, tof2(lerp2(Ar, Br, e[4])), tof2(lerp2(Ar, Br, e[5]))) * (1.f - 1e-5f);
                     }
                     tail += n, spillN -= n;
                 }
@@ -344,7 +352,9 @@ template <class T> __global__ void __launch_bounds__(32 * CSS_HALF_WPB, CSS_HALF
                 const v2 P0 = lerp2(A, B, t0), P1 = lerp2(A, B, t1);
                 const float fsg = (float)sg;
                 const f2 fO{0.f, 0.f};
-                if (fsg + fsegDist(fO, tof2(P0), tof2(P1)) * (1.f - 1e-5f) > fUb) active = false; // bound tightened since the push
+                // The bound may have tightened since the push: the lower bound computed then is checked again.  (Should sigma have
+                // dropped since, the stored bound is too high; the vertex is dirty in that case and its fan is spawned afresh.)
+                if (wp.rlb[p] > fUb) active = false;
                 // ---- unfold the entered face: apex C from the edge frame; corners / neighbours / edge indices rotated by e
                 const unsigned fvw = *reinterpret_cast<const unsigned*>(&wp.fvert[g]), faw = *reinterpret_cast<const unsigned*>(&wp.fadj[g]);
                 const unsigned fv3 = fvw & 0xFFFFFFu, fa3 = faw & 0xFFFFFFu, kb = (fvw >> 24) & 63u;
@@ -433,7 +443,8 @@ template <class T> __global__ void __launch_bounds__(32 * CSS_HALF_WPB, CSS_HALF
                     const f2 fX = j ? fC : fA, fY = j ? fB : fC, fO2 = j ? fA : fB;
                     const float dX = j ? fDC : fDA, dY = j ? fDB : fDC, dO = j ? fDA : fDB;
                     const f2 X0 = flerp(fX, fY, (float)m0), X1 = flerp(fX, fY, (float)m1);
-                    const bool reach = fsg + fsegDist(fO, X0, X1) <= fUb;
+                    const float lbc = fsg + fsegDist(fO, X0, X1) * (1.f - 1e-5f);
+                    const bool reach = lbc <= fUb;
                     const float keep = 1.f - 2e-5f;
                     const float s0 = (fsg + flen(X0.x, X0.y)) * keep, s1 = (fsg + flen(X1.x, X1.y)) * keep;
                     const f2 Xn = j ? X1 : X0; // the end of the child interval next to the parent edge
@@ -456,7 +467,7 @@ template <class T> __global__ void __launch_bounds__(32 * CSS_HALF_WPB, CSS_HALF
                             const int q = ((src ? tail1 : tail0) + rank) & MASKR;
                             wp.rax[q] = X.x, wp.ray[q] = X.y, wp.rbx[q] = Y.x, wp.rby[q] = Y.y;
                             wp.rt0[q] = m0, wp.rt1[q] = m1, wp.rmeta[q] = cmeta, wp.rpsv[q] = psv;
-                            wp.rcg[q] = ccg;
+                            wp.rcg[q] = ccg, wp.rlb[q] = lbc;
                         }
                         tail += toth;
                     } else {
@@ -466,7 +477,7 @@ template <class T> __global__ void __launch_bounds__(32 * CSS_HALF_WPB, CSS_HALF
                                 const int q = ((src ? tail1 : tail0) + rank) & MASKR;
                                 wp.rax[q] = X.x, wp.ray[q] = X.y, wp.rbx[q] = Y.x, wp.rby[q] = Y.y;
                                 wp.rt0[q] = m0, wp.rt1[q] = m1, wp.rmeta[q] = cmeta, wp.rpsv[q] = psv;
-                                wp.rcg[q] = ccg;
+                                wp.rcg[q] = ccg, wp.rlb[q] = lbc;
                             } else if ((src ? sp1 : sp0) + rank < SPILL_CAP) {
                                 double* e = spillPair + ((size_t)src * SPILL_CAP + (src ? sp1 : sp0) + rank) * SPILL_DOUBLES;
                                 e[0] = X.x, e[1] = X.y, e[2] = Y.x, e[3] = Y.y, e[4] = m0, e[5] = m1, e[6] = ccg.x, e[7] = ccg.y;

@@ -30,6 +30,7 @@ namespace {
 template <class T, bool LEAN> struct WinSmem { // per-warp workspace
     static constexpr int F = T::MAXF, V = T::MAXV, K = T::MAXK, R = T::RING;
     static constexpr bool lean = LEAN;
+    static constexpr bool ringLb = false; // (the two-sources-per-warp kernel carries a lower bound per ring entry)
     double2 geo[LEAN ? 1 : 3 * F];
     double vx[LEAN ? 1 : V], vy[LEAN ? 1 : V], vz[LEAN ? 1 : V];
     int gface[LEAN ? F : 1], gvert[LEAN ? V : 1];
