@@ -26,16 +26,23 @@ def _stale(target, deps):
 def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     hdrs = [os.path.join(CSRC, h) for h in ("common.cuh", "kernels.h", "window_common.cuh")] + [os.path.join(HERE, "..", "include", "css_api.h")]
-    objs = []
+    objs, cmds = [], []
     for src, extra in UNITS:
         s = os.path.join(CSRC, src)
         o = os.path.join(CSRC, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + hdrs):
-            cmd = [nvcc] + ARCH + COMMON + extra + ["-c", s, "-o", o]
+            cmds.append([nvcc] + ARCH + COMMON + extra + ["-c", s, "-o", o])
+    if cmds:  # the translation units are independent: compile them side by side
+        from concurrent.futures import ThreadPoolExecutor
+
+        def run(cmd):
             if verbose:
                 print(" ".join(cmd), file=sys.stderr)
             subprocess.check_call(cmd)
+
+        with ThreadPoolExecutor(max_workers=min(len(cmds), os.cpu_count() or 1)) as ex:
+            list(ex.map(run, cmds))
     if force or _stale(LIB, objs):
         cmd = [nvcc] + ARCH + ["-shared", "-o", LIB] + objs + ["-lnccl", "-Xlinker", "--no-undefined"]
         if verbose:
