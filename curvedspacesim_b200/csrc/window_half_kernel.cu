@@ -365,7 +365,7 @@ template <class T> __global__ void __launch_bounds__(32 * CSS_HALF_WPB, CSS_HALF
                 const v2 C{fma(cg.x, AB.x, fma(-cg.y, AB.y, A.x)), fma(cg.x, AB.y, fma(cg.y, AB.x, A.y))};
                 nWin += active && j == 0;
                 unsigned tm = (active && j == 0) ? wp.tmask[g] : 0u; // the even lane of the pair answers the queries
-                __syncwarp(); // every slot of this pass is read before anybody pushes
+                // (every slot of this pass is read before anybody pushes: the barrier after the vertex update below separates them)
                 // ---- queries: targets inside the entered face (rare: ~K/nF of the windows enter a face that holds a target)
                 while (__any_sync(FULL, tm != 0)) {
                     bool improvedT = false;
