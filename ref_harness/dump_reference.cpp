@@ -9,7 +9,8 @@
 // corner order in both files is the reference's own (getVertexIndicesFromFace), so no permutation is applied anywhere.
 // out.bin holds, little-endian: N, the neighbour CSR (offsets[N+1] int32, idx, dist f64, startTangent[.][3] f64,
 // endTangent[.][3] f64) from simpleModel::findNeighbors-equivalent calls of triangulatedMeshSpace::distance, the forces
-// (harmonicRepulsion k = 1, sigma = range), and the state (face, bary, vel, force) after nveSteps velocity-Verlet steps.
+// (harmonicRepulsion k = 1, sigma = range), the state (face, bary, vel, force) after nveSteps velocity-Verlet steps, and an
+// R3PositionsToMeshPositions block (points, faces, clamped weights) for css_locate.
 // tests/test_reference_dumps.py compares the oracle AND the CUDA path against every such file found under
 // tests/golden/reference_dumps/ (bars: bit-exact lists/faces, 1e-9 distances/tangents, 1e-8 forces, 1e-6 trajectories).
 #include "cellListNeighborStructure.h"
@@ -117,6 +118,22 @@ int main(int argc, char* argv[])
     simulator->addUpdater(nve, configuration);
     for (int s = 0; s < steps; ++s) simulator->performTimestep();
     putState(out, *configuration);
+
+    // optional trailing block (css_locate): the R^3 coordinates of the final state, nudged off the surface by 1e-9 along x,
+    // go through simpleModel::R3PositionsToMeshPositions (simpleModel.cpp:136-154); written as M, xyz[M][3], face[M], bary[M][3]
+    {
+    std::vector<meshPosition> finalE;
+    meshSpace->meshPositionToEuclideanLocation(configuration->positions, finalE);
+    std::vector<point3> r3;
+    for (int i = 0; i < N; ++i) r3.push_back(point3(finalE[i].x[0] + 1e-9, finalE[i].x[1], finalE[i].x[2]));
+    std::vector<meshPosition> located;
+    configuration->R3PositionsToMeshPositions(meshSpace->surface, r3, located);
+    int M = (int)located.size();
+    put(out, &M, 4);
+    for (int i = 0; i < M; ++i) for (int k = 0; k < 3; ++k) { double v = r3[i][k]; put(out, &v, 8); }
+    for (int i = 0; i < M; ++i) put(out, &located[i].faceIndex, 4);
+    for (int i = 0; i < M; ++i) for (int k = 0; k < 3; ++k) { double v = located[i].x[k]; put(out, &v, 8); }
+    }
     fclose(out);
     printf("dumped %d particles, %d neighbour pairs, %d NVE steps\n", N, off, steps);
     return 0;

@@ -34,8 +34,24 @@ def _load(path):
     d = {"N": N, "off": off, "idx": take(tot, np.int32), "dist": take(tot, np.float64), "ts": take(3 * tot, np.float64).reshape(tot, 3),
          "te": take(3 * tot, np.float64).reshape(tot, 3), "frc": take(3 * N, np.float64).reshape(N, 3), "face": take(N, np.int32),
          "bary": take(3 * N, np.float64).reshape(N, 3), "vel": take(3 * N, np.float64).reshape(N, 3), "frc_end": take(3 * N, np.float64).reshape(N, 3)}
+    if o < len(raw):  # trailing R3PositionsToMeshPositions block (dumps made by the current ref_harness)
+        M = int(take(1, np.int32)[0])
+        d["loc_xyz"] = take(3 * M, np.float64).reshape(M, 3)
+        d["loc_face"] = take(M, np.int32)
+        d["loc_bary"] = take(3 * M, np.float64).reshape(M, 3)
     assert o == len(raw)
     return d
+
+
+def _compare_locate(locate, ref):
+    """PMP::locate_with_AABB_tree + the reference's clamp against css_locate / the oracle: same face except where the point is
+    equidistant from two faces (the documented tie rule), weights to 1e-9."""
+    if "loc_xyz" not in ref:
+        pytest.skip("this dump has no R3PositionsToMeshPositions block")
+    f, b = locate(ref["loc_xyz"])
+    same = f == ref["loc_face"]
+    assert same.mean() > 0.99
+    assert np.max(np.abs(b[same] - ref["loc_bary"][same])) < 1e-9
 
 
 def _case(path):
@@ -74,6 +90,7 @@ def test_oracle_against_reference_dump(path):
     kind, params = force_params("harmonic", k=1.0, sigma=meta["range"])
     _compare("oracle", meta, face, bary, vel, ref, orc.set_state, orc.find_neighbors, lambda: orc.compute_forces(kind, params),
              lambda dt, n: orc.run_nve(kind, params, dt, n), orc.get_state)
+    _compare_locate(orc.locate, ref)
 
 
 @pytest.mark.gpu
@@ -95,3 +112,4 @@ def test_cuda_against_reference_dump(path, gpu_ctx_factory):
 
     _compare("cuda", meta, face, bary, vel, ref, ctx.set_state, lambda r: ctx.find_neighbors(r, want_end=True), forces,
              lambda dt, n: ctx.step_nve(kind, params, dt, n), ctx.get_state)
+    _compare_locate(ctx.locate, ref)
