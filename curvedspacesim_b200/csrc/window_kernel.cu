@@ -1,5 +1,7 @@
 // Stage 2 of the many-source geodesic path: exact window propagation on the patch records written by
-// patch_kernel.cu, ONE WARP PER SOURCE, the patch staged in shared memory.
+// patch_kernel.cu, ONE WARP PER SOURCE, the patch staged in shared memory.  This is the kernel of tier 1 (TierLarge records:
+// big patches, many candidates, coarse meshes) and of CSS_WIN_HALF=0; tier 0 runs window_half_kernel.cu (two sources per
+// warp), which shares the helpers of window_common.cuh with this file.
 //
 // Replaces CGAL::Surface_mesh_shortest_path as the reference uses it per source
 // (src/models/triangulatedMeshSpace.cpp:189-203: add_source_point, build_sequence_tree, then
@@ -8,8 +10,8 @@
 // velocity-Verlet half kick (src/updaters/velocityVerletNVE.cpp:27-28).
 //
 // Algorithm: Chen-Han window unfolding with the Xin-Wang vertex-distance filter; saddle and patch-border
-// vertices are pseudo-sources.  Windows live in a FIFO ring in shared memory and are propagated 32 at a
-// time, one per lane; children are compacted into the ring with a ballot-free shuffle scan.  A window is
+// vertices are pseudo-sources.  Windows live in a FIFO ring in shared memory and are propagated 16 at a
+// time, a pair of lanes per window (one child edge each); children are compacted into the ring with a ballot.  A window is
 // (A, B, S, t0, t1, sigma): the entered edge A->B and the image S of its (pseudo-)source in one common
 // unfolded 2-D frame, the visible interval [t0, t1] of the edge, and the distance sigma from the true source
 // to the pseudo-source.  Unfolding across a face is four FMAs with the precomputed edge frames
