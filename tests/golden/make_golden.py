@@ -12,6 +12,9 @@ absent; it is C++), so there are two kinds of fixture, both produced by code in 
   oracle_regression.npz     outputs of the CPU oracle on small seeded configurations (neighbour lists,
                             distances, tangents, forces, state after 50 NVE steps).  A regression guard for the
                             oracle itself and a second, travel-able comparison target for the GPU tests.
+  locate_regression.npz     R^3 points and the mesh positions the oracle's R3PositionsToMeshPositions restatement
+                            assigns to them (the oracle is checked against an independent numpy closest-point
+                            formulation in tests/test_oracle_model.py); same two roles.
 """
 from __future__ import annotations
 
@@ -112,6 +115,31 @@ def oracle_cases():
     np.savez_compressed(os.path.join(HERE, "oracle_regression.npz"), names=np.array(names), **out)
 
 
+def locate_points(V, corners, seed=3):
+    """On-surface (nudged by 1e-9), clearly off-surface, far away, on vertices, on edge midpoints, the origin."""
+    rng = np.random.default_rng(seed)
+    face0, bary0 = random_positions(len(corners), 300, rng)
+    on = np.einsum("nk,nkd->nd", bary0, V[corners[face0]])
+    ext = float(np.abs(V).max())
+    return np.concatenate([on + 1e-9 * rng.standard_normal((300, 3)), on + 0.05 * ext * rng.standard_normal((300, 3)),
+                           4.0 * ext * rng.standard_normal((50, 3)), V[:50], 0.5 * (V[corners[:50, 1]] + V[corners[:50, 2]]),
+                           np.zeros((1, 3))])
+
+
+def locate_cases():
+    from oracle_binding import Oracle
+
+    out, names = {}, []
+    for name in ("icosphere16", "torus60x24"):
+        V, F = golden_mesh(name)
+        corners = meshes.reference_corners(F)
+        P = locate_points(V, corners)
+        f, b = Oracle(V, corners).locate(P)
+        names.append(name)
+        out[name + "/xyz"], out[name + "/face"], out[name + "/bary"] = P, f, b
+    np.savez_compressed(os.path.join(HERE, "locate_regression.npz"), names=np.array(names), **out)
+
+
 def closed_form():
     """(mesh name, source point, target point, distance) tuples with analytically known answers."""
     rows = []
@@ -130,10 +158,12 @@ def closed_form():
 
 
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["closed", "oracle", "brute"]
+    what = sys.argv[1:] or ["closed", "oracle", "brute", "locate"]
     if "closed" in what:
         closed_form()
     if "oracle" in what:
         oracle_cases()
     if "brute" in what:
         brute_cases()
+    if "locate" in what:
+        locate_cases()

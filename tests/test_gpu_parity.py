@@ -466,6 +466,20 @@ def test_golden_oracle_regression(gpu_ctx_factory):
         assert np.max(np.abs(b2 - g[key + "/bary50"])) < 1e-9 and np.max(np.abs(v2 - g[key + "/vel50"])) < 1e-9
 
 
+def test_golden_locate(gpu_ctx_factory):
+    """css_locate against the committed fixture tests/golden/locate_regression.npz (points on / off / far from the surface, on
+    vertices and edges): same faces, same clamped weights."""
+    g = np.load(os.path.join(GOLDEN, "locate_regression.npz"))
+    for name in g["names"]:
+        name = str(name)
+        V, F = _mesh(name)
+        ctx = gpu_ctx_factory()
+        ctx.set_mesh(V, meshes.reference_corners(F))
+        f, b = ctx.locate(g[name + "/xyz"])
+        assert np.array_equal(f, g[name + "/face"])
+        assert np.max(np.abs(b - g[name + "/bary"])) < 1e-12
+
+
 # ------------------------------------------------------------------------------ edge cases / errors
 def test_edge_cases(gpu_ctx_factory):
     V, F = _mesh("icosphere16")

@@ -15,6 +15,10 @@ from curvedspacesim_b200 import meshes
 from helpers import csr_rows, interaction_range, make_state, random_positions, random_velocities
 from oracle_binding import Oracle, force_params
 
+import os
+
+from helpers import GOLDEN as GOLDEN_DIR
+
 
 def _setup(V, F, N, seed=13377, area_fraction=0.9):
     corners, face, bary, vel = make_state(V, F, N, seed=seed)
@@ -506,3 +510,18 @@ def test_locate_finds_the_closest_face_and_clamps_like_the_reference():
         w[1] = w[1] / (w[0] + w[1] + w[2])
         w[2] = w[2] / (w[0] + w[1] + w[2])
         assert np.array_equal(bv[0], np.array(w))
+
+
+def test_locate_matches_its_committed_fixture():
+    """tests/golden/locate_regression.npz (tests/golden/make_golden.py locate) is what the GPU test also compares with."""
+    import sys
+
+    sys.path.insert(0, GOLDEN_DIR)
+    from make_golden import golden_mesh
+
+    g = np.load(os.path.join(GOLDEN_DIR, "locate_regression.npz"))
+    for name in g["names"]:
+        name = str(name)
+        V, F = golden_mesh(name)
+        f, b = Oracle(V, meshes.reference_corners(F)).locate(g[name + "/xyz"])
+        assert np.array_equal(f, g[name + "/face"]) and np.array_equal(b, g[name + "/bary"])
