@@ -466,20 +466,6 @@ def test_golden_oracle_regression(gpu_ctx_factory):
         assert np.max(np.abs(b2 - g[key + "/bary50"])) < 1e-9 and np.max(np.abs(v2 - g[key + "/vel50"])) < 1e-9
 
 
-def test_golden_locate(gpu_ctx_factory):
-    """css_locate against the committed fixture tests/golden/locate_regression.npz (points on / off / far from the surface, on
-    vertices and edges): same faces, same clamped weights."""
-    g = np.load(os.path.join(GOLDEN, "locate_regression.npz"))
-    for name in g["names"]:
-        name = str(name)
-        V, F = _mesh(name)
-        ctx = gpu_ctx_factory()
-        ctx.set_mesh(V, meshes.reference_corners(F))
-        f, b = ctx.locate(g[name + "/xyz"])
-        assert np.array_equal(f, g[name + "/face"])
-        assert np.max(np.abs(b - g[name + "/bary"])) < 1e-12
-
-
 # ------------------------------------------------------------------------------ edge cases / errors
 def test_edge_cases(gpu_ctx_factory):
     V, F = _mesh("icosphere16")
@@ -848,3 +834,18 @@ def test_two_gpus_bitwise_equal_to_one(tmp_path):
         b = np.load(os.path.join(out, "world%d_rank%d_nccl.npz" % (world, r)))
         for k in ("face2", "bary2", "vel2", "frc2", "ke"):
             assert np.array_equal(a[k], b[k]), k
+
+
+# ------------------------------------------------------------------------------ committed fixture of css_locate
+def test_golden_locate(gpu_ctx_factory):
+    """css_locate against the committed fixture tests/golden/locate_regression.npz (points on / off / far from the surface, on
+    vertices and edges): same faces, same clamped weights."""
+    g = np.load(os.path.join(GOLDEN, "locate_regression.npz"))
+    for name in g["names"]:
+        name = str(name)
+        V, F = _mesh(name)
+        ctx = gpu_ctx_factory()
+        ctx.set_mesh(V, meshes.reference_corners(F))
+        f, b = ctx.locate(g[name + "/xyz"])
+        assert np.array_equal(f, g[name + "/face"])
+        assert np.max(np.abs(b - g[name + "/bary"])) < 1e-12
