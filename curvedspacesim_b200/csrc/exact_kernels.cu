@@ -349,7 +349,10 @@ __device__ __forceinline__ int walkOne(const MeshDev& m, int& face, double bary[
 }
 
 // particles [0,n) of this rank; global index = minIdx + i in face/bary
-__global__ void __launch_bounds__(64, 12) k_walk(MeshDev m, int n, int minIdx, int* __restrict__ face, double* __restrict__ bary, double* __restrict__ disp,
+#ifndef CSS_WALK_MINB
+#define CSS_WALK_MINB 12
+#endif
+__global__ void __launch_bounds__(64, CSS_WALK_MINB) k_walk(MeshDev m, int n, int minIdx, int* __restrict__ face, double* __restrict__ bary, double* __restrict__ disp,
                        double* __restrict__ vel, double* __restrict__ frc, int transportForce, int transportVelocity, int mode,
                        double dt, int* __restrict__ flagsOut, unsigned long long* __restrict__ counters, PeerWin pw)
 {

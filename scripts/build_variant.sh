@@ -6,7 +6,7 @@ NAME=$1; shift
 D=curvedspacesim_b200/csrc
 OUT=/tmp/variant_$NAME; mkdir -p $OUT
 COMMON="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden"
-nvcc $COMMON -fmad=false -c $D/exact_kernels.cu -o $OUT/exact.o &
+nvcc $COMMON -fmad=false "$@" -c $D/exact_kernels.cu -o $OUT/exact.o &
 nvcc $COMMON "$@" -c $D/geodesic_kernel.cu -o $OUT/geo.o &
 nvcc $COMMON "$@" -c $D/patch_kernel.cu -o $OUT/patch.o &
 nvcc $COMMON "$@" -c $D/window_kernel.cu -o $OUT/win.o &
