@@ -34,7 +34,7 @@ API_SYMBOLS = [
     "css_get_walk_flags", "css_step_nve", "css_step_nve_host", "css_step_gd", "css_nvt_init", "css_step_nvt", "css_nvt_state", "css_fire_init",
     "css_fire_minimize", "css_max_force", "css_force_norm", "css_comm_unique_id", "css_comm_init", "css_comm_info", "css_gather_positions",
     "css_reduce", "css_counters", "css_synchronize", "css_device_positions", "css_last_kernel_ms", "css_set_timing", "css_last_stage_ms",
-    "css_timer_record", "css_timer_elapsed_ms",
+    "css_timer_record", "css_timer_elapsed_ms", "css_microbench",
 ]
 
 _lib = None
@@ -355,6 +355,12 @@ class Context:
         p, w, r, g = C.c_float(), C.c_float(), C.c_float(), C.c_float()
         self._ck(self.L.css_last_stage_ms(self.h, C.byref(p), C.byref(w), C.byref(r), C.byref(g)))
         return {"patch_ms": p.value, "window_ms": w.value, "retry_ms": r.value, "gather_ms": g.value}
+
+    def microbench(self, what, reps=5):
+        """Measured device ceiling: what = 0 FP64 FMA TFLOP/s, 1 L2 read GB/s."""
+        v = C.c_double()
+        self._ck(self.L.css_microbench(self.h, int(what), int(reps), C.byref(v)))
+        return v.value
 
     def timer_record(self, slot):
         self._ck(self.L.css_timer_record(self.h, int(slot)))

@@ -1705,5 +1705,17 @@ int css_timer_elapsed_ms(css_ctx* ctx, int slotA, int slotB, float* ms)
     return CSS_OK;
 }
 
+int css_microbench(css_ctx* ctx, int what, int reps, double* value)
+{
+    if (!ctx || !value || what < 0 || what > 1 || reps < 1) return CSS_EINVAL;
+    BIND();
+    CU(cudaStreamSynchronize(ctx->st));
+    double v = runMicrobench(ctx->st, ctx->numSMs, what, reps);
+    ctx->hostKernels += (unsigned long long)reps + 1;
+    if (v < 0) return fail(ctx, CSS_ECUDA, "css_microbench: launch failed");
+    *value = v;
+    return CSS_OK;
+}
+
 } // extern "C"
 #pragma GCC visibility pop

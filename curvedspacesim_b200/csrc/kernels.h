@@ -207,4 +207,6 @@ void launchEnergy(cudaStream_t st, int nLocal, int kmax, const int* nbrCount, co
 void launchStress(cudaStream_t st, int nLocal, int kmax, const int* nbrCount, const double* nbrDist, const double* nbrTs, const double* vel,
                   ForceParams fp, double* partial, double* out); // out[18]: sum f (x) dr | sum v (x) v
 
+double runMicrobench(cudaStream_t st, int numSMs, int what, int reps); // microbench.cu: 0 FP64 FMA TFLOP/s, 1 L2 read GB/s
+
 } // namespace css

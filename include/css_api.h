@@ -179,6 +179,10 @@ int css_last_stage_ms(css_ctx* ctx, float* patch_ms, float* window_ms, float* re
 /* CUDA-event stopwatch on the context's own stream (slots 0..7) */
 int css_timer_record(css_ctx* ctx, int slot);
 int css_timer_elapsed_ms(css_ctx* ctx, int slotA, int slotB, float* ms); /* synchronises on slotB */
+/* measured ceilings of this device for the roofline statements (replaces nothing in the reference; its profiler.h:16-58 is a
+ * wall clock).  what = 0: double-precision FMA rate in TFLOP/s (8 independent FMA chains per thread, whole chip);
+ * what = 1: L2 -> SM read bandwidth in GB/s over a 32 MiB buffer.  Best of `reps` CUDA-event-timed launches. */
+int css_microbench(css_ctx* ctx, int what, int reps, double* value);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,380 @@
+"""BASELINE.json configs[0..2] on the reference's own example meshes at the stated particle counts.
+
+The OFF files under tests/golden/meshes/ are copies of /root/reference/exampleMeshes/*.off (test fixtures,
+data only).  Call shapes follow the reference mains:
+  config 1  curvedSpaceSimulation.cpp:72-147 (-z 2): sphere_radius1.off, N=100, harmonic k=1 sigma=r_c, NVE dt=0.01,
+            1000 steps, r_c = 2 sqrt(0.9 A / (N pi)) (:75-76), submeshing at r_c, cell list.
+  config 2  torusrb20.off, N=2000, gaussianRepulsion(alpha=1, sigma=r_c/2) with maximumInteractionRange = r_c
+            (SURVEY.md 8(d) config 2), NVE dt=0.01.
+  config 3  triangulatedElephant.off (genus 3, edge ratio 13x), N=5000, harmonic: FIRE (curvedSpaceSimulation -z 0,
+            defaults of fireMinimization.h:50-61, capped at 200 iterations) then Nose-Hoover M=2 tau=1 T=0.2 dt=0.01,
+            2 x 1000 steps (curvedSpaceNVTSim.cpp:101,111).
+
+CPU tests (not gpu) pin what can be pinned without CGAL on these meshes: the oracle against the literal
+transcriptions, the meshTesting.cpp:103-204 full-mesh / submesh self-consistency, the strict-trig walker variant,
+and the independent brute-force unfolding checker on patches cut from the elephant.  GPU tests compare the CUDA
+path with the oracle at the north-star bars."""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import pytest
+
+from curvedspacesim_b200 import meshes
+from helpers import GOLDEN, csr_rows, interaction_range, make_state, random_positions, random_velocities
+from oracle_binding import Oracle, force_params
+
+TOL_DIST = 1e-9     # relative, geodesic distances
+TOL_TAN = 1e-9      # absolute on unit tangents
+TOL_FORCE = 1e-8    # relative to the largest force component
+TOL_TRAJ = 1e-6     # positions / velocities after 1000 steps
+
+MESHDIR = os.path.join(GOLDEN, "meshes")
+CONFIGS = {
+    # name: (file, N, potential)
+    "cfg1": ("sphere_radius1.off", 100, "harmonic"),
+    "cfg2": ("torusrb20.off", 2000, "gaussian"),
+    "cfg3": ("triangulatedElephant.off", 5000, "harmonic"),
+}
+# FIRE defaults of fireMinimization.h:50-61 with the iteration cap of config 3 (p[1] is ignored, fireMinimization.cpp:74-90)
+FIRE_P = np.array([200, 0.001, 0.99, 0.1, 1e-5, 1.1, 0.95, 0.9, 4, 1e-12, 0.0])
+
+
+def load(name):
+    fn, N, pot = CONFIGS[name]
+    V, F = meshes.load_off(os.path.join(MESHDIR, fn))
+    return V, F, N, pot
+
+
+def setup_oracle(name, threads=8, seed=13377):
+    V, F, N, pot = load(name)
+    corners, face, bary, vel = make_state(V, F, N, seed=seed)
+    orc = Oracle(V, corners)
+    _, _, area = orc.mesh_info()
+    rc = interaction_range(area, N, 0.9)
+    if pot == "harmonic":
+        kind, params = force_params("harmonic", k=1.0, sigma=rc)
+    else:
+        kind, params = force_params("gaussian", alpha=1.0, sigma=0.5 * rc, range=rc)
+    orc.set_submeshing(True, rc)
+    orc.set_options(True, False, threads)
+    orc.set_state(face, bary, vel)
+    return orc, V, F, corners, face, bary, vel, N, rc, kind, params
+
+
+def setup_gpu(gpu, V, corners, face, bary, vel, rc, want_end=True):
+    ctx = gpu()
+    ctx.set_mesh(V, corners)
+    ctx.set_submeshing(True, rc)
+    ctx.set_options(True, want_end)
+    ctx.set_state(face, bary, vel)
+    return ctx
+
+
+def _rel(a, b):
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300))) if len(a) else 0.0
+
+
+# =============================================================================== CPU: what can be pinned without CGAL
+def test_fixture_meshes_match_survey_statistics():
+    """V, F, Euler characteristic, closedness and area of the three config meshes."""
+    expect = {"cfg1": (2432, 4860, 2, 12.5506), "cfg2": (2235, 4470, 0, 117.910), "cfg3": (2775, 5558, -4, 1.2450)}
+    for name, (nv, nf, chi, area) in expect.items():
+        V, F, _, _ = load(name)
+        adj, _ = meshes.build_adjacency(meshes.reference_corners(F))
+        assert (len(V), len(F)) == (nv, nf) and (adj >= 0).all()
+        assert len(V) - 3 * len(F) // 2 + len(F) == chi
+        assert abs(meshes.face_areas(V, F).sum() - area) < 1e-3 * area
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3"])
+def test_oracle_candidates_and_patches_follow_the_literal_transcriptions(name):
+    """Cell-list candidate order and submesher face sets on the real meshes, against tests/pyref.py (pure-Python literal
+    transcriptions of cellListNeighborStructure.cpp:45-84 / hyperRectangularCellList.cpp and submesher.cpp:55-147)."""
+    import pyref
+
+    orc, V, F, corners, face, bary, vel, N, rc, kind, params = setup_oracle(name, threads=1)
+    off, idx, maxd = orc.candidates(rc)
+    mn, mx, _ = orc.mesh_info()
+    eucl = orc.euclidean(face, bary)
+    sel = np.arange(N) if N <= 200 else np.random.default_rng(3).choice(N, 200, replace=False)
+    rows = csr_rows(off, idx)
+    adj, _ = orc.adjacency()
+    cands, Rs = pyref.candidate_lists(eucl, mn, mx, rc)
+    assert [list(r) for r in rows] == cands
+    for i in sel:
+        cand, R = cands[i], Rs[i]
+        if not cand:
+            continue
+        assert R == maxd[i]
+        tf = face[rows[i]]
+        got = set(orc.patch(int(face[i]), bary[i], tf, min(rc, R)).tolist())
+        want = pyref.patch_faces(V, corners, adj, int(face[i]), eucl[i], tf.tolist(), min(rc, R))
+        assert got == want
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3"])
+def test_oracle_full_mesh_vs_submesh_self_consistency(name):
+    """meshTesting.cpp:103-204: sum over targets with d_full < cutoff of (d_full - d_submesh) is ~0.  A patch geodesic can
+    only be longer than the full-mesh one, and only when the full-mesh path leaves the patch (it cannot when d < R')."""
+    orc, V, F, corners, face, bary, vel, N, rc, kind, params = setup_oracle(name, threads=1)
+    off, idx, d_sub, _, _ = orc.find_neighbors(rc)
+    rows = csr_rows(off, idx)
+    drow = csr_rows(off, d_sub)
+    rng = np.random.default_rng(11)
+    total, n = 0.0, 0
+    for i in rng.choice(N, 40, replace=False):
+        if len(rows[i]) == 0:
+            continue
+        orc.set_submeshing(False)
+        d_full = orc.distance(int(face[i]), bary[i], face[rows[i]], bary[rows[i]])[0]
+        orc.set_submeshing(True, rc)
+        assert np.all(drow[i] >= d_full * (1 - 1e-12))
+        inside = d_full < rc
+        total += float(np.sum(np.abs(d_full[inside] - drow[i][inside])))
+        n += int(inside.sum())
+    assert n > 20
+    assert total < 1e-10 * n * rc
+
+
+def test_strict_trig_walker_agrees_with_the_libm_free_rotation():
+    """the walker's one arithmetic deviation (cos = n.n', sin = |n x n'| instead of acos -> sin / cos,
+    functionUtilities.cpp:19-20) against the oracle's strictTrig switch on 20 000 random walks: same faces, barycentrics
+    and transported vectors to 1e-13 (measured ~1e-15 per crossing)."""
+    V, F, _, _ = load("cfg1")
+    corners = meshes.reference_corners(F)
+    rng = np.random.default_rng(17)
+    n = 20000
+    face, bary = random_positions(len(F), n, rng)
+    vel = random_velocities(V, corners, face, 1.0, rng)
+    disp = vel * rng.uniform(0.01, 1.5, n)[:, None]   # 0 .. ~30 edge crossings
+    vecs = random_velocities(V, corners, face, 1.0, rng).reshape(n, 1, 3)
+    a = Oracle(V, corners)
+    b = Oracle(V, corners)
+    b.set_options(True, True, 1)  # strict reference trig
+    fa, ba, da, va, fla, cra = a.transport(face, bary, disp, vecs)
+    fb, bb, db, vb, flb, crb = b.transport(face, bary, disp, vecs)
+    assert cra.sum() > 5 * n
+    ok = (fla == 0) & (flb == 0)
+    assert ok.mean() > 0.999
+    same = fa == fb
+    # a path may legitimately end within round-off of an edge and resolve to either side: allow a handful, compare the rest
+    assert (~same[ok]).sum() <= 3
+    m = ok & same
+    assert np.max(np.abs(ba[m] - bb[m])) < 1e-13 * np.maximum(1, cra.max())
+    assert np.max(np.abs(va[m] - vb[m])) < 1e-13 * np.maximum(1, cra.max())
+
+
+def test_bruteforce_unfolding_on_patches_cut_from_the_elephant():
+    """Independent exhaustive-unfolding checker (tests/bruteforce_geodesic.py, no shared code with the oracle) on patches
+    of the genus-3 elephant: distances of the oracle's patch-restricted geodesics agree to 1e-9."""
+    import bruteforce_geodesic as bf
+
+    orc, V, F, corners, face, bary, vel, N, rc, kind, params = setup_oracle("cfg3", threads=1)
+    off, idx, d_sub, _, _ = orc.find_neighbors(rc)
+    rows, drow = csr_rows(off, idx), csr_rows(off, d_sub)
+    saddle = orc.saddle()
+    checked = 0
+    order = np.random.default_rng(5).permutation(N)
+    for i in order:
+        if len(rows[i]) < 2:
+            continue
+        tf = face[rows[i]]
+        R = float(np.sqrt(np.max(np.sum((orc.euclidean(face[rows[i]], bary[rows[i]]) - orc.euclidean(face[[i]], bary[[i]])) ** 2, 1))))
+        pf = orc.patch(int(face[i]), bary[i], tf, min(rc, R))
+        if not (6 <= len(pf) <= 22):
+            continue
+        gv = np.unique(corners[pf])
+        if saddle[gv].sum() == 0:
+            continue  # want saddle vertices (pseudo-source candidates) inside the patch
+        want, ts, te = bf.BruteGeodesic(V, corners, faces=pf).solve(int(face[i]), bary[i], tf, bary[rows[i]])
+        ok = np.isfinite(want)
+        assert ok.any()
+        assert np.max(np.abs(want[ok] - drow[i][ok]) / want[ok]) < 1e-9
+        if (~ok).any():  # unreachable inside the patch: the reference's sentinel (triangulatedMeshSpace.cpp:198-203)
+            assert np.all(drow[i][~ok] == 2 * rc)
+        checked += 1
+        if checked == 12:
+            break
+    assert checked == 12
+
+
+# =============================================================================== GPU parity at the north-star bars
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3"])
+def test_real_mesh_neighbours_distances_tangents_forces(name, gpu_ctx_factory):
+    orc, V, F, corners, face, bary, vel, N, rc, kind, params = setup_oracle(name)
+    ctx = setup_gpu(gpu_ctx_factory, V, corners, face, bary, vel, rc)
+    assert np.array_equal(orc.euclidean(face, bary), ctx.euclidean(face, bary))                # bit-exact
+    ctx.counters(reset=True)
+    o_off, o_idx, o_d, o_ts, o_te = orc.find_neighbors(rc)
+    g_off, g_idx, g_d, g_ts, g_te = ctx.find_neighbors(rc, want_end=True)
+    assert np.array_equal(o_off, g_off) and np.array_equal(o_idx, g_idx)                      # bit-exact, ordered
+    c, oc = ctx.counters(), orc.counters()
+    assert c["patch_faces"] == oc["patch_faces"] and c["patch_verts"] == oc["patch_verts"]    # identical patches
+    assert c["queries"] == len(o_idx) and c["overflow"] == 0 and c["kernels"] > 0
+    print("%s: K mean %.2f max %d, patch faces %.1f verts %.1f, pseudo-source fans gpu %d / oracle %d, ties oracle %d, "
+          "disconnected gpu %d / oracle %d, tier retries %d" % (name, len(o_idx) / N, np.diff(o_off).max(), c["patch_faces"] / N,
+                                                              c["patch_verts"] / N, c["pseudo_sources"], oc["pseudo_sources"], oc["ties"],
+                                                              c["disconnected"], oc["disconnected"], c["tier_retry"]))
+    assert c["disconnected"] == oc["disconnected"]
+    assert _rel(g_d, o_d) < TOL_DIST
+    assert np.max(np.abs(g_ts - o_ts)) < TOL_TAN and np.max(np.abs(g_te - o_te)) < TOL_TAN
+    f0 = orc.compute_forces(kind, params)
+    ctx.compute_forces(kind, params)
+    f1 = ctx.get_state()[3]
+    assert np.max(np.abs(f0 - f1)) < TOL_FORCE * np.abs(f0).max()
+    e0 = orc.compute_energy(kind, params)
+    assert abs(ctx.compute_energy(kind, params) - e0) < 1e-9 * abs(e0)
+    assert ctx.counters()["overflow"] == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3"])
+def test_real_mesh_full_mesh_vs_submesh_self_consistency_on_the_gpu(name, gpu_ctx_factory):
+    """meshTesting.cpp:103-204 through the C ABI: css_distance on the whole mesh against the submeshed neighbour distances."""
+    orc, V, F, corners, face, bary, vel, N, rc, kind, params = setup_oracle(name)
+    ctx = setup_gpu(gpu_ctx_factory, V, corners, face, bary, vel, rc)
+    off, idx, d_sub, _, _ = ctx.find_neighbors(rc)
+    rows, drow = csr_rows(off, idx), csr_rows(off, d_sub)
+    rng = np.random.default_rng(11)
+    total, n = 0.0, 0
+    ctx.set_submeshing(False)
+    for i in rng.choice(N, 25, replace=False):
+        if len(rows[i]) == 0:
+            continue
+        d_full = ctx.distance(int(face[i]), bary[i], face[rows[i]], bary[rows[i]])[0]
+        assert np.all(drow[i] >= d_full * (1 - 1e-12))
+        inside = d_full < rc
+        total += float(np.sum(np.abs(d_full[inside] - drow[i][inside])))
+        n += int(inside.sum())
+    ctx.set_submeshing(True, rc)
+    assert n > 10 and total < 1e-10 * n * rc
+
+
+def _traj_check(orc, ctx, flagged, tol=TOL_TRAJ):
+    of, ob, ov, ofr = orc.get_state()
+    gf, gb, gv, gfr = ctx.get_state()
+    ok = ~flagged
+    assert np.array_equal(of[ok], gf[ok])                                                       # face index: bit-exact
+    eo, eg = orc.euclidean(of, ob), orc.euclidean(gf, gb)
+    dev = float(np.max(np.abs(eo - eg)[ok])), float(np.max(np.abs(ov - gv)[ok]))
+    assert dev[0] < tol and dev[1] < tol
+    return dev
+
+
+@pytest.mark.gpu
+def test_config1_sphere_radius1_nve_1000_steps(gpu_ctx_factory):
+    orc, V, F, corners, face, bary, vel, N, rc, kind, params = setup_oracle("cfg1")
+    ctx = setup_gpu(gpu_ctx_factory, V, corners, face, bary, vel, rc, want_end=False)
+    orc.compute_forces(kind, params)
+    ctx.compute_forces(kind, params)
+    flagged = np.zeros(N, bool)
+    for _ in range(10):
+        orc.run_nve(kind, params, 0.01, 100)
+        ctx.step_nve(kind, params, 0.01, 100)
+        flagged |= (orc.walk_flags() != 0) | (ctx.walk_flags() != 0)
+    dev = _traj_check(orc, ctx, flagged)
+    c = ctx.counters()
+    print("cfg1 after 1000 steps: max |dx| %.2e |dv| %.2e, flagged %d, crossings %d, retries %d" % (dev[0], dev[1], flagged.sum(), c["crossings"], c["tier_retry"]))
+    assert flagged.sum() <= 2
+    assert c["overflow"] == 0 and c["walk_nohit"] == 0 and c["walk_nan"] == 0 and c["walk_itercap"] == 0
+
+
+@pytest.mark.gpu
+def test_config2_torusrb20_gaussian_nve_1000_steps(gpu_ctx_factory):
+    orc, V, F, corners, face, bary, vel, N, rc, kind, params = setup_oracle("cfg2")
+    ctx = setup_gpu(gpu_ctx_factory, V, corners, face, bary, vel, rc, want_end=False)
+    orc.compute_forces(kind, params)
+    ctx.compute_forces(kind, params)
+    flagged = np.zeros(N, bool)
+    for _ in range(10):
+        orc.run_nve(kind, params, 0.01, 100)
+        ctx.step_nve(kind, params, 0.01, 100)
+        flagged |= (orc.walk_flags() != 0) | (ctx.walk_flags() != 0)
+    dev = _traj_check(orc, ctx, flagged)
+    c = ctx.counters()
+    print("cfg2 after 1000 steps: max |dx| %.2e |dv| %.2e, flagged %d, crossings %d, fans %d, retries %d" % (dev[0], dev[1], flagged.sum(), c["crossings"], c["pseudo_sources"], c["tier_retry"]))
+    assert flagged.sum() <= 20
+    assert c["overflow"] == 0 and c["walk_nohit"] == 0 and c["walk_nan"] == 0 and c["walk_itercap"] == 0
+    of, _, _, ofr = orc.get_state()
+    gfr = ctx.get_state()[3]
+    assert np.max(np.abs(ofr - gfr)) < TOL_FORCE * np.abs(ofr).max() + TOL_TRAJ
+
+
+@pytest.mark.gpu
+def test_config3_elephant_fire_then_nose_hoover(gpu_ctx_factory):
+    orc, V, F, corners, face, bary, vel, N, rc, kind, params = setup_oracle("cfg3")
+    ctx = setup_gpu(gpu_ctx_factory, V, corners, face, bary, vel, rc, want_end=False)
+    # phase A: FIRE from the thermal initial state (curvedSpaceSimulation -z 0 keeps the Maxwell-Boltzmann velocities)
+    orc.fire_init(FIRE_P, dt0=0.001, alpha0=0.99)
+    ctx.fire_init(FIRE_P, dt0=0.001, alpha0=0.99)
+    _, o_out = orc.run_fire(kind, params)
+    g_out = ctx.fire_minimize(kind, params)
+    assert o_out[0] == g_out[0] == 200
+    assert abs(o_out[1] - g_out[1]) < 1e-8 * o_out[1] and o_out[2] == g_out[2] and o_out[3] == g_out[3]
+    of, ob, ov, ofr = orc.get_state()
+    gf, gb, gv, gfr = ctx.get_state()
+    fl = (orc.walk_flags() != 0) | (ctx.walk_flags() != 0)
+    assert np.array_equal(of[~fl], gf[~fl]) and np.max(np.abs(ob - gb)[~fl]) < 1e-9 and np.max(np.abs(ov - gv)[~fl]) < 1e-9
+    assert np.max(np.abs(ofr - gfr)[~fl]) < TOL_FORCE * np.abs(ofr).max()
+    # phase B: Nose-Hoover from the minimised positions with fresh Maxwell-Boltzmann velocities, 2 x 1000 steps
+    vel2 = random_velocities(V, corners, of, 0.2, np.random.default_rng(99))
+    orc.set_state(of, ob, vel2)
+    ctx.set_state(of, ob, vel2)
+    orc.compute_forces(kind, params)
+    ctx.compute_forces(kind, params)
+    orc.nvt_init(0.01, 0.2, tau=1.0, M=2)
+    ctx.nvt_init(0.01, 0.2, tau=1.0, M=2)
+    flagged = np.zeros(N, bool)
+    devs = []
+    for blk in range(20):
+        orc.run_nvt(kind, params, 100)
+        ctx.step_nvt(kind, params, 100)
+        flagged |= (orc.walk_flags() != 0) | (ctx.walk_flags() != 0)
+        if blk == 9:
+            devs.append(_traj_check(orc, ctx, flagged))            # the north-star bar: 1e-6 after 1000 steps
+        if blk == 19:
+            # beyond the bar: a 1e-16 perturbation of the walker (oracle strictTrig on/off) grows to 1e-7 by step 2000 here
+            devs.append(_traj_check(orc, ctx, flagged, tol=1e-5))
+    ob_, oke, osc = orc.nvt_state()
+    gb_, gke, gsc = ctx.nvt_state()
+    assert np.max(np.abs(ob_ - gb_)) < 1e-8 * max(1.0, np.abs(ob_).max()) and abs(oke - gke) < 1e-8 * oke
+    assert abs(ctx.temperature() - orc.temperature()) < 1e-8
+    c = ctx.counters()
+    print("cfg3: FIRE 200 it fmax %.3e; NH after 1000 steps |dx| %.2e |dv| %.2e, after 2000 |dx| %.2e |dv| %.2e; flagged %d; T %.4f; "
+          "fans %d, disconnected %d, retries %d" % (g_out[1], devs[0][0], devs[0][1], devs[1][0], devs[1][1], flagged.sum(), ctx.temperature(),
+                                                    c["pseudo_sources"], c["disconnected"], c["tier_retry"]))
+    assert c["overflow"] == 0 and c["walk_nohit"] == 0 and c["walk_nan"] == 0 and c["walk_itercap"] == 0
+    assert flagged.sum() <= 50
+
+
+@pytest.mark.gpu
+def test_vertex_aimed_displacements_are_flagged_and_bit_equal(gpu_ctx_factory):
+    """meshTesting.cpp:206-241 (branch -1): face 1 of torus_isotropic_remesh.off, from (0.4,0.3,0.3) along twice the chord to
+    (0.7,0.3,0) -- as coded it crosses the edge opposite corner 2, not a vertex -- and the same source aimed exactly at each
+    corner of its face (two edges hit at once: the vertex case).  GPU == oracle bit for bit, vertex events flagged."""
+    V, F = meshes.load_off(os.path.join(MESHDIR, "torus_isotropic_remesh.off"))
+    corners = meshes.reference_corners(F)
+    orc = Oracle(V, corners)
+    ctx = gpu_ctx_factory()
+    ctx.set_mesh(V, corners)
+    src = np.array([[0.4, 0.3, 0.3]])
+    fidx = np.array([1], np.int32)
+    p = orc.euclidean(fidx, src)[0]
+    targets = [np.array([0.7, 0.3, 0.0]), np.array([1.0, 0.0, 0.0]), np.array([0.0, 1.0, 0.0]), np.array([0.0, 0.0, 1.0])]
+    for ti, tb in enumerate(targets):
+        q = orc.euclidean(fidx, tb[None, :])[0]
+        disp = (2 * q - 2 * p)[None, :]
+        vec = (q - p)[None, None, :]
+        of, ob, od, ovec, ofl, ocr = orc.transport(fidx, src, disp, vec)
+        gf, gb, gd, gvec, gfl = ctx.transport(fidx, src, disp, vec)
+        assert np.array_equal(of, gf) and np.array_equal(ob, gb) and np.array_equal(ovec, gvec) and np.array_equal(ofl, gfl)
+        assert (ofl[0] & 1) == (1 if ti > 0 else 0)       # WALK_VERTEX exactly for the corner-aimed walks
+        assert of[0] != 1                                  # the particle left the source face
+        # the transported vector keeps its length and stays in the plane of the final face
+        c = corners[of[0]]
+        n = np.cross(V[c[1]] - V[c[0]], V[c[2]] - V[c[0]])
+        n /= np.linalg.norm(n)
+        assert abs(np.linalg.norm(ovec[0, 0]) - np.linalg.norm(q - p)) < 1e-12 and abs(n @ ovec[0, 0]) < 1e-12
