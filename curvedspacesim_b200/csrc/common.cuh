@@ -91,8 +91,18 @@ enum {
     C_CLK_BATCH = 22, C_CLK_FAN = 23, C_CLK_PROP = 24, C_CLK_PATCH = 25, C_CLK_TOTAL = 26, /* summed per-warp clock64 cycles */
     C_PEER_TIMEOUT = 27, /* a peer-exchange flag wait gave up (a rank died or left the collective sequence) */
     C_SPILLED = 28,      /* windows pushed to a global spill stack by k_windows_half */
+    C_KMAX_NEED = 29,    /* neighbour stride that would have been enough (max 27-cell occupancy - 1), set with C_KMAX_OVERFLOW */
+    C_STEP_GUARD = 30,   /* walker launches that really moved particles since the host last cleared it (see strideGuard) */
     NUM_COUNTERS = 32
 };
 #define CSS_WALK_MAX_CROSSINGS 100000
+
+// Neighbour-stride guard.  Before stage 1 the cell-list build bounds every particle's candidate count by the occupancy of its
+// 27-cell stencil; when that exceeds the neighbour stride it raises counters[C_KMAX_OVERFLOW].  While the flag is up every
+// kernel of the step pipeline (patch, window, retry tiers, walker) returns at once, so a fused multi-step call (CUDA-graph
+// replays included) freezes in a recoverable state: positions and velocities after the move of the failed step, forces not yet
+// recomputed.  The host regrows the stride, finishes that step and runs the remaining ones.  The bound depends only on the
+// replicated positions, so every rank of a sharded run raises the flag in the same step.
+__device__ __forceinline__ bool strideGuardUp(const unsigned long long* counters) { return *(volatile const unsigned long long*)(counters + C_KMAX_OVERFLOW) != 0ull; }
 
 } // namespace css

@@ -17,6 +17,8 @@
 
 using namespace css;
 
+#define CSS_GATHER_PAD 64 /* spare position entries behind nTotal (>= nranks - 1, see css_gather_positions) */
+
 struct css_ctx {
     int device = 0;
     cudaStream_t st = nullptr;
@@ -188,7 +190,9 @@ static size_t peerFaceBytes(int cap) { return ((size_t)cap * sizeof(int) + 255) 
 static int ensurePeerWindow(css_ctx* ctx)
 {
     if (ctx->nranks <= 1 || !ctx->p2pEnabled || ctx->p2pFailed || ctx->nranks > CSS_MAX_PEERS) return CSS_OK;
-    if (ctx->pw.n > 1 && ctx->winCap >= ctx->nTotal) return CSS_OK;
+    // window capacity derived from nTotal only, so that every rank computes the same layout whatever its allocation history
+    const int cap = (ctx->nTotal + 1023) / 1024 * 1024;
+    if (ctx->pw.n > 1 && ctx->winCap == cap) return CSS_OK;
     if (ctx->capturing) return fail(ctx, CSS_ESTATE, "peer window must exist before a step is captured");
     const int R = ctx->nranks;
     if (!ctx->d_ipcBuf) {
@@ -217,7 +221,6 @@ static int ensurePeerWindow(css_ctx* ctx)
     if (rc) return rc;
     releasePeerWindow(ctx);
     // 2. new local window, flags and epoch zeroed before anybody can signal
-    const int cap = ctx->capTotal;
     const size_t bytes = CSS_PEER_FLAG_BYTES + peerFaceBytes(cap) + sizeof(double) * 3 * (size_t)cap;
     mine.ok = cudaMalloc(&ctx->winLocal, bytes) == cudaSuccess;
     if (mine.ok) {
@@ -803,8 +806,10 @@ int css_distance(css_ctx* ctx, int srcFace, const double srcBary[3], int K, cons
 static int ensureParticles(css_ctx* ctx, int nLocal, int nTotal)
 {
     if (nTotal > ctx->capTotal) {
-        CU(regrow(ctx->d_face, nTotal));
-        CU(regrow(ctx->d_bary, 3 * (size_t)nTotal));
+        // CSS_GATHER_PAD spare entries: in the padded all-gather of css_gather_positions the last rank's block is shorter than
+        // ceil(N/R), and every rank sends a full block starting at its own offset
+        CU(regrow(ctx->d_face, (size_t)nTotal + CSS_GATHER_PAD));
+        CU(regrow(ctx->d_bary, 3 * ((size_t)nTotal + CSS_GATHER_PAD)));
         CU(regrow(ctx->d_eucl, 3 * (size_t)nTotal));
         CU(regrow(ctx->d_cellOf, nTotal));
         CU(regrow(ctx->d_cellSlot, nTotal));
@@ -926,7 +931,7 @@ static int findNeighborsImpl(css_ctx* ctx, double range, int forceMode, ForcePar
         CU(cudaMemsetAsync(ctx->d_cellCount, 0, sizeof(int) * ((size_t)ctx->nCells + 1), ctx->st));
         launchEuclidCell(ctx->st, m, ctx->grid, ctx->nTotal, ctx->d_face, ctx->d_bary, ctx->d_eucl, ctx->d_cellOf, ctx->d_cellCount, ctx->d_cellSlot);
         launchCellBuild(ctx->st, ctx->nTotal, ctx->nCells, ctx->d_cellOf, ctx->d_cellSlot, ctx->d_cellCount, ctx->d_cellStart, ctx->d_tmpItems,
-                        ctx->d_items);
+                        ctx->d_items, ctx->grid, ctx->kmax, ctx->d_counters);
         ctx->hostKernels += 4;
     } else {
         launchEuclidCell(ctx->st, m, ctx->grid, ctx->nTotal, ctx->d_face, ctx->d_bary, ctx->d_eucl, nullptr, nullptr, nullptr);
@@ -960,19 +965,23 @@ static int findNeighborsImpl(css_ctx* ctx, double range, int forceMode, ForcePar
 }
 
 // checks the capacity counters after a synchronisation point; grows kmax when the stride was too small
-static int checkCapacity(css_ctx* ctx, bool* rerun)
+static int checkCapacity(css_ctx* ctx, bool* rerun, int* stepsDone = nullptr)
 {
     unsigned long long h[NUM_COUNTERS];
     CU(cudaMemcpyAsync(h, ctx->d_counters, sizeof h, cudaMemcpyDeviceToHost, ctx->st));
     CU(cudaStreamSynchronize(ctx->st));
     if (rerun) *rerun = false;
-    if (h[C_KMAX_OVERFLOW]) {
+    if (h[C_KMAX_OVERFLOW]) { // the stride guard is up (common.cuh): nothing downstream of the cell list has run
         CU(cudaMemsetAsync(ctx->d_counters + C_KMAX_OVERFLOW, 0, sizeof(unsigned long long), ctx->st));
-        ctx->kmax *= 2;
+        CU(cudaMemsetAsync(ctx->d_counters + C_KMAX_NEED, 0, sizeof(unsigned long long), ctx->st));
+        int need = (int)std::min<unsigned long long>(h[C_KMAX_NEED], 1ull << 24), k = ctx->kmax * 2;
+        while (k < need) k *= 2;
+        ctx->kmax = k;
         ctx->capNbr = 0;
         ctx->nveCalls = 0;
+        if (stepsDone) *stepsDone = (int)h[C_STEP_GUARD];
         if (rerun) *rerun = true;
-        else return fail(ctx, CSS_ECAPACITY, "neighbour stride exceeded during a fused step; stride doubled, rerun");
+        else return fail(ctx, CSS_ECAPACITY, "neighbour stride exceeded; stride grown to %d, rerun", k);
     }
     if (h[C_OVERFLOW]) {
         CU(cudaMemsetAsync(ctx->d_counters + C_OVERFLOW, 0, sizeof(unsigned long long), ctx->st));
@@ -1101,7 +1110,7 @@ int css_compute_energy(css_ctx* ctx, int kind, const double* params, double* ene
     return css_reduce(ctx, CSS_SUM, 1, energy);
 }
 
-static int reduceDevice(css_ctx* ctx, double out[5]);
+static int reduceDevice(css_ctx* ctx, double out[5], bool* guardUp = nullptr);
 // simulation::computeMonodisperseStress (simulation.cpp:104-173) for one force computer: virial + kinetic parts of the
 // Euclidean 3x3 "stress" of the surface, density = N / area
 int css_compute_stress(css_ctx* ctx, int kind, const double* params, double stress[9])
@@ -1282,6 +1291,33 @@ static int nveSteps(css_ctx* ctx, const ForceParams& fp, double range, double dt
     return rc;
 }
 
+// nveSteps + the host half of the stride guard (common.cuh): when the cell-list build of some step found a stencil fuller than
+// the neighbour stride, the rest of the call froze behind the guard.  Regrow the stride, finish that step (forces + second
+// half kick from the positions its walker produced) and run the remaining steps.  Ends with a synchronisation.
+static int nveStepsGuarded(css_ctx* ctx, const ForceParams& fp, double range, double dt, int nsteps)
+{
+    int remaining = nsteps;
+    for (int attempt = 0; attempt < 16; ++attempt) {
+        CU(cudaMemsetAsync(ctx->d_counters + C_STEP_GUARD, 0, sizeof(unsigned long long), ctx->st));
+        int rc = nveSteps(ctx, fp, range, dt, remaining);
+        if (rc) return rc;
+        bool rerun = false;
+        int done = 0;
+        if ((rc = checkCapacity(ctx, &rerun, &done))) return rc;
+        if (!rerun) return CSS_OK;
+        if (done < 1 || done > remaining) return fail(ctx, CSS_ESTATE, "stride guard: inconsistent step count %d of %d", done, remaining);
+        for (int a2 = 0;; ++a2) { // second half of step `done - 1`
+            if ((rc = findNeighborsImpl(ctx, range, 1, fp, 1, 0.5 * dt))) return rc;
+            if ((rc = checkCapacity(ctx, &rerun))) return rc;
+            if (!rerun) break;
+            if (a2 == 8) return fail(ctx, CSS_ECAPACITY, "neighbour stride keeps overflowing");
+        }
+        remaining -= done;
+        if (remaining == 0) return CSS_OK;
+    }
+    return fail(ctx, CSS_ECAPACITY, "neighbour stride keeps overflowing");
+}
+
 int css_step_nve(css_ctx* ctx, int kind, const double* params, double dt, int nsteps)
 {
     if (!ctx || !params) return CSS_EINVAL;
@@ -1289,9 +1325,7 @@ int css_step_nve(css_ctx* ctx, int kind, const double* params, double dt, int ns
     BIND();
     double range;
     ForceParams fp = mkForce(kind, params, &range);
-    int rc = nveSteps(ctx, fp, range, dt, nsteps);
-    if (rc) return rc;
-    rc = checkCapacity(ctx, nullptr);
+    int rc = nveStepsGuarded(ctx, fp, range, dt, nsteps);
     if (ctx->timing && nsteps > 0) {
         cudaEventElapsedTime(&ctx->msCell, ctx->ev[0], ctx->ev[1]);
         cudaEventElapsedTime(&ctx->msGeo, ctx->ev[1], ctx->ev[2]);
@@ -1325,12 +1359,40 @@ int css_step_nve_host(css_ctx* ctx, int kind, const double* params, double dt, i
     CU(cudaMemcpyAsync(ctx->d_vel, vel, sizeof(double) * 3 * nL, cudaMemcpyHostToDevice, ctx->st));
     CU(cudaMemcpyAsync(ctx->d_frc, frc, sizeof(double) * 3 * nL, cudaMemcpyHostToDevice, ctx->st));
     ctx->ioFace = face, ctx->ioBary = bary;
+    CU(cudaMemsetAsync(ctx->d_counters + C_STEP_GUARD, 0, sizeof(unsigned long long), ctx->st));
     int rc = nveSteps(ctx, fp, range, dt, 1);
     ctx->ioFace = nullptr, ctx->ioBary = nullptr;
     if (rc) return rc;
     CU(cudaMemcpyAsync(vel, ctx->d_vel, sizeof(double) * 3 * nL, cudaMemcpyDeviceToHost, ctx->st));
     CU(cudaMemcpyAsync(frc, ctx->d_frc, sizeof(double) * 3 * nL, cudaMemcpyDeviceToHost, ctx->st));
-    return checkCapacity(ctx, nullptr); // synchronises the stream (which has joined the copy stream)
+    bool rerun = false;
+    if ((rc = checkCapacity(ctx, &rerun))) return rc; // synchronises the stream (which has joined the copy stream)
+    for (int a2 = 0; rerun; ++a2) { // stride guard (common.cuh): the positions (already downloaded) are final, forces and the second kick are not
+        if (a2 == 8) return fail(ctx, CSS_ECAPACITY, "neighbour stride keeps overflowing");
+        if ((rc = findNeighborsImpl(ctx, range, 1, fp, 1, 0.5 * dt))) return rc;
+        CU(cudaMemcpyAsync(vel, ctx->d_vel, sizeof(double) * 3 * nL, cudaMemcpyDeviceToHost, ctx->st));
+        CU(cudaMemcpyAsync(frc, ctx->d_frc, sizeof(double) * 3 * nL, cudaMemcpyDeviceToHost, ctx->st));
+        if ((rc = checkCapacity(ctx, &rerun))) return rc;
+    }
+    return CSS_OK;
+}
+
+// force phase of the host-driven updaters (GD, NVT, FIRE) with the host half of the stride guard: the counters are read after
+// the phase (one small copy + synchronisation; these updaters synchronise every step anyway) and the phase is repeated with a
+// larger stride when the guard went up.  Nothing downstream of the cell list ran in that case, so repeating is exact.
+static int forcesGuarded(css_ctx* ctx, double range, const ForceParams& fp, double kick)
+{
+    for (int attempt = 0; attempt < 10; ++attempt) {
+        int rc = findNeighborsImpl(ctx, range, 1, fp, 1, kick);
+        if (rc) return rc;
+        unsigned long long ovf = 0;
+        CU(cudaMemcpyAsync(&ovf, ctx->d_counters + C_KMAX_OVERFLOW, sizeof ovf, cudaMemcpyDeviceToHost, ctx->st));
+        CU(cudaStreamSynchronize(ctx->st));
+        if (!ovf) return CSS_OK;
+        bool rerun = false;
+        if ((rc = checkCapacity(ctx, &rerun))) return rc;
+    }
+    return fail(ctx, CSS_ECAPACITY, "neighbour stride keeps overflowing");
 }
 
 int css_step_gd(css_ctx* ctx, int kind, const double* params, double dt, int nsteps)
@@ -1341,7 +1403,7 @@ int css_step_gd(css_ctx* ctx, int kind, const double* params, double dt, int nst
     double range;
     ForceParams fp = mkForce(kind, params, &range);
     for (int s = 0; s < nsteps; ++s) {
-        int rc = findNeighborsImpl(ctx, range, 1, fp, 1, 0.0);
+        int rc = forcesGuarded(ctx, range, fp, 0.0);
         if (rc) return rc;
         launchAxpy(ctx->st, 1, ctx->nLocal, dt, 0, ctx->d_vel, ctx->d_frc, ctx->d_disp);
         ctx->hostKernels++;
@@ -1350,12 +1412,16 @@ int css_step_gd(css_ctx* ctx, int kind, const double* params, double dt, int nst
     return checkCapacity(ctx, nullptr);
 }
 
-static int reduceDevice(css_ctx* ctx, double out[5])
+// guardUp (optional): the stride-guard flag (common.cuh), read in the same synchronisation
+static int reduceDevice(css_ctx* ctx, double out[5], bool* guardUp)
 {
     launchReduce(ctx->st, ctx->nLocal, ctx->d_vel, ctx->d_frc, ctx->d_partial, ctx->d_red);
     ctx->hostKernels += 2;
+    unsigned long long ovf = 0;
     CU(cudaMemcpyAsync(out, ctx->d_red, 5 * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
+    if (guardUp) CU(cudaMemcpyAsync(&ovf, ctx->d_counters + C_KMAX_OVERFLOW, sizeof ovf, cudaMemcpyDeviceToHost, ctx->st));
     CU(cudaStreamSynchronize(ctx->st));
+    if (guardUp) *guardUp = ovf != 0;
     if (ctx->nranks > 1) {
         double s[4] = {out[0], out[1], out[2], out[4]};
         int rc = css_reduce(ctx, CSS_SUM, 4, s);
@@ -1450,11 +1516,17 @@ int css_step_nvt(css_ctx* ctx, int kind, const double* params, int nsteps)
         ctx->hostKernels += 2;
         int rc = moveImpl(ctx, 0, 1, 0, 0.0);
         if (rc) return rc;
-        if ((rc = findNeighborsImpl(ctx, range, 1, fp, 1, h.dt))) return rc; // v += (dt/m) f fused as the kick
-        launchAxpy(ctx->st, 3, ctx->nLocal, h.dt2, 0, ctx->d_vel, ctx->d_frc, ctx->d_disp);
-        ctx->hostKernels++;
         double r[5];
-        if ((rc = reduceDevice(ctx, r))) return rc;
+        for (int attempt = 0;; ++attempt) { // repeated with a larger neighbour stride when the stride guard went up (common.cuh)
+            if ((rc = findNeighborsImpl(ctx, range, 1, fp, 1, h.dt))) return rc; // v += (dt/m) f fused as the kick
+            launchAxpy(ctx->st, 3, ctx->nLocal, h.dt2, 0, ctx->d_vel, ctx->d_frc, ctx->d_disp);
+            ctx->hostKernels++;
+            bool guardUp = false, rerun = false;
+            if ((rc = reduceDevice(ctx, r, &guardUp))) return rc;
+            if (!guardUp) break;
+            if (attempt == 8) return fail(ctx, CSS_ECAPACITY, "neighbour stride keeps overflowing");
+            if ((rc = checkCapacity(ctx, &rerun))) return rc;
+        }
         h.KE = r[4];
         if ((rc = moveImpl(ctx, 0, 1, 0, 0.0))) return rc;
         propagateChain(ctx);
@@ -1496,17 +1568,27 @@ int css_fire_minimize(css_ctx* ctx, int kind, const double* params, double* out)
     double range;
     ForceParams fp = mkForce(kind, params, &range);
     auto& f = ctx->fire;
-    int rc = findNeighborsImpl(ctx, range, 1, fp, 1, 0.0);
-    if (rc) return rc;
+    int rc;
     double r[5];
-    if ((rc = reduceDevice(ctx, r))) return rc;
+    // force phase + reductions; repeated with a larger neighbour stride when the stride guard went up (common.cuh)
+    auto forcesAndReduce = [&](double kick) -> int {
+        for (int attempt = 0;; ++attempt) {
+            int rc2 = findNeighborsImpl(ctx, range, 1, fp, 1, kick);
+            if (rc2) return rc2;
+            bool guardUp = false, rerun = false;
+            if ((rc2 = reduceDevice(ctx, r, &guardUp))) return rc2;
+            if (!guardUp) return CSS_OK;
+            if (attempt == 8) return fail(ctx, CSS_ECAPACITY, "neighbour stride keeps overflowing");
+            if ((rc2 = checkCapacity(ctx, &rerun))) return rc2;
+        }
+    };
+    if ((rc = forcesAndReduce(0.0))) return rc;
     f.forceMax = std::sqrt(r[3]);
     f.iterations = 0;
     while (f.iterations < f.maximumIterations && f.forceMax > f.forceCutoff) { // minimizeByFire :3-21
         f.iterations += 1;
         if ((rc = moveImpl(ctx, 1, 1, 1, f.dt))) return rc;                       // first half + move, transporting [force, velocity]
-        if ((rc = findNeighborsImpl(ctx, range, 1, fp, 1, 0.5 * f.dt))) return rc; // forces + second half kick
-        if ((rc = reduceDevice(ctx, r))) return rc;                                // fireStep :36-72
+        if ((rc = forcesAndReduce(0.5 * f.dt))) return rc;                         // forces + second half kick; fireStep :36-72
         double forceNorm = r[0], velocityNorm = r[1], power = r[2];
         double scaling = 0.0;
         if (forceNorm > 0) scaling = std::sqrt(velocityNorm / forceNorm);
@@ -1576,6 +1658,7 @@ int css_gather_positions(css_ctx* ctx)
     BIND();
     int per = (ctx->nTotal + ctx->nranks - 1) / ctx->nranks;
     if (ctx->minIdx != ctx->rank * per) return fail(ctx, CSS_EINVAL, "sharding does not follow mpiModel::determineIndexBounds");
+    if ((size_t)per * ctx->nranks > (size_t)ctx->nTotal + CSS_GATHER_PAD) return fail(ctx, CSS_EINVAL, "css_gather_positions: more than %d ranks", CSS_GATHER_PAD);
     if (per * ctx->nranks == ctx->nTotal) { // equal blocks: gather in place, no scratch and no copies
         NC(ncclGroupStart());
         NC(ncclAllGather(ctx->d_face + ctx->minIdx, ctx->d_face, per, ncclInt32, ctx->comm, ctx->st));

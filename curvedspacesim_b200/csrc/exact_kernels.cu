@@ -153,16 +153,30 @@ __global__ void k_cell_fill(int n, const int* __restrict__ cellOf, const int* __
     tmpItems[cellStart[cellOf[i]] + cellSlot[i]] = i;
 }
 // rank of particle i inside its cell = number of members with a smaller index
+// ... and the stride guard (common.cuh): the occupancy of the particle's 27-cell stencil bounds its candidate count
 __global__ void k_cell_rank(int n, const int* __restrict__ cellOf, const int* __restrict__ cellStart, const int* __restrict__ cellCount,
-                            const int* __restrict__ tmpItems, int* __restrict__ items)
+                            const int* __restrict__ tmpItems, int* __restrict__ items, int nx, int ny, int nz, int kmax,
+                            unsigned long long* __restrict__ counters)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    int c = cellOf[i];
-    int s0 = cellStart[c], cnt = cellCount[c];
-    int r = 0;
-    for (int s = 0; s < cnt; ++s) r += (tmpItems[s0 + s] < i);
-    items[s0 + r] = i;
+    int occ = 0;
+    if (i < n) {
+        int c = cellOf[i];
+        int s0 = cellStart[c], cnt = cellCount[c];
+        int r = 0;
+        for (int s = 0; s < cnt; ++s) r += (tmpItems[s0 + s] < i);
+        items[s0 + r] = i;
+        const int ix = c % nx, iy = (c / nx) % ny, iz = c / (nx * ny);
+        for (int xx = max(0, ix - 1); xx <= min(nx - 1, ix + 1); ++xx)
+            for (int yy = max(0, iy - 1); yy <= min(ny - 1, iy + 1); ++yy)
+                for (int zz = max(0, iz - 1); zz <= min(nz - 1, iz + 1); ++zz) occ += cellCount[xx + yy * nx + zz * nx * ny];
+        occ -= 1; // the particle itself
+    }
+    occ = __reduce_max_sync(0xffffffffu, occ);
+    if ((threadIdx.x & 31) == 0 && occ > kmax) {
+        atomicMax(counters + C_KMAX_NEED, (unsigned long long)occ);
+        atomicAdd(counters + C_KMAX_OVERFLOW, 1ull);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -234,6 +248,209 @@ template <int NT> __device__ __forceinline__ void projectVectorsIfOverBoundary(d
         }
 }
 
+
+// ---- vertex events (rare; kept out of line).  The same operation sequence as the CPU checker used by the tests: throughVertex /
+// updateForVertexIntersection (triangulatedMeshSpace.cpp:247-407, :566-611) with their intended semantics, and the boundary
+// vertex rule of the open spaces (openMeshSpace.cpp:3-70, absorbing/tangentialOpenMeshSpace::updateAtBoundaryVertex).
+// Angles use deterministic IEEE-only trigonometry so that host oracle and device agree bit for bit.
+__device__ __noinline__ double detAngle(double s, double c)
+{
+    const double PI = 3.14159265358979323846;
+    double r = sqrt(s * s + c * c);
+    if (!(r > 0)) return 0.0;
+    bool obtuse = c < 0;
+    double ca = obtuse ? -c : c;
+    double t = s / (r + ca);
+    t = t / (1.0 + sqrt(1.0 + t * t));
+    t = t / (1.0 + sqrt(1.0 + t * t));
+    double t2 = t * t;
+    double a = 1.0 / 19.0;
+    a = 1.0 / 17.0 - t2 * a;
+    a = 1.0 / 15.0 - t2 * a;
+    a = 1.0 / 13.0 - t2 * a;
+    a = 1.0 / 11.0 - t2 * a;
+    a = 1.0 / 9.0 - t2 * a;
+    a = 1.0 / 7.0 - t2 * a;
+    a = 1.0 / 5.0 - t2 * a;
+    a = 1.0 / 3.0 - t2 * a;
+    a = 1.0 - t2 * a;
+    double phi = 8.0 * (t * a);
+    return obtuse ? PI - phi : phi;
+}
+__device__ __noinline__ void detSinCos(double x, double& s, double& c)
+{
+    double y = x * 0.125, y2 = y * y;
+    double ps = 1.0 - y2 / 272.0;
+    ps = 1.0 - y2 / 210.0 * ps;
+    ps = 1.0 - y2 / 156.0 * ps;
+    ps = 1.0 - y2 / 110.0 * ps;
+    ps = 1.0 - y2 / 72.0 * ps;
+    ps = 1.0 - y2 / 42.0 * ps;
+    ps = 1.0 - y2 / 20.0 * ps;
+    ps = 1.0 - y2 / 6.0 * ps;
+    double pc = 1.0 - y2 / 306.0;
+    pc = 1.0 - y2 / 240.0 * pc;
+    pc = 1.0 - y2 / 182.0 * pc;
+    pc = 1.0 - y2 / 132.0 * pc;
+    pc = 1.0 - y2 / 90.0 * pc;
+    pc = 1.0 - y2 / 56.0 * pc;
+    pc = 1.0 - y2 / 30.0 * pc;
+    pc = 1.0 - y2 / 12.0 * pc;
+    pc = 1.0 - y2 / 2.0 * pc;
+    s = y * ps, c = pc;
+    for (int i = 0; i < 3; ++i) {
+        double s2 = 2.0 * s * c, c2 = 1.0 - 2.0 * s * s;
+        s = s2, c = c2;
+    }
+}
+__device__ __forceinline__ double angleBetweenUnit(const d3& u, const d3& v) { return detAngle(norm(cross(u, v)), dot(u, v)); }
+__device__ __forceinline__ d3 unitTo(const d3& from, const d3& to)
+{
+    d3 d = to - from;
+    return d / norm(d);
+}
+#define CSS_WALK_MAX_VALENCE 64
+struct FanFace {
+    int g, kc; // the vertex sits at corner kc of face g
+};
+__device__ __forceinline__ int pick3(const int4& v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : v.z); }
+__device__ __forceinline__ FanFace fanClockwise(const MeshDev& m, FanFace a)
+{
+    const int e = (a.kc + 2) % 3;
+    const int4 ad = __ldg(m.adj + a.g);
+    const int g = pick3(ad, e);
+    return FanFace{g, g < 0 ? 0 : (((ad.w >> (2 * e)) & 3) + 2) % 3};
+}
+__device__ __forceinline__ FanFace fanCounterClockwise(const MeshDev& m, FanFace a)
+{
+    const int e = (a.kc + 1) % 3;
+    const int4 ad = __ldg(m.adj + a.g);
+    const int g = pick3(ad, e);
+    return FanFace{g, g < 0 ? 0 : (((ad.w >> (2 * e)) & 3) + 1) % 3};
+}
+__device__ __forceinline__ double fanAngle(const MeshDev& m, FanFace a, const d3& Pv, d3& eNext, d3& ePrev)
+{
+    const int4 c = __ldg(m.corner + a.g);
+    eNext = unitTo(Pv, ldvert(m, pick3(c, (a.kc + 1) % 3)));
+    ePrev = unitTo(Pv, ldvert(m, pick3(c, (a.kc + 2) % 3)));
+    return angleBetweenUnit(eNext, ePrev);
+}
+__device__ __noinline__ bool throughVertex(const MeshDev& m, int f, int kv, const d3& travel, int& gOut, d3& heading)
+{
+    const d3 Pv = ldvert(m, pick3(__ldg(m.corner + f), kv));
+    const FanFace src{f, kv};
+    d3 eN, eP;
+    double total = 0;
+    int n = 0;
+    for (FanFace a = fanClockwise(m, src);; a = fanClockwise(m, a)) {
+        if (a.g < 0 || ++n > CSS_WALK_MAX_VALENCE) return false;
+        total += fanAngle(m, a, Pv, eN, eP);
+        if (a.g == f) break;
+    }
+    const double half = total / 2.0;
+    d3 back = d3{0, 0, 0} - travel;
+    fanAngle(m, src, Pv, eN, eP);
+    double traveled = angleBetweenUnit(back, eN);
+    FanFace land = src;
+    if (traveled < half) {
+        for (FanFace a = fanClockwise(m, src);; a = fanClockwise(m, a)) {
+            traveled += fanAngle(m, a, Pv, eN, eP);
+            land = a;
+            if (traveled >= half || a.g == f) break;
+        }
+    }
+    double delta = traveled - half, sn, cs;
+    if (delta < 0) delta = 0;
+    detSinCos(delta, sn, cs);
+    d3 u = cross(eN, eP);
+    u = u / norm(u);
+    d3 w = cross(u, eN);
+    heading = cs * eN + sn * w;
+    heading = heading / norm(heading);
+    gOut = land.g;
+    return true;
+}
+__device__ __noinline__ bool boundaryVertexHeading(const MeshDev& m, int f, int kv, const d3& dhat, int& gOut, int& wOut, d3& heading)
+{
+    const d3 Pv = ldvert(m, pick3(__ldg(m.corner + f), kv));
+    const FanFace src{f, kv};
+    double best = -1;
+    bool found = false;
+    for (int dir = 0; dir < 2; ++dir) {
+        int n = 0;
+        for (FanFace a = dir ? fanCounterClockwise(m, src) : fanClockwise(m, src); a.g >= 0 && a.g != f && ++n <= CSS_WALK_MAX_VALENCE;
+             a = dir ? fanCounterClockwise(m, a) : fanClockwise(m, a)) {
+            const int4 c = __ldg(m.corner + a.g);
+            for (int j = 1; j <= 2; ++j) {
+                int w = pick3(c, (a.kc + j) % 3);
+                d3 out = unitTo(Pv, ldvert(m, w));
+                double overlap = dot(out, dhat);
+                if (overlap > best) best = overlap, heading = out, gOut = a.g, wOut = w, found = true;
+            }
+        }
+    }
+    return found;
+}
+
+// the path goes through the vertex at corner kv of face f.  Returns true when the walk goes on (state updated), false when it
+// stops at S (closed space at a boundary vertex, absorbing space, nothing left to slide along)
+template <int NT>
+__device__ __noinline__ bool vertexEvent(const MeshDev& m, int& f, Tri& tri, int kv, double S[3], d3& p, d3& q, d3& disp, d3& n,
+                                         d3 (&T)[NT > 0 ? NT : 1], int nT, int& flags)
+{
+    flags |= WALK_VERTEX;
+    const d3 travel = disp / norm(disp);
+    int g2 = -1;
+    d3 heading;
+    if (throughVertex(m, f, kv, travel, g2, heading)) {
+        Tri tri2 = ldtri(m, g2);
+        d3 n2 = tnormal(tri2);
+        double rem = norm(q - p);
+        d3 side = cross(n, travel), side2 = cross(n2, heading);
+#pragma unroll
+        for (int i = 0; i < NT; ++i)
+            if (i < nT) {
+                double ta = dot(T[i], travel), tb = dot(T[i], side), tc = dot(T[i], n);
+                T[i] = ta * heading + tb * side2 + tc * n2;
+            }
+        disp = rem * heading;
+        q = p + disp;
+        f = g2;
+        tri = tri2;
+        ericson(tri, p, S);
+        n = n2;
+        return true;
+    }
+    flags |= WALK_BORDER;
+    int w = -1;
+    if (m.boundary == 0 || !boundaryVertexHeading(m, f, kv, travel, g2, w, heading)) return false;
+    const int vIdx = pick3(__ldg(m.corner + f), kv);
+    const d3 Pv = ldvert(m, vIdx);
+    d3 rest = q - p;
+    f = g2;
+    tri = ldtri(m, f);
+    n = tnormal(tri);
+    ericson(tri, Pv, S);
+    if (nT > 0) {
+        d3 orth = cross(n, heading);
+        orth = orth / norm(orth);
+        const int4 c = __ldg(m.corner + f);
+        d3 inside = Pv;
+        for (int j = 0; j < 3; ++j) {
+            int cv = pick3(c, j);
+            if (cv != vIdx && cv != w) inside = ldvert(m, cv);
+        }
+        projectVectorsIfOverBoundary<NT>(T, nT, orth, inside - Pv);
+    }
+    if (m.boundary == 1) return false;
+    double slide = dot(rest, heading);
+    if (!(slide > 1e-9 * norm(ldvert(m, w) - Pv))) return false;
+    disp = slide * heading;
+    p = tpoint(tri, S);
+    q = p + disp;
+    return true;
+}
+
 template <int NT>
 __device__ __forceinline__ int walkOne(const MeshDev& m, int& face, double bary[3], d3& disp, d3 (&T)[NT > 0 ? NT : 1], int nT,
                                        int& nCross)
@@ -280,7 +497,15 @@ __device__ __forceinline__ int walkOne(const MeshDev& m, int& face, double bary[
         S[0] = I[0], S[1] = I[1], S[2] = I[2];
         p = x;
         int k = nh >= 2 ? k1 : k0;
-        if (nh >= 2) flags |= WALK_VERTEX;
+        if (nh >= 2 && k0 != k1) { // two edges hit: the path goes through their common vertex (corner 3 - k0 - k1)
+            last = -1;
+            if (vertexEvent<NT>(m, f, tri, 3 - k0 - k1, S, p, q, disp, n, T, nT, flags)) {
+                nCross++;
+                continue;
+            }
+            E[0] = S[0], E[1] = S[1], E[2] = S[2];
+            break;
+        }
         int4 a = __ldg(m.adj + f);
         int g = k == 0 ? a.x : (k == 1 ? a.y : a.z);
         if (g < 0) { // border edge: openMeshSpace.cpp:114-238 and its absorbing / tangential subclasses
@@ -358,6 +583,8 @@ __global__ void __launch_bounds__(64, CSS_WALK_MINB) k_walk(MeshDev m, int n, in
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int fl = 0, nc = 0;
+    if (strideGuardUp(counters)) return; // a step upstream is waiting for a larger neighbour stride: nothing moves (common.cuh)
+    if (i == 0) atomicAdd(counters + C_STEP_GUARD, 1ull);
     if (i < n) {
         d3 d;
         if (mode & 1) { // velocityVerletNVE::velocityVerletFirstHalfStep
@@ -758,12 +985,12 @@ void launchEuclidCell(cudaStream_t st, const MeshDev& m, const CellGrid& g, int 
 }
 // cellCount[nCells] is the bump counter (cleared with the counts)
 void launchCellBuild(cudaStream_t st, int n, int nCells, const int* cellOf, const int* cellSlot, int* cellCount, int* cellStart, int* tmpItems,
-                     int* items)
+                     int* items, const CellGrid& g, int kmax, unsigned long long* counters)
 {
     if (n <= 0) return;
     k_cell_place<<<gridFor(n, 256), 256, 0, st>>>(n, cellOf, cellSlot, cellCount, cellStart, cellCount + nCells);
     k_cell_fill<<<gridFor(n, 256), 256, 0, st>>>(n, cellOf, cellSlot, cellStart, tmpItems);
-    k_cell_rank<<<gridFor(n, 256), 256, 0, st>>>(n, cellOf, cellStart, cellCount, tmpItems, items);
+    k_cell_rank<<<gridFor(n, 256), 256, 0, st>>>(n, cellOf, cellStart, cellCount, tmpItems, items, g.n[0], g.n[1], g.n[2], kmax, counters);
 }
 void launchWalk(cudaStream_t st, const MeshDev& m, int n, int minIdx, int* face, double* bary, double* disp, double* vel, double* frc,
                 int transportForce, int transportVelocity, int mode, double dt, int* flags, unsigned long long* counters, const PeerWin& pw)

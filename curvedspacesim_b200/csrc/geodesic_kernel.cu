@@ -307,7 +307,7 @@ __device__ int processSource(const GeoArgs& a, const WS& w, int li, int lane)
         for (int t = lane; t < K; t += 32) w.tIdx[t] = t < gi ? t : t + 1;
     }
     if (!explicitQ && K > a.kmax) {
-        if (lane == 0) atomicAdd(a.counters + C_KMAX_OVERFLOW, 1ull);
+        if (lane == 0) atomicMax(a.counters + C_KMAX_NEED, (unsigned long long)K), atomicAdd(a.counters + C_KMAX_OVERFLOW, 1ull);
         K = a.kmax; // truncated; the host grows kmax and reruns
     }
     __syncwarp();
@@ -951,6 +951,7 @@ __global__ void __launch_bounds__(128, 3) k_geodesic(GeoArgs a, size_t wsBytes)
     WS w;
     wsLayout(a.caps, base, &w);
     unsigned long long* cnt = w.wcnt;
+    if (a.xK < 0 && strideGuardUp(a.counters)) return; // neighbour phase waiting for a larger stride (common.cuh); explicit queries are not affected
     if (lane < 16) cnt[lane] = 0;
     __syncwarp();
 

@@ -138,7 +138,7 @@ template <class T> __device__ int buildPatch(const PatchArgs& a, PatchSmem<T>& s
         int incl = warpInclusiveScan(mine, lane);
         K = __shfl_sync(FULL, incl, 31);
         if (K > a.kmax) { // neighbour stride too small: the host doubles it and reruns the step
-            if (lane == 0) atomicAdd(a.counters + C_KMAX_OVERFLOW, 1ull);
+            if (lane == 0) atomicMax(a.counters + C_KMAX_NEED, (unsigned long long)K), atomicAdd(a.counters + C_KMAX_OVERFLOW, 1ull);
             return 1;
         }
         if (K > T::RECK) return 2; // 1 + reason (0 candidates, 1 faces, 2 vertices)
@@ -295,6 +295,7 @@ template <class T> __global__ void __launch_bounds__(PATCH_THREADS) k_patch(Patc
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     PatchSmem<T>& s = reinterpret_cast<PatchSmem<T>*>(smemRaw)[wib];
     unsigned long long nRetry = 0;
+    if (strideGuardUp(a.counters)) return; // the cell-list build found a stencil fuller than the neighbour stride (common.cuh)
     const int nWork = a.srcList ? *a.srcCount : a.nLocal;
     for (;;) {
         int w = 0;
@@ -336,7 +337,10 @@ template <class T> __global__ void __launch_bounds__(PATCH_THREADS) k_patch(Patc
 template <class T> cudaError_t launchPatch(cudaStream_t st, const PatchArgs& a, int numSMs)
 {
     size_t smem = sizeof(PatchSmem<T>) * (PATCH_THREADS / 32);
-    static int perSM = 0;
+    static int perSMdev[64] = {0}; // the attribute and the occupancy are per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int& perSM = perSMdev[dev & 63];
     if (!perSM) {
         cudaFuncSetAttribute(k_patch<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_patch<T>, PATCH_THREADS, smem) != cudaSuccess || perSM < 1) perSM = 1;

@@ -122,6 +122,7 @@ template <class T> __global__ void __launch_bounds__(32 * CSS_HALF_WPB, CSS_HALF
     const unsigned hmask = 0xFFFFu << hbase;
     W* const wpair = reinterpret_cast<W*>(smemRaw) + 2 * wib;
     W& w = wpair[half];
+    if (strideGuardUp(a.counters)) return; // stage 1 did not run: the host regrows the neighbour stride and repeats the phase
     // spill stacks of this warp's two sources (global memory, L2-resident; see the push in the pass loop)
     double* const spillPair = a.spill + (size_t)(blockIdx.x * (blockDim.x >> 5) + wib) * 2 * SPILL_CAP * SPILL_DOUBLES;
     double* const spill = spillPair + (size_t)half * SPILL_CAP * SPILL_DOUBLES;
@@ -672,7 +673,10 @@ template <class T> cudaError_t launchWindowsHalf(cudaStream_t st, const WinArgs&
 {
     constexpr int wpb = CSS_HALF_WPB;
     const size_t smem = sizeof(HalfSmem<T>) * 2 * wpb;
-    static int perSM = 0;
+    static int perSMdev[64] = {0}; // the attribute and the occupancy are per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int& perSM = perSMdev[dev & 63];
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
     if (!perSM) {
         cudaFuncSetAttribute(k_windows_half<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

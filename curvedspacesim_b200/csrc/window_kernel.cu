@@ -542,6 +542,7 @@ template <class T, bool LEAN> __global__ void __launch_bounds__(128, LEAN ? CSS_
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     WinSmem<T, LEAN>& w = reinterpret_cast<WinSmem<T, LEAN>*>(smemRaw)[wib];
     unsigned long long* cnt = w.wcnt;
+    if (strideGuardUp(a.counters)) return; // stage 1 did not run (common.cuh)
     if (lane < 16) cnt[lane] = 0;
     __syncwarp();
     const int nWork = a.srcList ? min(*a.srcCount, a.maxRecords) : a.nLocal;
@@ -570,7 +571,10 @@ template <class T, bool LEAN> __global__ void __launch_bounds__(128, LEAN ? CSS_
 template <class T, bool LEAN> static cudaError_t launchWindowsImpl(cudaStream_t st, const WinArgs& a, int warpsPerBlock, int numSMs)
 {
     size_t smem = sizeof(WinSmem<T, LEAN>) * warpsPerBlock;
-    static int perSM[5] = {0, 0, 0, 0, 0};
+    static int perSMdev[64][5] = {{0}}; // the attribute and the occupancy are per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int* perSM = perSMdev[dev & 63];
     if (warpsPerBlock < 1 || warpsPerBlock > 4 || smem > 227 * 1024) return cudaErrorInvalidConfiguration;
     if (!perSM[warpsPerBlock]) {
         cudaFuncSetAttribute(k_windows<T, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

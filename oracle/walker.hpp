@@ -11,9 +11,18 @@
 //  * open meshes (openMeshSpace.cpp:114-238): a border edge ends the walk in the closed space (flag), stops the particle on
 //    the edge in the absorbing space (absorbingOpenMeshSpace.cpp:2-24) or redirects the displacement along the edge in the
 //    tangential space (tangentialOpenMeshSpace.cpp:3-42); transported vectors pointing over the boundary are projected
-//    (triangulatedMeshSpace.cpp:411-426).  Boundary VERTEX events take the edge rule of the last edge hit and are flagged.
-//  * vertex crossings (two edges hit), no-hit and runaway loops do not throw: they set a flag bit and
-//    continue/stop in a defined way; the north star excludes them from parity and counts them.
+//    (triangulatedMeshSpace.cpp:411-426).
+//  * vertex crossings (two edges hit): updateForVertexIntersection / throughVertex (:247-407, :566-611) are restated with
+//    their INTENDED semantics, flagged WALK_VERTEX and counted: the vertex is the corner shared by the two
+//    hit edges (the reference takes involvedVertex[0], which is that corner in one of the three cases only); the fan is
+//    circulated clockwise from the source face through the face adjacency (= CGAL's Vertex_around_target_circulator started
+//    at the successor of the vertex in the source face, :256-300); the outgoing heading leaves half of the total angle on
+//    either side (:319-348); the remaining length is |target - vertex| (the reference re-uses the pre-hop length, :578-581);
+//    transported vectors keep their angle to the path (the reference rotates them about n x n' only when n.n' < 0, :589).
+//    Angles come from detAngle / detSinCos (IEEE + - * / sqrt in a fixed order) instead of acos / sin / cos so that host and
+//    device agree bit for bit.  Boundary vertices of open meshes follow openMeshSpace::getBoundaryVertexHeading (openMeshSpace.cpp:3-70,
+//    the ring edge that overlaps the heading most) with absorbing / tangentialOpenMeshSpace::updateAtBoundaryVertex.
+//  * no-hit and runaway loops do not throw: they set a flag bit and stop in a defined way.
 #pragma once
 #include "mesh.hpp"
 #include <vector>
@@ -114,6 +123,156 @@ inline int edgeHits(const double S[3], const double E[3], int lastEdge, int hitK
     return nh;
 }
 
+
+// ---- deterministic trigonometry: IEEE + - * / sqrt only, evaluated in this order by the oracle and by the CUDA walker ----
+// angle in [0, pi] of a rotation with sine s >= 0 and cosine c (not necessarily normalised)
+inline double detAngle(double s, double c)
+{
+    const double PI = 3.14159265358979323846;
+    double r = std::sqrt(s * s + c * c);
+    if (!(r > 0)) return 0.0;
+    bool obtuse = c < 0;
+    double ca = obtuse ? -c : c;
+    double t = s / (r + ca);                  // tan(phi / 2), phi in [0, pi/2]
+    t = t / (1.0 + std::sqrt(1.0 + t * t));   // tan(phi / 4)
+    t = t / (1.0 + std::sqrt(1.0 + t * t));   // tan(phi / 8) <= 0.0985
+    double t2 = t * t;
+    double a = 1.0 / 19.0;
+    a = 1.0 / 17.0 - t2 * a;
+    a = 1.0 / 15.0 - t2 * a;
+    a = 1.0 / 13.0 - t2 * a;
+    a = 1.0 / 11.0 - t2 * a;
+    a = 1.0 / 9.0 - t2 * a;
+    a = 1.0 / 7.0 - t2 * a;
+    a = 1.0 / 5.0 - t2 * a;
+    a = 1.0 / 3.0 - t2 * a;
+    a = 1.0 - t2 * a;
+    double phi = 8.0 * (t * a);
+    return obtuse ? PI - phi : phi;
+}
+// sine and cosine of x in [0, pi]
+inline void detSinCos(double x, double& s, double& c)
+{
+    double y = x * 0.125, y2 = y * y;
+    double ps = 1.0 - y2 / 272.0;             // sin y = y (1 - y2/6 (1 - y2/20 (1 - y2/42 ( ... ))))
+    ps = 1.0 - y2 / 210.0 * ps;
+    ps = 1.0 - y2 / 156.0 * ps;
+    ps = 1.0 - y2 / 110.0 * ps;
+    ps = 1.0 - y2 / 72.0 * ps;
+    ps = 1.0 - y2 / 42.0 * ps;
+    ps = 1.0 - y2 / 20.0 * ps;
+    ps = 1.0 - y2 / 6.0 * ps;
+    double pc = 1.0 - y2 / 306.0;             // cos y = 1 - y2/2 (1 - y2/12 (1 - y2/30 ( ... )))
+    pc = 1.0 - y2 / 240.0 * pc;
+    pc = 1.0 - y2 / 182.0 * pc;
+    pc = 1.0 - y2 / 132.0 * pc;
+    pc = 1.0 - y2 / 90.0 * pc;
+    pc = 1.0 - y2 / 56.0 * pc;
+    pc = 1.0 - y2 / 30.0 * pc;
+    pc = 1.0 - y2 / 12.0 * pc;
+    pc = 1.0 - y2 / 2.0 * pc;
+    s = y * ps, c = pc;
+    for (int i = 0; i < 3; ++i) {             // three angle doublings
+        double s2 = 2.0 * s * c, c2 = 1.0 - 2.0 * s * s;
+        s = s2, c = c2;
+    }
+}
+inline double angleBetweenUnit(const V3& u, const V3& v) { return detAngle(norm(cross(u, v)), dot(u, v)); } // functionUtilities.cpp:34-45
+inline V3 unitTo(const V3& from, const V3& to)
+{
+    V3 d = to - from;
+    return d / norm(d);
+}
+static const int WALK_MAX_VALENCE = 64;
+
+// one face of the fan of vertex v: v sits at corner kc of face g
+struct FanFace {
+    int g, kc;
+};
+// next face clockwise (CGAL Vertex_around_target_circulator++ for counter-clockwise faces): across the edge (v, successor of v)
+inline FanFace fanClockwise(const Mesh& m, FanFace a)
+{
+    int e = (a.kc + 2) % 3, g = m.adj[3 * a.g + e];
+    return FanFace{g, g < 0 ? 0 : (m.adjk[3 * a.g + e] + 2) % 3};
+}
+inline FanFace fanCounterClockwise(const Mesh& m, FanFace a)
+{
+    int e = (a.kc + 1) % 3, g = m.adj[3 * a.g + e];
+    return FanFace{g, g < 0 ? 0 : (m.adjk[3 * a.g + e] + 1) % 3};
+}
+// interior angle of the fan face at v, and the unit edge vectors to the successor / predecessor of v in that face
+inline double fanAngle(const Mesh& m, FanFace a, const V3& Pv, V3& eNext, V3& ePrev)
+{
+    eNext = unitTo(Pv, m.v[m.c[3 * a.g + (a.kc + 1) % 3]]);
+    ePrev = unitTo(Pv, m.v[m.c[3 * a.g + (a.kc + 2) % 3]]);
+    return angleBetweenUnit(eNext, ePrev);
+}
+
+// Straightest geodesic through the interior vertex at corner kv of face f (throughVertex :247-407 + updateForVertexIntersection
+// :566-611, intended semantics).  travel = unit direction of motion inside f.  Returns false when the fan meets a border
+// (boundary vertex) or is malformed; otherwise the landing face and the unit heading inside it.
+inline bool throughVertex(const Mesh& m, int f, int kv, const V3& travel, int& gOut, V3& heading)
+{
+    const V3 Pv = m.v[m.c[3 * f + kv]];
+    const FanFace src{f, kv};
+    V3 eN, eP;
+    // pass 1: total angle, sectors in circulation order (first clockwise neighbour ... source face last)
+    double total = 0;
+    int n = 0;
+    for (FanFace a = fanClockwise(m, src);; a = fanClockwise(m, a)) {
+        if (a.g < 0 || ++n > WALK_MAX_VALENCE) return false;
+        total += fanAngle(m, a, Pv, eN, eP);
+        if (a.g == f) break;
+    }
+    const double half = total / 2.0;
+    // pass 2: from the incoming direction (seen from the vertex) clockwise until half of the total angle is used up
+    V3 back = V3{0, 0, 0} - travel;
+    fanAngle(m, src, Pv, eN, eP);
+    double traveled = angleBetweenUnit(back, eN); // :322 firstAngle, measured to the successor of v in the source face
+    FanFace land = src;
+    if (traveled < half) {
+        for (FanFace a = fanClockwise(m, src);; a = fanClockwise(m, a)) {
+            traveled += fanAngle(m, a, Pv, eN, eP);
+            land = a;
+            if (traveled >= half || a.g == f) break;
+        }
+    }
+    // heading: the successor edge of the landing face turned back by (traveled - half) towards its predecessor edge (:334-345)
+    double delta = traveled - half, sn, cs;
+    if (delta < 0) delta = 0;
+    detSinCos(delta, sn, cs);
+    V3 u = cross(eN, eP);
+    u = u / norm(u);
+    V3 w = cross(u, eN);
+    heading = cs * eN + sn * w;
+    heading = heading / norm(heading);
+    gOut = land.g;
+    return true;
+}
+
+// openMeshSpace::getBoundaryVertexHeading (openMeshSpace.cpp:3-70): among the ring edges of the boundary vertex that belong to a
+// face other than the source face, the one that overlaps the heading most.  Returns false when no other face touches v.
+inline bool boundaryVertexHeading(const Mesh& m, int f, int kv, const V3& dhat, int& gOut, int& wOut, V3& heading)
+{
+    const V3 Pv = m.v[m.c[3 * f + kv]];
+    const FanFace src{f, kv};
+    double best = -1;
+    bool found = false;
+    for (int dir = 0; dir < 2; ++dir) {
+        int n = 0;
+        for (FanFace a = dir ? fanCounterClockwise(m, src) : fanClockwise(m, src); a.g >= 0 && a.g != f && ++n <= WALK_MAX_VALENCE;
+             a = dir ? fanCounterClockwise(m, a) : fanClockwise(m, a)) {
+            for (int j = 1; j <= 2; ++j) {
+                int w = m.c[3 * a.g + (a.kc + j) % 3];
+                V3 out = unitTo(Pv, m.v[w]);
+                double overlap = dot(out, dhat);
+                if (overlap > best) best = overlap, heading = out, gOut = a.g, wOut = w, found = true;
+            }
+        }
+    }
+    return found;
+}
+
 // Returns flag word; crossings (optional) counts edge hops.
 inline int transport(const Mesh& m, int& face, double bary[3], V3& disp, V3* T, int nT, bool strictTrig = false, int* crossings = nullptr,
                      int boundaryMode = BOUNDARY_CLOSED)
@@ -162,7 +321,68 @@ inline int transport(const Mesh& m, int& face, double bary[3], V3& disp, V3* T, 
         int k = nh >= 2 ? hk[1] : hk[0];
         ORC_WALK_TRACE("hop %d face %d nh %d k %d S=(%.3e %.3e %.3e) E=(%.3e %.3e %.3e) |disp| %.3e adj %d\n", nCross, f, nh, k, S[0], S[1], S[2], E[0],
                        E[1], E[2], norm(disp), m.adj[3 * f + k]);
-        if (nh >= 2) flags |= WALK_VERTEX;                 // :520-532 (see header: treated as a crossing of the last hit edge)
+        if (nh >= 2 && hk[0] != hk[1]) {                   // :520-532 two edges hit: the path goes through their common vertex
+            flags |= WALK_VERTEX;
+            const int kv = 3 - hk[0] - hk[1];
+            const V3 travel = disp / norm(disp);           // direction of motion inside f (parallel to toIntersection, :516)
+            int g2 = -1;
+            V3 heading;
+            if (throughVertex(m, f, kv, travel, g2, heading)) {
+                V3 n2 = m.normal(g2);
+                double rem = norm(q - p);                  // what is left of the displacement beyond the vertex
+                V3 side = cross(n, travel), side2 = cross(n2, heading);
+                for (int i = 0; i < nT; ++i) {             // parallel transport: same components in the (path, side, normal) frames
+                    double ta = dot(T[i], travel), tb = dot(T[i], side), tc = dot(T[i], n);
+                    T[i] = ta * heading + tb * side2 + tc * n2;
+                }
+                disp = rem * heading;
+                q = p + disp;
+                f = g2;
+                ericsonBary(m.v[m.c[3 * f]], m.v[m.c[3 * f + 1]], m.v[m.c[3 * f + 2]], p, S); // :606
+                n = n2;
+                last = -1;                                 // :609-610
+                nCross++;
+                continue;
+            }
+            // boundary vertex (the fan is open): closed space stops (the reference throws, :522-523)
+            flags |= WALK_BORDER;
+            int w = -1;
+            if (boundaryMode == BOUNDARY_CLOSED || !boundaryVertexHeading(m, f, kv, travel, g2, w, heading)) {
+                E[0] = S[0], E[1] = S[1], E[2] = S[2];
+                break;
+            }
+            const int vIdx = m.c[3 * f + kv];
+            const V3 Pv = m.v[vIdx];
+            V3 rest = q - p;                               // remaining displacement
+            f = g2;                                        // openMeshSpace.cpp:63-67: the source moves to the vertex, seen from the new face
+            n = m.normal(f);
+            ericsonBary(m.v[m.c[3 * f]], m.v[m.c[3 * f + 1]], m.v[m.c[3 * f + 2]], Pv, S);
+            if (nT > 0) {                                  // projectVectorsForBoundaryVertex :72-100
+                V3 orth = cross(n, heading);
+                orth = orth / norm(orth);
+                V3 inside = Pv;
+                for (int j = 0; j < 3; ++j) {
+                    int cv = m.c[3 * f + j];
+                    if (cv != vIdx && cv != w) inside = m.v[cv];
+                }
+                projectVectorsIfOverBoundary(T, nT, orth, inside - Pv);
+            }
+            last = -1;
+            if (boundaryMode == BOUNDARY_ABSORBING) {      // absorbingOpenMeshSpace.cpp:26-50: stop at the vertex
+                E[0] = S[0], E[1] = S[1], E[2] = S[2];
+                break;
+            }
+            double slide = dot(rest, heading);             // tangentialOpenMeshSpace.cpp:42-64: projectVectorOntoDirection
+            if (!(slide > 1e-9 * norm(m.v[w] - Pv))) {
+                E[0] = S[0], E[1] = S[1], E[2] = S[2];
+                break;
+            }
+            disp = slide * heading;
+            p = m.point(f, S);
+            q = p + disp;
+            nCross++;
+            continue;
+        }
         int g = m.adj[3 * f + k];
         if (g < 0) {                                       // border edge
             flags |= WALK_BORDER;

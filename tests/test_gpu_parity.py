@@ -518,6 +518,78 @@ def test_dense_neighbourhoods_grow_the_stride(area_fraction, kmin, gpu_ctx_facto
     assert c["overflow"] == 0 and c["tier_retry"] > 0
 
 
+def test_stride_guard_regrows_inside_fused_steps(gpu_ctx_factory):
+    """More candidates than the neighbour stride (32) met for the first time INSIDE fused steps: at the first step of a fresh
+    context (css_step_nve, css_step_nve_host, NVT, FIRE, GD) and in the middle of CUDA-graph replays (a converging flow piles
+    the particles up).  The guard freezes the pipeline, the host regrows the stride, finishes the step and runs the rest:
+    the result equals the oracle's, which has no stride at all."""
+    V, F = _mesh("torus60x24")
+    for upd in ("nve", "nve_host", "nvt", "fire", "gd"):
+        orc, ctx, corners, face, bary, vel, rc, kind, params = _pair(V, F, 600, "harmonic", gpu_ctx_factory, area_fraction=12.0, want_end=False)
+        f0 = orc.compute_forces(kind, params)
+        ctx.set_state(face, bary, vel, f0)                   # no neighbour phase has run on the GPU yet: stride still 32
+        if upd == "nve":
+            orc.run_nve(kind, params, 0.01, 6)
+            ctx.step_nve(kind, params, 0.01, 6)
+        elif upd == "nve_host":
+            orc.run_nve(kind, params, 0.01, 2)
+            hf, hb, hv, hfr = face.copy(), bary.copy(), vel.copy(), f0.copy()
+            for _ in range(2):
+                ctx.step_nve_host(kind, params, 0.01, hf, hb.reshape(-1), hv.reshape(-1), hfr.reshape(-1))
+            of, ob, ov, ofr = orc.get_state()
+            assert np.array_equal(of, hf) and np.max(np.abs(ob - hb)) < 1e-9 and np.max(np.abs(ov - hv)) < 1e-9
+        elif upd == "nvt":
+            orc.nvt_init(0.01, 0.2, tau=1.0, M=2)
+            ctx.nvt_init(0.01, 0.2, tau=1.0, M=2)
+            orc.run_nvt(kind, params, 4)
+            ctx.step_nvt(kind, params, 4)
+        elif upd == "fire":
+            p = np.array([5, 0.01, 0.99, 0.1, 1e-5, 1.1, 0.95, 0.9, 4, 1e-12, 0.0])
+            orc.fire_init(p, dt0=0.01, alpha0=0.99)
+            ctx.fire_init(p, dt0=0.01, alpha0=0.99)
+            orc.run_fire(kind, params)
+            ctx.fire_minimize(kind, params)
+        else:
+            orc.run_gd(kind, params, 0.01, 4)
+            ctx.step_gd(kind, params, 0.01, 4)
+        of, ob, ov, ofr = orc.get_state()
+        gf, gb, gv, gfr = ctx.get_state()
+        ok = (orc.walk_flags() == 0) & (ctx.walk_flags() == 0)
+        assert np.array_equal(of[ok], gf[ok]), upd
+        assert np.max(np.abs(ob - gb)[ok]) < 1e-9 and np.max(np.abs(ov - gv)[ok]) < 1e-9, upd
+        assert np.max(np.abs(ofr - gfr)[ok]) < TOL_FORCE * np.abs(ofr).max(), upd
+        c = ctx.counters()
+        assert c["overflow"] == 0 and c["kmax_overflow"] == 0   # raised, handled and cleared
+    # mid-run: particles streaming towards one point of a sphere; the stride is exceeded after the graph has been captured
+    V, F = _mesh("icosphere16")
+    orc, ctx, corners, face, bary, vel, rc, kind, params = _pair(V, F, 400, "harmonic", gpu_ctx_factory, want_end=False)
+    x = orc.euclidean(face, bary)
+    pole = np.array([0.0, 0.0, 1.0])
+    tang = pole[None, :] - (x @ pole)[:, None] * x / np.sum(x * x, 1, keepdims=True)
+    c3 = corners[face]
+    n = np.cross(V[c3[:, 1]] - V[c3[:, 0]], V[c3[:, 2]] - V[c3[:, 0]])
+    n /= np.linalg.norm(n, axis=1, keepdims=True)
+    tang -= np.sum(tang * n, 1, keepdims=True) * n            # in the plane of each particle's face
+    vel = 1.2 * tang
+    orc.set_state(face, bary, vel)
+    ctx.set_state(face, bary, vel)
+    orc.compute_forces(kind, params)
+    ctx.compute_forces(kind, params)
+    assert np.diff(ctx.find_neighbors(rc)[0]).max() < 16
+    flagged = np.zeros(400, bool)
+    for _ in range(6):
+        orc.run_nve(kind, params, 0.01, 30)
+        ctx.step_nve(kind, params, 0.01, 30)
+        flagged |= (orc.walk_flags() != 0) | (ctx.walk_flags() != 0)
+    assert np.diff(orc.find_neighbors(rc)[0]).max() > 40      # the pile-up really went beyond the initial stride
+    of, ob, ov, ofr = orc.get_state()
+    gf, gb, gv, gfr = ctx.get_state()
+    ok = ~flagged
+    assert ok.sum() > 380 and np.array_equal(of[ok], gf[ok])
+    assert np.max(np.abs(orc.euclidean(of, ob) - orc.euclidean(gf, gb))[ok]) < TOL_TRAJ and np.max(np.abs(ov - gv)[ok]) < TOL_TRAJ
+    assert ctx.counters()["overflow"] == 0
+
+
 def test_error_convention(gpu_ctx_factory):
     ctx = gpu_ctx_factory()
     V, F = _mesh("cube1")
