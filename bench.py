@@ -341,7 +341,7 @@ def main():
     total_ms = max_over_ranks(float(np.sum(step_ms)))
     value = N * args.steps / (total_ms * 1e-3)
     queries = sum_over_ranks(float(cnt["queries"]))
-    geo_total_ms = max_over_ranks(float(np.sum(geo_ms)))
+    geo_total_ms = max(max_over_ranks(float(np.sum(geo_ms))), 1e-9)
 
     # ---- hot-L2 back-to-back bracket (same K steps, no flush): reported beside the headline
     barrier()
@@ -380,7 +380,7 @@ def main():
     ctx.synchronize()
     te_queries = sum_over_ranks(float(c1["queries"] - c0["queries"]))
     te_total = max_over_ranks(float(np.sum(te_step)))
-    te_geo_total = max_over_ranks(float(np.sum(te_geo)))
+    te_geo_total = max(max_over_ranks(float(np.sum(te_geo))), 1e-9)
 
     # ---- end to end through the C ABI with HOST buffers: every step uploads the step's inputs (positions, velocities,
     # forces) from pinned host memory, runs one step and reads the step's result back into the same pinned buffers; timed by
@@ -423,8 +423,8 @@ def main():
     pf, pv, kq = cnt["patch_faces"] / ns, cnt["patch_verts"] / ns, cnt["queries"] / ns
     b_step = 152 + 60 + 24 * pf + 24 * pv + 28 * kq + 36 * kq + (152 if nvt else 0)
     builder_bytes = (16 + 5 * kq + 5 * pv + 12 * pf) + 48 * pf + 24 * pv + 48 * kq + 52 + 36 * kq + 24 + 48
-    stage = {"k_patch": float(np.mean(patch_ms)), "k_windows_half": float(np.mean(win_ms))}
-    dom = max(stage, key=stage.get)
+    stage = {"k_patch": float(np.mean(patch_ms)), "k_windows_half": float(np.mean(win_ms)), "retry_tiers": float(np.mean(retry_ms))}
+    dom = max(stage, key=stage.get)  # retry_tiers = k_patch<Large> + k_windows<Large> + last tier: dominant only on coarse meshes (config 1)
     dom_ms = stage[dom]
     achieved = (b_step * nloc) / (dom_ms * 1e-3) / 1e9
     pk, pk_kind = peaks()
@@ -437,13 +437,14 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
                 "traffic": km.get("dram_bytes_per_launch"),
                 "peak_source": pk_kind + " (MEASURED_PEAKS.json hbm_gbs, burst copy)" if pk_kind == "measured" else "fallback 6650 GB/s",
-                "kernel": dom + (" (stage 2, two sources per warp: window propagation + queries + pair forces + half kick)" if dom == "k_windows_half"
-                                 else " (stage 1: ordered candidates + patch flood fill + local indexing)"),
+                "kernel": dom + {"k_windows_half": " (stage 2, two sources per warp: window propagation + queries + pair forces + half kick)",
+                                 "k_patch": " (stage 1: ordered candidates + patch flood fill + local indexing)",
+                                 "retry_tiers": " (large-capacity tier: k_patch<Large> + k_windows<Large>, one warp per source; patches above 96 faces)"}[dom],
                 "formula": "SURVEY 8(d): B_step = 152 + 60 + 24 P_f + 24 P_v + 64 K" + (" + 152 (second NVT move)" if nvt else ""),
                 "algorithmic_bytes_per_source": b_step, "builder_bytes_per_source": builder_bytes,
                 "frac_builder_bytes": (builder_bytes * nloc) / (dom_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
                 "kernel_ms_per_launch": dom_ms,
-                "kernel_share_of_step": max_over_ranks(float(np.sum(win_ms if dom == "k_windows_half" else patch_ms))) / inst_total_ms,
+                "kernel_share_of_step": max_over_ranks(float(np.sum({"k_windows_half": win_ms, "k_patch": patch_ms, "retry_tiers": retry_ms}[dom]))) / inst_total_ms,
                 "ms_per_step_with_phase_events": inst_total_ms / args.steps,
                 "other_kernels_ms_per_step": {"k_patch": stage["k_patch"], "k_windows_half": stage["k_windows_half"],
                                               "retry_tiers": float(np.mean(retry_ms)), "k_walk": float(np.mean(walk_ms)),

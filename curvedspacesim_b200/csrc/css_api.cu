@@ -912,7 +912,8 @@ static int setupGrid(css_ctx* ctx, double range)
     }
     ctx->grid.range2 = range * range;
     if (ctx->nCells > ctx->capCells) {
-        CU(regrow(ctx->d_cellCount, (size_t)ctx->nCells + 1));
+        // counts | bump counter | occupancy of the 2x2x2 coarse blocks (sharded runs: replicated stride bound), cleared together
+        CU(regrow(ctx->d_cellCount, 2 * (size_t)ctx->nCells + 2)); // (a coarse grid never has more blocks than the grid has cells)
         CU(regrow(ctx->d_cellStart, (size_t)ctx->nCells + 1));
         ctx->capCells = ctx->nCells;
     }
@@ -928,10 +929,13 @@ static int findNeighborsImpl(css_ctx* ctx, double range, int forceMode, ForcePar
     if (ctx->timing) recordEvent(ctx, ctx->ev[0]);
     if (ctx->useCellList) {
         if ((rc = setupGrid(ctx, range))) return rc;
-        CU(cudaMemsetAsync(ctx->d_cellCount, 0, sizeof(int) * ((size_t)ctx->nCells + 1), ctx->st));
-        launchEuclidCell(ctx->st, m, ctx->grid, ctx->nTotal, ctx->d_face, ctx->d_bary, ctx->d_eucl, ctx->d_cellOf, ctx->d_cellCount, ctx->d_cellSlot);
+        const size_t nCoarse = (size_t)((ctx->grid.n[0] + 1) / 2) * ((ctx->grid.n[1] + 1) / 2) * ((ctx->grid.n[2] + 1) / 2);
+        int* coarse = ctx->nranks > 1 ? ctx->d_cellCount + ctx->nCells + 1 : nullptr;
+        CU(cudaMemsetAsync(ctx->d_cellCount, 0, sizeof(int) * ((size_t)ctx->nCells + 1 + (coarse ? nCoarse : 0)), ctx->st));
+        launchEuclidCell(ctx->st, m, ctx->grid, ctx->nTotal, ctx->d_face, ctx->d_bary, ctx->d_eucl, ctx->d_cellOf, ctx->d_cellCount, ctx->d_cellSlot,
+                         coarse);
         launchCellBuild(ctx->st, ctx->nTotal, ctx->nCells, ctx->d_cellOf, ctx->d_cellSlot, ctx->d_cellCount, ctx->d_cellStart, ctx->d_tmpItems,
-                        ctx->d_items, ctx->grid, ctx->kmax, ctx->d_counters);
+                        ctx->d_items, coarse, ctx->grid, ctx->kmax, ctx->d_counters);
         ctx->hostKernels += 4;
     } else {
         launchEuclidCell(ctx->st, m, ctx->grid, ctx->nTotal, ctx->d_face, ctx->d_bary, ctx->d_eucl, nullptr, nullptr, nullptr);
@@ -992,6 +996,16 @@ static int checkCapacity(css_ctx* ctx, bool* rerun, int* stepsDone = nullptr)
         return fail(ctx, CSS_ENCCL, "peer position exchange timed out (%llu flag waits gave up): a rank left the collective sequence", h[C_PEER_TIMEOUT]);
     }
     return CSS_OK;
+}
+
+// phase durations of the last launches (the stream has been synchronised by the caller)
+static void readPhaseTimes(css_ctx* ctx, bool walked)
+{
+    if (!ctx->timing) return;
+    if (cudaEventElapsedTime(&ctx->msCell, ctx->ev[0], ctx->ev[1]) != cudaSuccess) ctx->msCell = 0;
+    if (cudaEventElapsedTime(&ctx->msGeo, ctx->ev[1], ctx->ev[2]) != cudaSuccess) ctx->msGeo = 0;
+    if (walked && cudaEventElapsedTime(&ctx->msWalk, ctx->ev[3], ctx->ev[4]) != cudaSuccess) ctx->msWalk = 0;
+    (void)cudaGetLastError();
 }
 
 static ForceParams mkForce(int kind, const double* p, double* range)
@@ -1533,7 +1547,9 @@ int css_step_nvt(css_ctx* ctx, int kind, const double* params, int nsteps)
         launchAxpy(ctx->st, 2, ctx->nLocal, h.scale, 0, ctx->d_vel, ctx->d_frc, ctx->d_disp);
         ctx->hostKernels++;
     }
-    return checkCapacity(ctx, nullptr);
+    int rc = checkCapacity(ctx, nullptr);
+    if (nsteps > 0) readPhaseTimes(ctx, true);
+    return rc;
 }
 int css_nvt_state(css_ctx* ctx, double* bath, double* ke, double* scale)
 {
@@ -1612,7 +1628,9 @@ int css_fire_minimize(css_ctx* ctx, int kind, const double* params, double* out)
         f.forceMax = std::sqrt(r[3]);
     }
     if (out) out[0] = f.iterations, out[1] = f.forceMax, out[2] = f.dt, out[3] = f.alpha;
-    return checkCapacity(ctx, nullptr);
+    rc = checkCapacity(ctx, nullptr);
+    readPhaseTimes(ctx, f.iterations > 0);
+    return rc;
 }
 
 // --------------------------------------------------------------------------------------- multi-GPU

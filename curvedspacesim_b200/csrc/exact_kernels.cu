@@ -103,8 +103,10 @@ __device__ __forceinline__ d3 rotateAboutAxis(const d3& p, const d3& base, const
 }
 
 // ------------------------------------------------------------------------------------------------
+// coarse (optional, sharded runs only): occupancy of the 2x2x2 blocks of cells, for the replicated stride bound of k_cell_rank
 __global__ void k_euclid_cell(MeshDev m, CellGrid g, int n, const int* __restrict__ face, const double* __restrict__ bary,
-                              double* __restrict__ eucl, int* __restrict__ cellOf, int* __restrict__ cellCount, int* __restrict__ cellSlot)
+                              double* __restrict__ eucl, int* __restrict__ cellOf, int* __restrict__ cellCount, int* __restrict__ cellSlot,
+                              int* __restrict__ coarse)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -117,6 +119,7 @@ __global__ void k_euclid_cell(MeshDev m, CellGrid g, int n, const int* __restric
         int c = ix + iy * g.n[0] + iz * g.n[0] * g.n[1];
         cellOf[i] = c;
         cellSlot[i] = atomicAdd(cellCount + c, 1); // arrival order inside the cell; the first arrival places the cell (k_cell_place)
+        if (coarse) atomicAdd(coarse + (ix >> 1) + (iy >> 1) * ((g.n[0] + 1) >> 1) + (iz >> 1) * ((g.n[0] + 1) >> 1) * ((g.n[1] + 1) >> 1), 1);
     }
 }
 
@@ -153,10 +156,13 @@ __global__ void k_cell_fill(int n, const int* __restrict__ cellOf, const int* __
     tmpItems[cellStart[cellOf[i]] + cellSlot[i]] = i;
 }
 // rank of particle i inside its cell = number of members with a smaller index
-// ... and the stride guard (common.cuh): the occupancy of the particle's 27-cell stencil bounds its candidate count
+// ... and, in sharded runs (coarse != nullptr), the replicated half of the stride guard (common.cuh): the particle's 3x3x3 cell
+// stencil lies inside 2x2x2 coarse blocks, whose occupancy therefore bounds its candidate count.  Every rank evaluates the
+// bound for ALL particles from the replicated positions, so every rank raises the guard in the same step without talking to
+// the others.  (On one rank the exact candidate count found by stage 1 raises it, at no cost.)
 __global__ void k_cell_rank(int n, const int* __restrict__ cellOf, const int* __restrict__ cellStart, const int* __restrict__ cellCount,
-                            const int* __restrict__ tmpItems, int* __restrict__ items, int nx, int ny, int nz, int kmax,
-                            unsigned long long* __restrict__ counters)
+                            const int* __restrict__ tmpItems, int* __restrict__ items, const int* __restrict__ coarse, int nx, int ny, int nz,
+                            int kmax, unsigned long long* __restrict__ counters)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int occ = 0;
@@ -166,12 +172,18 @@ __global__ void k_cell_rank(int n, const int* __restrict__ cellOf, const int* __
         int r = 0;
         for (int s = 0; s < cnt; ++s) r += (tmpItems[s0 + s] < i);
         items[s0 + r] = i;
-        const int ix = c % nx, iy = (c / nx) % ny, iz = c / (nx * ny);
-        for (int xx = max(0, ix - 1); xx <= min(nx - 1, ix + 1); ++xx)
-            for (int yy = max(0, iy - 1); yy <= min(ny - 1, iy + 1); ++yy)
-                for (int zz = max(0, iz - 1); zz <= min(nz - 1, iz + 1); ++zz) occ += cellCount[xx + yy * nx + zz * nx * ny];
-        occ -= 1; // the particle itself
+        if (coarse) {
+            const int ix = c % nx, iy = (c / nx) % ny, iz = c / (nx * ny);
+            const int cx = (nx + 1) >> 1, cy = (ny + 1) >> 1;
+            const int x0 = max(0, ix - 1) >> 1, x1 = min(nx - 1, ix + 1) >> 1, y0 = max(0, iy - 1) >> 1, y1 = min(ny - 1, iy + 1) >> 1;
+            const int z0 = max(0, iz - 1) >> 1, z1 = min(nz - 1, iz + 1) >> 1;
+            for (int zz = z0; zz <= z1; ++zz)
+                for (int yy = y0; yy <= y1; ++yy)
+                    for (int xx = x0; xx <= x1; ++xx) occ += coarse[xx + yy * cx + zz * cx * cy];
+            occ -= 1; // the particle itself
+        }
     }
+    if (!coarse) return;
     occ = __reduce_max_sync(0xffffffffu, occ);
     if ((threadIdx.x & 31) == 0 && occ > kmax) {
         atomicMax(counters + C_KMAX_NEED, (unsigned long long)occ);
@@ -979,18 +991,18 @@ void launchLocate(cudaStream_t st, const MeshDev& m, const double gmn[3], double
 static inline int gridFor(int n, int b) { return (n + b - 1) / b; }
 
 void launchEuclidCell(cudaStream_t st, const MeshDev& m, const CellGrid& g, int n, const int* face, const double* bary, double* eucl,
-                      int* cellOf, int* cellCount, int* cellSlot)
+                      int* cellOf, int* cellCount, int* cellSlot, int* coarse)
 {
-    if (n > 0) k_euclid_cell<<<gridFor(n, 256), 256, 0, st>>>(m, g, n, face, bary, eucl, cellOf, cellCount, cellSlot);
+    if (n > 0) k_euclid_cell<<<gridFor(n, 256), 256, 0, st>>>(m, g, n, face, bary, eucl, cellOf, cellCount, cellSlot, coarse);
 }
 // cellCount[nCells] is the bump counter (cleared with the counts)
 void launchCellBuild(cudaStream_t st, int n, int nCells, const int* cellOf, const int* cellSlot, int* cellCount, int* cellStart, int* tmpItems,
-                     int* items, const CellGrid& g, int kmax, unsigned long long* counters)
+                     int* items, const int* coarse, const CellGrid& g, int kmax, unsigned long long* counters)
 {
     if (n <= 0) return;
     k_cell_place<<<gridFor(n, 256), 256, 0, st>>>(n, cellOf, cellSlot, cellCount, cellStart, cellCount + nCells);
     k_cell_fill<<<gridFor(n, 256), 256, 0, st>>>(n, cellOf, cellSlot, cellStart, tmpItems);
-    k_cell_rank<<<gridFor(n, 256), 256, 0, st>>>(n, cellOf, cellStart, cellCount, tmpItems, items, g.n[0], g.n[1], g.n[2], kmax, counters);
+    k_cell_rank<<<gridFor(n, 256), 256, 0, st>>>(n, cellOf, cellStart, cellCount, tmpItems, items, coarse, g.n[0], g.n[1], g.n[2], kmax, counters);
 }
 void launchWalk(cudaStream_t st, const MeshDev& m, int n, int minIdx, int* face, double* bary, double* disp, double* vel, double* frc,
                 int transportForce, int transportVelocity, int mode, double dt, int* flags, unsigned long long* counters, const PeerWin& pw)

@@ -171,9 +171,9 @@ size_t windowsHalfSpillBytes(int numSMs);
 int geodesicMaxSmemPerBlock();
 
 void launchEuclidCell(cudaStream_t st, const MeshDev& m, const CellGrid& g, int n, const int* face, const double* bary, double* eucl,
-                      int* cellOf, int* cellCount, int* cellSlot);
+                      int* cellOf, int* cellCount, int* cellSlot, int* coarse = nullptr);
 void launchCellBuild(cudaStream_t st, int n, int nCells, const int* cellOf, const int* cellSlot, int* cellCount, int* cellStart, int* tmpItems,
-                     int* items, const CellGrid& g, int kmax, unsigned long long* counters);
+                     int* items, const int* coarse, const CellGrid& g, int kmax, unsigned long long* counters);
 // ---- peer-memory position exchange, fused with the walker (replaces the all-gather after every move:
 // mpiSimulation::synchronizeAndTransferBuffers, src/simulation/mpiSimulation.cpp:11-42).  Every rank owns an exchange
 // window (cudaMalloc + CUDA IPC, mapped by all peers over NVLink/NVSwitch): a staging copy of the replicated position

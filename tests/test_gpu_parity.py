@@ -700,7 +700,8 @@ def test_full_size_properties(workload, gpu_ctx_factory):
       * idempotence: a second call returns the same bits."""
     import bench
 
-    V, F, corners, face, bary, vel, N, rc = bench.build_workload(workload)
+    wl = bench.Workload(workload, 0.01)
+    V, F, corners, face, bary, vel, N, rc = wl.V, wl.F, wl.corners, wl.face, wl.bary, wl.vel, wl.N, wl.rc
     ctx = gpu_ctx_factory()
     ctx.set_mesh(V, corners)
     ctx.set_submeshing(True, rc)
@@ -764,7 +765,8 @@ def test_full_size_properties(workload, gpu_ctx_factory):
 def test_full_size_step_is_deterministic_and_flag_free(gpu_ctx_factory):
     import bench
 
-    V, F, corners, face, bary, vel, N, rc = bench.build_workload("cfg4_icosphere_250kfaces_N25k")
+    wl = bench.Workload("cfg4_icosphere_250kfaces_N25k", 0.01)
+    V, F, corners, face, bary, vel, N, rc = wl.V, wl.F, wl.corners, wl.face, wl.bary, wl.vel, wl.N, wl.rc
     kind, params = force_params("harmonic", k=1.0, sigma=rc)
     res = []
     for _ in range(2):
