@@ -6,7 +6,7 @@
 namespace css {
 
 // ---- mesh in HBM (L2-resident at 1 M faces: 16 MB vertices + 16 MB corners + 16 MB adjacency) ----
-// vertices : double4 {x,y,z,0}   one 32-byte sector per gather
+// vertices : double4 {x,y,z,s}   one 32-byte sector per gather; s = 1.0 when the vertex is a saddle (angle sum >= 2 pi), else 0
 // corners  : int4 {c0,c1,c2,0}   reference corner order
 // adjacency: int4 {a0,a1,a2,kk}  a_k = face across the edge opposite corner k (-1 border);
 //                                kk packs the index of that edge inside the neighbour, 2 bits per k
@@ -21,6 +21,9 @@ struct MeshDev {
     // geo[3 f + e] = {cxn, cyn}; lets a window be unfolded across a face with four FMAs and no 3-D geometry.
     const double2* geo;
     int boundary; // walker at a border edge: 0 closed space (flag + stop), 1 absorbing, 2 tangential (openMeshSpace variants)
+    // flood-fill table of stage 1, two int4 per face (one 32-byte sector): {a0,a1,a2,kk} as in `adj`, then {o0,o1,o2,0} with
+    // o_k = the vertex of neighbour a_k that lies opposite the shared edge (-1 at a border)
+    const int4* adjopp;
 };
 
 struct CellGrid {

@@ -28,6 +28,7 @@ struct css_ctx {
     double4* d_vert = nullptr;
     int4* d_corner = nullptr;
     int4* d_adj = nullptr;
+    int4* d_adjopp = nullptr; // [2 nF] flood-fill table of stage 1 (common.cuh MeshDev::adjopp)
     unsigned char* d_saddle = nullptr;
     double2* d_geo = nullptr; // edge frames, [3 nF]
     double bbmin[3] = {0, 0, 0}, bbmax[3] = {0, 0, 0}, area = 0;
@@ -323,7 +324,7 @@ int css_destroy(css_ctx* ctx)
                     ctx->d_cellSlot, ctx->d_tmpItems, ctx->d_items,  ctx->d_nbrCount, ctx->d_nbrIdx,  ctx->d_nbrDist,
                     ctx->d_nbrTs,  ctx->d_nbrTe,     ctx->d_work,    ctx->d_retry[0], ctx->d_retry[1], ctx->d_retry[2], ctx->d_gws,
                     ctx->d_partial, ctx->d_red,      ctx->d_counters, ctx->d_sendI,  ctx->d_sendD,    ctx->d_recvI,   ctx->d_recvD,
-                    ctx->d_redBuf,  ctx->d_geo,       ctx->d_records, ctx->d_recordsL, ctx->d_epoch, ctx->d_ticket, ctx->d_ipcBuf, ctx->d_spill, ctx->d_fgStart, ctx->d_fgFaces};
+                    ctx->d_redBuf,  ctx->d_geo,       ctx->d_records, ctx->d_recordsL, ctx->d_epoch, ctx->d_ticket, ctx->d_ipcBuf, ctx->d_spill, ctx->d_fgStart, ctx->d_fgFaces, ctx->d_adjopp};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (auto& e : ctx->ev)
@@ -374,6 +375,16 @@ int css_set_mesh(css_ctx* ctx, int nV, const double* xyz, int nF, const int32_t*
         hc[f] = make_int4(corners[3 * f], corners[3 * f + 1], corners[3 * f + 2], 0);
         ha[f] = make_int4(a3[0], a3[1], a3[2], kk);
     }
+    std::vector<int4> hao(2 * (size_t)nF);
+    for (int f = 0; f < nF; ++f) {
+        int o3[3];
+        for (int k = 0; k < 3; ++k) {
+            const int g = k == 0 ? ha[f].x : (k == 1 ? ha[f].y : ha[f].z);
+            o3[k] = g < 0 ? -1 : corners[3 * g + ((ha[f].w >> (2 * k)) & 3)]; // corner kk of g is opposite its edge kk
+        }
+        hao[2 * (size_t)f] = ha[f];
+        hao[2 * (size_t)f + 1] = make_int4(o3[0], o3[1], o3[2], 0);
+    }
     // bounding box seeded with the origin (triangulatedMeshSpace::updateMeshSpanAndTree :9-30), area, angle sums
     std::vector<double4> hv(nV);
     for (int d = 0; d < 3; ++d) ctx->bbmin[d] = ctx->bbmax[d] = 0;
@@ -413,12 +424,14 @@ int css_set_mesh(css_ctx* ctx, int nV, const double* xyz, int nF, const int32_t*
                                                  std::sqrt(cr[0] * cr[0] + cr[1] * cr[1] + cr[2] * cr[2]) / l2);
         }
     std::vector<unsigned char> sad(nV);
-    for (int i = 0; i < nV; ++i) sad[i] = ang[i] >= 2.0 * M_PI - 1e-9;
+    for (int i = 0; i < nV; ++i) sad[i] = ang[i] >= 2.0 * M_PI - 1e-9, hv[i].w = sad[i] ? 1.0 : 0.0;
     for (int d = 0; d < 3; ++d) ctx->cellMin[d] = ctx->bbmin[d], ctx->cellMax[d] = ctx->bbmax[d];
     ctx->gridRange = -1;
     CU(regrow(ctx->d_vert, nV));
     CU(regrow(ctx->d_corner, nF));
     CU(regrow(ctx->d_adj, nF));
+    CU(regrow(ctx->d_adjopp, 2 * (size_t)nF));
+    CU(cudaMemcpy(ctx->d_adjopp, hao.data(), sizeof(int4) * 2 * (size_t)nF, cudaMemcpyHostToDevice));
     CU(regrow(ctx->d_saddle, nV));
     CU(regrow(ctx->d_geo, 3 * (size_t)nF));
     CU(cudaMemcpy(ctx->d_geo, hg.data(), sizeof(double2) * 3 * (size_t)nF, cudaMemcpyHostToDevice));
@@ -487,7 +500,7 @@ int css_set_options(css_ctx* ctx, int useCellList, int wantEndTangents)
     return CSS_OK;
 }
 
-static MeshDev meshDev(css_ctx* c) { return MeshDev{c->nV, c->nF, c->d_vert, c->d_corner, c->d_adj, c->d_saddle, c->d_geo, c->boundaryMode}; }
+static MeshDev meshDev(css_ctx* c) { return MeshDev{c->nV, c->nF, c->d_vert, c->d_corner, c->d_adj, c->d_saddle, c->d_geo, c->boundaryMode, c->d_adjopp}; }
 
 // ------------------------------------------------------------------------------- per-call parity
 int css_euclidean(css_ctx* ctx, int n, const int32_t* face, const double* bary, double* xyz)
@@ -687,6 +700,7 @@ static int runGeodesicTiers(css_ctx* ctx, GeoArgs a, int nSrc)
         PatchArgs p{};
         p.m = a.m, p.grid = a.grid, p.nLocal = a.nLocal, p.minIdx = a.minIdx;
         p.face = a.face, p.eucl = a.eucl, p.cellStart = a.cellStart, p.cellCount = a.cellCount, p.cellItems = a.cellItems;
+        p.cellOf = ctx->d_cellOf, p.invNx = 1.0 / a.grid.n[0], p.invNxy = 1.0 / ((double)a.grid.n[0] * a.grid.n[1]);
         p.submeshing = a.submeshing, p.maxDist = a.maxDist, p.kmax = a.kmax;
         p.counters = ctx->d_counters;
         WinArgs w{};
@@ -1235,7 +1249,7 @@ static uint64_t nveGraphKey(css_ctx* ctx, const ForceParams& fp, double range, d
     MIX(fp.kind), MIX(fp.a), MIX(fp.sigma), MIX(range), MIX(dt);
     MIX(ctx->nLocal), MIX(ctx->nTotal), MIX(ctx->minIdx), MIX(ctx->kmax), MIX(ctx->nranks), MIX(ctx->timing), MIX(ctx->submeshing),
         MIX(ctx->maxDist), MIX(ctx->boundaryMode), MIX(ctx->useCellList), MIX(ctx->wantEnd), MIX(ctx->twoStage), MIX(ctx->winWpb), MIX(ctx->winLean), MIX(ctx->winHalf), MIX(ctx->grid), MIX(ctx->nCells);
-    void* ptrs[] = {ctx->d_vert, ctx->d_corner, ctx->d_adj, ctx->d_geo, ctx->d_saddle, ctx->d_face, ctx->d_bary, ctx->d_eucl, ctx->d_vel, ctx->d_frc,
+    void* ptrs[] = {ctx->d_vert, ctx->d_corner, ctx->d_adj, ctx->d_adjopp, ctx->d_geo, ctx->d_saddle, ctx->d_face, ctx->d_bary, ctx->d_eucl, ctx->d_vel, ctx->d_frc,
                     ctx->d_disp, ctx->d_walkFlags, ctx->d_cellOf, ctx->d_cellCount, ctx->d_cellStart, ctx->d_cellSlot, ctx->d_tmpItems,
                     ctx->d_items, ctx->d_nbrCount, ctx->d_nbrIdx, ctx->d_nbrDist, ctx->d_nbrTs, ctx->d_nbrTe, ctx->d_retry[0], ctx->d_retry[1],
                     ctx->d_retry[2], ctx->d_gws, ctx->d_records, ctx->d_recordsL, ctx->d_spill, ctx->d_recvI, ctx->d_recvD, (void*)ctx->comm, ctx->winLocal,

@@ -120,6 +120,8 @@ struct PatchArgs {
     const int* cellStart;
     const int* cellCount;
     const int* cellItems;
+    const int* cellOf;    // [nTotal] linear cell index of every particle (k_euclid_cell)
+    double invNx, invNxy; // 1 / grid.n[0], 1 / (grid.n[0] grid.n[1])
     int submeshing;
     double maxDist;
     int kmax;

@@ -12,6 +12,7 @@ nvcc $COMMON "$@" -c $D/patch_kernel.cu -o $OUT/patch.o &
 nvcc $COMMON "$@" -c $D/window_kernel.cu -o $OUT/win.o &
 nvcc $COMMON "$@" -c $D/window_half_kernel.cu -o $OUT/winhalf.o &
 nvcc $COMMON "$@" -c $D/css_api.cu -o $OUT/api.o &
+nvcc $COMMON "$@" -c $D/microbench.cu -o $OUT/micro.o &
 wait
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -o curvedspacesim_b200/libvariant_$NAME.so $OUT/*.o -lnccl
 echo built curvedspacesim_b200/libvariant_$NAME.so

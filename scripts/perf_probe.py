@@ -17,8 +17,9 @@ _cache = {}
 
 def run(workload, steps=int(os.environ.get("PROBE_STEPS", "5")), label=""):
     if workload not in _cache:
-        _cache[workload] = bench.build_workload(workload)
-    V, F, corners, face, bary, vel, N, rc = _cache[workload]
+        _cache[workload] = bench.Workload(workload, 0.01)
+    wl = _cache[workload]
+    V, F, corners, face, bary, vel, N, rc = wl.V, wl.F, wl.corners, wl.face, wl.bary, wl.vel, wl.N, wl.rc
     kind, params = binding.force_params("harmonic", k=1.0, sigma=rc)
     ctx = binding.Context(0)
     ctx.set_mesh(V, corners)
