@@ -29,15 +29,6 @@ namespace css {
 
 namespace {
 
-template <class T> struct PatchSmem { // per-warp scratch
-    int fhKey[T::HASHF];             // global face id -> slot
-    int vhKey[T::HASHV];             // global vertex id -> slot
-    unsigned char fhVal[T::HASHF];   // slot -> local face id
-    unsigned char vhVal[T::HASHV];   // slot -> local vertex id
-    int misc[4];                     // nF, nV, overflow
-    alignas(16) unsigned char rec[T::BYTES];
-};
-
 __device__ __forceinline__ unsigned hashInt(int k) { return (unsigned)k * 2654435761u; }
 
 __device__ __forceinline__ int hashInsert(int* keys, int mask, int key, bool& isNew)
@@ -75,219 +66,6 @@ __device__ __forceinline__ int warpInclusiveScan(int v, int lane)
     }
     return v;
 }
-__device__ __forceinline__ double warpMaxD(double v)
-{
-#pragma unroll
-    for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
-    return v;
-}
-
-// returns 0 ok, 1 overflow (source goes to the retry tiers)
-template <class T> __device__ int buildPatch(const PatchArgs& a, PatchSmem<T>& s, int li, int lane)
-{
-    constexpr int HF = T::HASHF, HV = T::HASHV;
-    const int gi = a.minIdx + li;
-    int* tIdx = reinterpret_cast<int*>(s.rec + T::OFF_TIDX);
-    int* gface = reinterpret_cast<int*>(s.rec + T::OFF_GFACE);
-    int* gvert = reinterpret_cast<int*>(s.rec + T::OFF_GVERT);
-    unsigned char* tFace = s.rec + T::OFF_TFACE;
-    unsigned char* velig = s.rec + T::OFF_VELIG;
-    uchar4* fvert = reinterpret_cast<uchar4*>(s.rec + T::OFF_FVERT);
-    uchar4* fadj = reinterpret_cast<uchar4*>(s.rec + T::OFF_FADJ);
-    int* hdr = reinterpret_cast<int*>(s.rec);
-
-    const int sf = a.face[gi];
-    const d3 sp{a.eucl[3 * gi], a.eucl[3 * gi + 1], a.eucl[3 * gi + 2]};
-
-    // ---------------- 1. ordered candidates ----------------
-    int K = 0;
-    double R;
-    {
-        const CellGrid& g = a.grid;
-        int ix = cellCoord(g, sp.x, 0), iy = cellCoord(g, sp.y, 1), iz = cellCoord(g, sp.z, 2);
-        int x0 = max(0, ix - 1), x1 = min(g.n[0] - 1, ix + 1);
-        int y0 = max(0, iy - 1), y1 = min(g.n[1] - 1, iy + 1);
-        int z0 = max(0, iz - 1), z1 = min(g.n[2] - 1, iz + 1);
-        int ny = y1 - y0 + 1, nz = z1 - z0 + 1, ncell = (x1 - x0 + 1) * ny * nz;
-        int s0 = 0, s1 = 0;
-        if (lane < ncell) { // stencil order: xx outer, yy, zz inner
-            int xx = x0 + lane / (ny * nz), rem = lane % (ny * nz);
-            int yy = y0 + rem / nz, zz = z0 + rem % nz;
-            int c = xx + yy * g.n[0] + zz * g.n[0] * g.n[1];
-            s0 = a.cellStart[c];
-            s1 = s0 + a.cellCount[c];
-        }
-        // one pass: each lane keeps the first few hits of its cell in registers (cells hold ~0.3 particles
-        // on average at the target densities); a second pass over the cell is taken only when it has more
-        int mine = 0, h0 = -1, h1 = -1, h2 = -1, h3 = -1;
-        double maxd2 = 0;
-        for (int q = s0; q < s1; ++q) {
-            int j = a.cellItems[q];
-            if (j == gi) continue;
-            d3 p{a.eucl[3 * j], a.eucl[3 * j + 1], a.eucl[3 * j + 2]};
-            double d2 = xsqlen(xsub3(sp, p));
-            if (d2 < g.range2) {
-                if (mine == 0) h0 = j;
-                else if (mine == 1) h1 = j;
-                else if (mine == 2) h2 = j;
-                else if (mine == 3) h3 = j;
-                mine++;
-                maxd2 = d2 > maxd2 ? d2 : maxd2;
-            }
-        }
-        int incl = warpInclusiveScan(mine, lane);
-        K = __shfl_sync(FULL, incl, 31);
-        if (K > a.kmax) { // neighbour stride too small: the host doubles it and reruns the step
-            if (lane == 0) atomicMax(a.counters + C_KMAX_NEED, (unsigned long long)K), atomicAdd(a.counters + C_KMAX_OVERFLOW, 1ull);
-            return 1;
-        }
-        if (K > T::RECK) return 2; // 1 + reason (0 candidates, 1 faces, 2 vertices)
-        maxd2 = warpMaxD(maxd2);
-        R = xsqrt(maxd2);
-        int pos = incl - mine;
-        if (mine <= 4) {
-            if (mine > 0) tIdx[pos] = h0;
-            if (mine > 1) tIdx[pos + 1] = h1;
-            if (mine > 2) tIdx[pos + 2] = h2;
-            if (mine > 3) tIdx[pos + 3] = h3;
-        } else {
-            for (int q = s0; q < s1; ++q) {
-                int j = a.cellItems[q];
-                if (j == gi) continue;
-                d3 p{a.eucl[3 * j], a.eucl[3 * j + 1], a.eucl[3 * j + 2]};
-                if (xsqlen(xsub3(sp, p)) < g.range2) tIdx[pos++] = j;
-            }
-        }
-    }
-    if (lane == 0) hdr[2] = K;
-    if (K == 0) {
-        if (lane == 0) hdr[0] = 0, hdr[1] = 0, hdr[3] = 0;
-        return 0;
-    }
-    double thr2 = __longlong_as_double(0x7ff0000000000000LL);
-    if (a.submeshing) { // triangulatedMeshSpace::distanceWithSubmeshing :167-169
-        double thr = a.maxDist;
-        if (R < a.maxDist) thr = R;
-        thr2 = xmul(thr, thr);
-    }
-
-    // ---------------- 2. flood fill ----------------
-    for (int h = lane; h < HF; h += 32) s.fhKey[h] = -1;
-    for (int h = lane; h < HV; h += 32) s.vhKey[h] = -1;
-    if (lane == 0) s.misc[0] = 0, s.misc[1] = 0, s.misc[2] = 0;
-    __syncwarp();
-    auto addFace = [&](int g) {
-        bool isNew;
-        int slot = hashInsert(s.fhKey, HF - 1, g, isNew);
-        if (isNew) {
-            int id = atomicAdd(&s.misc[0], 1);
-            if (id < T::MAXF) {
-                gface[id] = g;
-                s.fhVal[slot] = (unsigned char)id;
-            } else
-                s.misc[2] = 1;
-        }
-    };
-    int myTF = lane < K ? a.face[tIdx[lane]] : sf; // K <= T::RECK <= 32: one target per lane
-    if (lane == 0) addFace(sf);
-    __syncwarp();
-    if (__any_sync(FULL, myTF != sf)) {
-        int4 sadj = __ldg(a.m.adj + sf);
-        if (lane < 3) {
-            int g = lane == 0 ? sadj.x : (lane == 1 ? sadj.y : sadj.z);
-            if (g >= 0) addFace(g);
-        }
-        __syncwarp();
-        if (__any_sync(FULL, hashFind(s.fhKey, HF - 1, myTF) < 0)) {
-            // frontier faces [head, tail) x 3 edges, one (face, edge) pair per lane: 10 faces per pass
-            int head = 1;
-            for (;;) {
-                __syncwarp();
-                // one lane's view of the queue for the whole warp: a lane that read it later could already see pushes of this
-                // pass, and lanes disagreeing on `head` would leave the loop at different times
-                const int tail = min(__shfl_sync(FULL, s.misc[0], 0), T::MAXF);
-                if (__shfl_sync(FULL, s.misc[2], 0)) return 3;
-                if (head >= tail) break;
-                int slotF = lane / 3, k = lane - 3 * slotF;
-                int idx = head + slotF;
-                if (slotF < 10 && idx < tail) {
-                    int4 ad = __ldg(a.m.adj + gface[idx]);
-                    int g = k == 0 ? ad.x : (k == 1 ? ad.y : ad.z);
-                    if (g >= 0 && hashFind(s.fhKey, HF - 1, g) < 0) {
-                        int4 c = __ldg(a.m.corner + g);
-                        d3 p0 = ldvert(a.m, c.x), p1 = ldvert(a.m, c.y), p2 = ldvert(a.m, c.z);
-                        bool far = xsqlen(xsub3(sp, p0)) > thr2 && xsqlen(xsub3(sp, p1)) > thr2 && xsqlen(xsub3(sp, p2)) > thr2;
-                        if (!far) {
-                            if (s.misc[0] >= T::MAXF) s.misc[2] = 1;
-                            else addFace(g);
-                        }
-                    }
-                }
-                head = min(head + 10, tail);
-            }
-            if (hashFind(s.fhKey, HF - 1, myTF) < 0) { // leftover goal faces (submesher.cpp:143-144)
-                if (s.misc[0] >= T::MAXF) s.misc[2] = 1;
-                else addFace(myTF);
-            }
-        }
-    }
-    __syncwarp();
-    if (s.misc[2] || s.misc[0] > T::MAXF) return 3;
-    const int nF = s.misc[0];
-
-    // ---------------- 3. local indexing ----------------
-    for (int f = lane; f < nF; f += 32) {
-        int4 c = __ldg(a.m.corner + gface[f]);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            int gv = k == 0 ? c.x : (k == 1 ? c.y : c.z);
-            bool isNew;
-            int slot = hashInsert(s.vhKey, HV - 1, gv, isNew);
-            if (isNew) {
-                int id = atomicAdd(&s.misc[1], 1);
-                if (id < T::MAXV) {
-                    gvert[id] = gv;
-                    s.vhVal[slot] = (unsigned char)id;
-                } else
-                    s.misc[2] = 1;
-            }
-        }
-        if (s.misc[2]) break; // the table is sized 2 x T::MAXV + 3 x 32 in-flight inserts: it cannot fill up before this trips
-    }
-    __syncwarp();
-    if (s.misc[2] || s.misc[1] > T::MAXV) return 4;
-    const int nV = s.misc[1];
-    for (int v = lane; v < nV; v += 32) velig[v] = a.m.saddle[gvert[v]];
-    __syncwarp();
-    for (int f = lane; f < nF; f += 32) {
-        int gf = gface[f];
-        int4 c = __ldg(a.m.corner + gf);
-        int4 ad = __ldg(a.m.adj + gf);
-        unsigned char lv[3], la[3];
-        lv[0] = s.vhVal[hashFind(s.vhKey, HV - 1, c.x)];
-        lv[1] = s.vhVal[hashFind(s.vhKey, HV - 1, c.y)];
-        lv[2] = s.vhVal[hashFind(s.vhKey, HV - 1, c.z)];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            int g = k == 0 ? ad.x : (k == 1 ? ad.y : ad.z);
-            int sl = g < 0 ? -1 : hashFind(s.fhKey, HF - 1, g);
-            la[k] = sl < 0 ? (unsigned char)REC_NONE : s.fhVal[sl];
-        }
-#pragma unroll
-        for (int k = 0; k < 3; ++k)
-            if (la[k] == REC_NONE) { // patch border edge k: its endpoints are corners k+1, k+2
-                velig[lv[(k + 1) % 3]] = 1;
-                velig[lv[(k + 2) % 3]] = 1;
-            }
-        fvert[f] = make_uchar4(lv[0], lv[1], lv[2], (unsigned char)(ad.w & 63));
-        fadj[f] = make_uchar4(la[0], la[1], la[2], 0);
-    }
-    if (lane < K) tFace[lane] = s.fhVal[hashFind(s.fhKey, HF - 1, myTF)];
-    if (lane == 0) hdr[0] = nF, hdr[1] = nV, hdr[3] = 0;
-    return 0;
-}
-
-
 // ------------------------------------------------------------------------------------------------------------------------
 // Version 2 of the patch builder (default).  Same candidates, same face set, same record as buildPatch above; what changes is
 // how the flood fill walks the mesh:
@@ -566,13 +344,8 @@ template <class T> __device__ int buildPatch2(const PatchArgs& a, PatchSmem2<T>&
 
 } // namespace
 
-#ifndef CSS_PATCH_V1
 template <class T> using PatchWs = PatchSmem2<T>;
 #define BUILD_PATCH buildPatch2
-#else
-template <class T> using PatchWs = PatchSmem<T>;
-#define BUILD_PATCH buildPatch
-#endif
 
 template <class T> __global__ void __launch_bounds__(PATCH_THREADS) k_patch(PatchArgs a)
 {
