@@ -12,7 +12,7 @@ LIB = os.path.join(HERE, "libcurvedspacesim_b200.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 # (source, extra flags).  exact_kernels.cu must not contract a*b+c into FMA (bit parity with the oracle).
-UNITS = [("exact_kernels.cu", ["-fmad=false"]), ("geodesic_kernel.cu", []), ("patch_kernel.cu", []), ("window_kernel.cu", []), ("window_half_kernel.cu", []),
+UNITS = [("exact_kernels.cu", ["-fmad=false"]), ("geodesic_kernel.cu", []), ("patch_kernel.cu", []), ("stencil_kernel.cu", []), ("window_kernel.cu", []), ("window_half_kernel.cu", []),
          ("microbench.cu", []), ("css_api.cu", [])]
 
 

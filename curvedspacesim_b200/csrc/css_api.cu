@@ -29,6 +29,14 @@ struct css_ctx {
     int4* d_corner = nullptr;
     int4* d_adj = nullptr;
     int4* d_adjopp = nullptr; // [2 nF] flood-fill table of stage 1 (common.cuh MeshDev::adjopp)
+    // static face stencils of stage 1 (stencil_kernel.cu): built at the first neighbour phase after the mesh / the submeshing
+    // cut-off changed; used while most faces have one
+    unsigned char* d_stencil = nullptr;
+    unsigned* d_stencilLen = nullptr;
+    size_t stencilCap = 0;
+    bool useStencil = true, stencilValid = false, stencilUsable = false;
+    double stencilMeanFaces = 0;
+    long long stencilMissing = 0;
     unsigned char* d_saddle = nullptr;
     double2* d_geo = nullptr; // edge frames, [3 nF]
     double bbmin[3] = {0, 0, 0}, bbmax[3] = {0, 0, 0}, area = 0;
@@ -56,7 +64,7 @@ struct css_ctx {
     double *d_nbrDist = nullptr, *d_nbrTs = nullptr, *d_nbrTe = nullptr;
     bool nbrValid = false;
     // geodesic tiers
-    int *d_work = nullptr, *d_retry[3] = {nullptr, nullptr, nullptr};
+    int *d_work = nullptr, *d_retry[4] = {nullptr, nullptr, nullptr, nullptr}; // [3]: sources the stencil stage hands to the flood fill
     int capRetry = 0;
     char* d_gws = nullptr;
     size_t gwsBytes = 0;
@@ -305,6 +313,7 @@ int css_create(css_ctx** out, int device)
     if (const char* v = getenv("CSS_NO_GRAPH")) ctx->useGraph = atoi(v) == 0;
     if (const char* v = getenv("CSS_WIN_LEAN")) ctx->winLean = atoi(v) != 0;
     if (const char* v = getenv("CSS_WIN_HALF")) ctx->winHalf = atoi(v) != 0; // 0: one warp per source in tier 0 (window_kernel.cu)
+    if (const char* v = getenv("CSS_STENCIL")) ctx->useStencil = atoi(v) != 0; // 0: stage 1 of tier 0 flood-fills every patch (patch_kernel.cu)
     if (const char* v = getenv("CSS_WIN_WPB")) ctx->winWpb = std::max(1, std::min(4, atoi(v)));
     if (const char* v = getenv("CSS_P2P")) ctx->p2pEnabled = atoi(v) != 0;
     *out = ctx;
@@ -322,9 +331,9 @@ int css_destroy(css_ctx* ctx)
     void* ptrs[] = {ctx->d_vert,   ctx->d_corner,    ctx->d_adj,     ctx->d_saddle,  ctx->d_face,     ctx->d_bary,    ctx->d_eucl,
                     ctx->d_vel,    ctx->d_frc,       ctx->d_disp,    ctx->d_walkFlags, ctx->d_cellOf, ctx->d_cellCount, ctx->d_cellStart,
                     ctx->d_cellSlot, ctx->d_tmpItems, ctx->d_items,  ctx->d_nbrCount, ctx->d_nbrIdx,  ctx->d_nbrDist,
-                    ctx->d_nbrTs,  ctx->d_nbrTe,     ctx->d_work,    ctx->d_retry[0], ctx->d_retry[1], ctx->d_retry[2], ctx->d_gws,
+                    ctx->d_nbrTs,  ctx->d_nbrTe,     ctx->d_work,    ctx->d_retry[0], ctx->d_retry[1], ctx->d_retry[2], ctx->d_retry[3], ctx->d_gws,
                     ctx->d_partial, ctx->d_red,      ctx->d_counters, ctx->d_sendI,  ctx->d_sendD,    ctx->d_recvI,   ctx->d_recvD,
-                    ctx->d_redBuf,  ctx->d_geo,       ctx->d_records, ctx->d_recordsL, ctx->d_epoch, ctx->d_ticket, ctx->d_ipcBuf, ctx->d_spill, ctx->d_fgStart, ctx->d_fgFaces, ctx->d_adjopp};
+                    ctx->d_redBuf,  ctx->d_geo,       ctx->d_records, ctx->d_recordsL, ctx->d_epoch, ctx->d_ticket, ctx->d_ipcBuf, ctx->d_spill, ctx->d_fgStart, ctx->d_fgFaces, ctx->d_adjopp, ctx->d_stencil, ctx->d_stencilLen};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (auto& e : ctx->ev)
@@ -441,6 +450,7 @@ int css_set_mesh(css_ctx* ctx, int nV, const double* xyz, int nF, const int32_t*
     CU(cudaMemcpy(ctx->d_saddle, sad.data(), nV, cudaMemcpyHostToDevice));
     ctx->nV = nV;
     ctx->nF = nF;
+    ctx->stencilValid = false;
     ctx->fgValid = false;
     ctx->nbrValid = false;
     ctx->nveCalls = 0;
@@ -470,6 +480,7 @@ int css_set_submeshing(css_ctx* ctx, int enabled, double maxDist)
 {
     if (!ctx) return CSS_EINVAL;
     ctx->nveCalls = 0;
+    if ((enabled != 0) != ctx->submeshing || maxDist != ctx->maxDist) ctx->stencilValid = false;
     ctx->submeshing = enabled != 0;
     ctx->maxDist = maxDist;
     ctx->nbrValid = false;
@@ -653,10 +664,52 @@ int css_transport(css_ctx* ctx, int n, int32_t* face, double* bary, double* disp
 }
 
 // ------------------------------------------------------------------------------------- geodesics
+// (re)builds the static face stencils for the current mesh and submeshing cut-off; never called while a step is being captured
+static int ensureStencils(css_ctx* ctx)
+{
+    if (ctx->stencilValid || !ctx->useStencil || !ctx->submeshing) return CSS_OK;
+    if (ctx->capturing) return fail(ctx, CSS_ESTATE, "face stencils must exist before a step is captured");
+    ctx->stencilUsable = false;
+    const size_t bytes = stencilBytes(ctx->nF);
+    if (bytes > (32ull << 30)) { // meshes beyond ~17 M faces keep the flood fill
+        ctx->stencilValid = true;
+        return CSS_OK;
+    }
+    if (bytes > ctx->stencilCap) {
+        CU(cudaStreamSynchronize(ctx->st));
+        if (ctx->d_stencil) cudaFree(ctx->d_stencil);
+        ctx->d_stencil = nullptr, ctx->stencilCap = 0;
+        if (ctx->d_stencilLen) cudaFree(ctx->d_stencilLen);
+        ctx->d_stencilLen = nullptr;
+        if (cudaMalloc(&ctx->d_stencil, bytes) != cudaSuccess || cudaMalloc(&ctx->d_stencilLen, sizeof(unsigned) * (size_t)ctx->nF) != cudaSuccess) { // no room: the flood fill serves every source
+            if (ctx->d_stencil) cudaFree(ctx->d_stencil);
+            ctx->d_stencil = nullptr;
+            (void)cudaGetLastError();
+            ctx->stencilValid = true;
+            return CSS_OK;
+        }
+        ctx->stencilCap = bytes;
+    }
+    unsigned long long* dstats = reinterpret_cast<unsigned long long*>(ctx->d_red); // 24 doubles of scratch
+    CU(buildStencils(ctx->st, meshDev(ctx), ctx->maxDist, ctx->d_stencil, ctx->d_stencilLen, dstats, ctx->numSMs));
+    ctx->hostKernels++;
+    unsigned long long h[2] = {0, 0};
+    CU(cudaMemcpyAsync(h, dstats, sizeof h, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    ctx->stencilMissing = (long long)h[0];
+    ctx->stencilMeanFaces = ctx->nF > (int)h[0] ? (double)h[1] / (ctx->nF - (double)h[0]) : 0.0;
+    ctx->stencilUsable = 2 * h[0] <= (unsigned long long)ctx->nF; // with most faces uncovered (coarse meshes) the flood fill is the better first stage
+    ctx->stencilValid = true;
+    if (getenv("CSS_VERBOSE"))
+        fprintf(stderr, "[css] face stencils: %d faces, %.1f MB, mean %.1f stencil faces, %lld faces without one -> %s\n", ctx->nF, bytes / 1e6,
+                ctx->stencilMeanFaces, ctx->stencilMissing, ctx->stencilUsable ? "stencil stage 1" : "flood-fill stage 1");
+    return CSS_OK;
+}
+
 static int ensureTierBuffers(css_ctx* ctx, int nSrc)
 {
     if (nSrc > ctx->capRetry) {
-        for (int t = 0; t < 3; ++t) CU(regrow(ctx->d_retry[t], nSrc));
+        for (int t = 0; t < 4; ++t) CU(regrow(ctx->d_retry[t], nSrc));
         ctx->capRetry = nSrc;
     }
     return CSS_OK;
@@ -680,6 +733,7 @@ static int runGeodesicTiers(css_ctx* ctx, GeoArgs a, int nSrc)
         return CSS_OK;
     };
     const bool staged = ctx->twoStage && a.xK < 0 && a.cellStart != nullptr;
+    if (staged && (rc = ensureStencils(ctx))) return rc;
     if (staged) {
         // Two-stage tiers: patch records (integer / latency-bound, high occupancy), then window propagation (fp64).
         // Tier 0 = TierSmall over every local source; tier 1 = TierLarge over the sources tier 0 handed on.
@@ -716,7 +770,17 @@ static int runGeodesicTiers(css_ctx* ctx, GeoArgs a, int nSrc)
         w.srcList = nullptr, w.srcCount = nullptr, w.maxRecords = p.maxRecords;
         w.workCounter = ctx->d_work + 3, w.retryList = ctx->d_retry[0], w.retryCount = ctx->d_work + 4, w.records = ctx->d_records;
         if (ctx->timing) recordEvent(ctx, ctx->evS[0]);
-        CU(launchPatch<TierSmall>(ctx->st, p, ctx->numSMs));
+        p.stencil = ctx->d_stencil, p.stencilLen = ctx->d_stencilLen;
+        if (ctx->useStencil && ctx->stencilUsable && a.submeshing) {
+            p.fallbackList = ctx->d_retry[3], p.fallbackCount = ctx->d_work + 9;
+            CU(launchPatchStencil<TierSmall>(ctx->st, p, ctx->numSMs));
+            // the few sources whose face has no stencil: flood fill into the same records
+            PatchArgs q = p;
+            q.srcList = ctx->d_retry[3], q.srcCount = ctx->d_work + 9, q.workCounter = ctx->d_work + 10, q.recordByParticle = 1;
+            CU(launchPatch<TierSmall>(ctx->st, q, ctx->numSMs));
+            ctx->hostKernels++;
+        } else
+            CU(launchPatch<TierSmall>(ctx->st, p, ctx->numSMs));
         if (ctx->timing) recordEvent(ctx, ctx->evS[1]);
         if (ctx->winHalf) CU(launchWindowsHalf<TierHalf>(ctx->st, w, ctx->numSMs));
         else CU(launchWindows<TierSmall>(ctx->st, w, ctx->winWpb, ctx->numSMs, ctx->winLean));
@@ -1248,11 +1312,11 @@ static uint64_t nveGraphKey(css_ctx* ctx, const ForceParams& fp, double range, d
 #define MIX(x) mix(&(x), sizeof(x))
     MIX(fp.kind), MIX(fp.a), MIX(fp.sigma), MIX(range), MIX(dt);
     MIX(ctx->nLocal), MIX(ctx->nTotal), MIX(ctx->minIdx), MIX(ctx->kmax), MIX(ctx->nranks), MIX(ctx->timing), MIX(ctx->submeshing),
-        MIX(ctx->maxDist), MIX(ctx->boundaryMode), MIX(ctx->useCellList), MIX(ctx->wantEnd), MIX(ctx->twoStage), MIX(ctx->winWpb), MIX(ctx->winLean), MIX(ctx->winHalf), MIX(ctx->grid), MIX(ctx->nCells);
+        MIX(ctx->maxDist), MIX(ctx->boundaryMode), MIX(ctx->useCellList), MIX(ctx->wantEnd), MIX(ctx->twoStage), MIX(ctx->winWpb), MIX(ctx->winLean), MIX(ctx->winHalf), MIX(ctx->useStencil), MIX(ctx->stencilUsable), MIX(ctx->grid), MIX(ctx->nCells);
     void* ptrs[] = {ctx->d_vert, ctx->d_corner, ctx->d_adj, ctx->d_adjopp, ctx->d_geo, ctx->d_saddle, ctx->d_face, ctx->d_bary, ctx->d_eucl, ctx->d_vel, ctx->d_frc,
                     ctx->d_disp, ctx->d_walkFlags, ctx->d_cellOf, ctx->d_cellCount, ctx->d_cellStart, ctx->d_cellSlot, ctx->d_tmpItems,
                     ctx->d_items, ctx->d_nbrCount, ctx->d_nbrIdx, ctx->d_nbrDist, ctx->d_nbrTs, ctx->d_nbrTe, ctx->d_retry[0], ctx->d_retry[1],
-                    ctx->d_retry[2], ctx->d_gws, ctx->d_records, ctx->d_recordsL, ctx->d_spill, ctx->d_recvI, ctx->d_recvD, (void*)ctx->comm, ctx->winLocal,
+                    ctx->d_retry[2], ctx->d_retry[3], ctx->d_gws, ctx->d_records, ctx->d_recordsL, ctx->d_stencil, ctx->d_spill, ctx->d_recvI, ctx->d_recvD, (void*)ctx->comm, ctx->winLocal,
                     ctx->winPeer[0], ctx->winPeer[1], ctx->winPeer[2], ctx->winPeer[3], ctx->winPeer[4], ctx->winPeer[5], ctx->winPeer[6],
                     ctx->winPeer[7]};
     MIX(ptrs);

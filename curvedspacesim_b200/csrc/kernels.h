@@ -1,6 +1,7 @@
 // Host-side launch interface between css_api.cu and the kernel translation units.
 #pragma once
 #include "common.cuh"
+#include <algorithm>
 
 namespace css {
 
@@ -111,6 +112,19 @@ static_assert(TierHalf::BYTES == TierSmall::BYTES && TierHalf::OFF_FVERT == Tier
 #define REC_NONE 255
 #define PATCH_THREADS 256
 
+// Static face stencils (stencil_kernel.cu): per mesh face, the superset of every patch a source lying in that face can get.
+// Records are STENCIL_BYTES apart; inside a record the sections are packed back to back, so a source reads (and prefetches)
+// one contiguous run of 16 + 12 nSF + 4 nSV bytes:
+//   int4  hdr              nSF, nSV, status, 0
+//   int   gface[nSF]       stencil face -> global face; entry 0 is the face itself, entries 1.. ascend
+//   u32   fvert[nSF]       stencil corner ids v0 | v1 << 8 | v2 << 16 | kk bits << 24
+//   u32   fadj[nSF]        stencil face across edge k (REC_NONE = not in the stencil) n0 | n1 << 8 | n2 << 16 | parent << 24
+//   int   gvert[nSV]       stencil vertex -> global vertex
+// A separate table holds nSF | nSV << 16 per face (0 = the face has no stencil: more than STENCIL_F faces / STENCIL_V vertices).
+#define STENCIL_F 160 /* multiples of 32; ids below REC_NONE */
+#define STENCIL_V 128
+#define STENCIL_BYTES (16 + 12 * STENCIL_F + 4 * STENCIL_V)
+
 struct PatchArgs {
     MeshDev m;
     CellGrid grid;
@@ -134,8 +148,19 @@ struct PatchArgs {
     int* retryCount;
     unsigned long long* counters;
     unsigned char* records; // [maxRecords][Tier::BYTES]
+    const unsigned char* stencil; // [nF][STENCIL_BYTES] (launchPatchStencil only)
+    const unsigned* stencilLen;   // [nF] nSF | nSV << 16, 0 = no stencil
+    // launchPatchStencil: sources it cannot serve (face without a stencil, target outside the stencil) are listed here and
+    // flood-filled by launchPatch into the SAME tier-0 records (recordByParticle: record index = particle, not list position)
+    int* fallbackList;
+    int* fallbackCount;
+    int recordByParticle;
 };
 template <class Tier> cudaError_t launchPatch(cudaStream_t st, const PatchArgs& a, int numSMs);
+// tier 0 through static face stencils (stencil_kernel.cu); statsDev[0] = faces without a stencil, statsDev[1] = sum of stencil sizes
+size_t stencilBytes(int nF);
+cudaError_t buildStencils(cudaStream_t st, const MeshDev& m, double maxDist, unsigned char* out, unsigned* lenOut, unsigned long long* statsDev, int numSMs);
+template <class Tier> cudaError_t launchPatchStencil(cudaStream_t st, const PatchArgs& a, int numSMs);
 
 struct WinArgs {
     MeshDev m;

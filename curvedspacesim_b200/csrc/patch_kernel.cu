@@ -362,7 +362,7 @@ template <class T> __global__ void __launch_bounds__(PATCH_THREADS) k_patch(Patc
         if (w >= nWork) break;
         const int li = a.srcList ? a.srcList[w] : w;
         int* hdr = reinterpret_cast<int*>(s.rec);
-        if (w >= a.maxRecords) { // no record slot left in this tier: hand the source on
+        if (!a.recordByParticle && w >= a.maxRecords) { // no record slot left in this tier: hand the source on
             if (lane == 0) {
                 int r = atomicAdd(a.retryCount, 1);
                 a.retryList[r] = li;
@@ -384,7 +384,7 @@ template <class T> __global__ void __launch_bounds__(PATCH_THREADS) k_patch(Patc
         // coalesced record store, section by section and only as far as each section is used (a record is 1.6 kB apart, ~0.8 kB
         // of it carries data at the design point); what lies beyond is never read
         const int4* src = reinterpret_cast<const int4*>(s.rec);
-        int4* dst = reinterpret_cast<int4*>(a.records + (size_t)w * T::BYTES);
+        int4* dst = reinterpret_cast<int4*>(a.records + (size_t)(a.recordByParticle ? li : w) * T::BYTES);
         const int nF = hdr[0], nV = hdr[1];
         if (hdr[3] || nF == 0) {
             for (int q = lane; q < T::OFF_TFACE / 16; q += 32) dst[q] = src[q]; // header and candidate ids

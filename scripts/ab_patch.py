@@ -29,7 +29,7 @@ f, b, v, fr = ctx.get_state()
 import hashlib
 h = hashlib.sha256(f.tobytes() + b.tobytes() + v.tobytes() + fr.tobytes()).hexdigest()[:16]
 hn = hashlib.sha256(off.tobytes() + idx.tobytes() + d.tobytes() + ts.tobytes()).hexdigest()[:16]
-print(json.dumps({"lib": os.environ.get("CSS_LIB_PATH", "default").split("/")[-1] + " pair=" + os.environ.get("CSS_PATCH_PAIR", "1"), "step_ms": float(np.median(T)), "patch_ms": float(np.median(P)), "window_ms": float(np.median(W)),
+print(json.dumps({"lib": os.environ.get("CSS_LIB_PATH", "default").split("/")[-1] + " stencil=" + os.environ.get("CSS_STENCIL", "1"), "step_ms": float(np.median(T)), "patch_ms": float(np.median(P)), "window_ms": float(np.median(W)),
                   "retry_ms": float(np.median(R)), "walk_ms": float(np.median(Wk)), "cell_ms": float(np.median(Ce)), "state_hash": h, "nbr_hash": hn,
                   "patch_faces": c["patch_faces"], "patch_verts": c["patch_verts"], "queries": c["queries"], "retry": c["tier_retry"], "overflow": c["overflow"]}))
 ''' % ROOT
@@ -41,5 +41,9 @@ for spec in sys.argv[2:]:  # "<lib or default>[:ENV=VALUE[:ENV=VALUE...]]"
         env[kv.split("=")[0]] = kv.split("=")[1]
     if lib != "default":
         env["CSS_LIB_PATH"] = os.path.join(ROOT, lib)
+    env["CSS_VERBOSE"] = "1"
     r = subprocess.run([sys.executable, "-c", code, wl], env=env, capture_output=True, text=True)
+    for ln in r.stderr.splitlines():
+        if ln.startswith("[css]"):
+            print(ln, flush=True)
     print(r.stdout.strip().splitlines()[-1] if r.stdout.strip() else "FAILED " + spec + ": " + r.stderr[-800:], flush=True)

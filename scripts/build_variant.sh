@@ -9,6 +9,7 @@ COMMON="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompi
 nvcc $COMMON -fmad=false "$@" -c $D/exact_kernels.cu -o $OUT/exact.o &
 nvcc $COMMON "$@" -c $D/geodesic_kernel.cu -o $OUT/geo.o &
 nvcc $COMMON "$@" -c $D/patch_kernel.cu -o $OUT/patch.o &
+nvcc $COMMON "$@" -c $D/stencil_kernel.cu -o $OUT/stencil.o &
 nvcc $COMMON "$@" -c $D/window_kernel.cu -o $OUT/win.o &
 nvcc $COMMON "$@" -c $D/window_half_kernel.cu -o $OUT/winhalf.o &
 nvcc $COMMON "$@" -c $D/css_api.cu -o $OUT/api.o &
