@@ -85,6 +85,33 @@ __device__ __forceinline__ int cellCoord(const CellGrid& g, double x, int d)
     return max(0, min(g.n[d] - 1, c));
 }
 
+// ---- programmatic dependent launch (PDL).  The kernels of a step are tiny next to their launch latency at the tail of the
+// sequence (cell list, empty retry tiers) and the big ones end with a ragged tail.  Every step kernel is launched with the
+// programmatic-stream-serialization attribute and starts with PDL_ENTRY(): it tells the scheduler that its successor may be
+// made resident as soon as SM resources free up (launch_dependents) and then waits until its predecessor has completed and
+// flushed (wait) -- memory ordering is exactly that of plain stream order, only launch latency and block scheduling overlap
+// the predecessor's tail.  Without the attribute both instructions are no-ops.
+#define PDL_ENTRY()                                             \
+    do {                                                        \
+        asm volatile("griddepcontrol.launch_dependents;");      \
+        asm volatile("griddepcontrol.wait;" ::: "memory");      \
+    } while (0)
+
+#ifdef __CUDACC__
+bool pdlEnabled(); // CSS_PDL=0 switches the attribute off (css_api.cu)
+template <class... KArgs, class... Args>
+inline cudaError_t launchStep(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at, cfg.numAttrs = pdlEnabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
+
 // walker flag bits / counters (mirrors include/css_api.h)
 enum { WALK_VERTEX = 1, WALK_NOHIT = 2, WALK_ITERCAP = 4, WALK_NAN = 8, WALK_BORDER = 16 };
 enum {

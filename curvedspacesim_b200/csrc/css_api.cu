@@ -144,6 +144,17 @@ struct css_ctx {
 static void recordEvent(css_ctx* c, cudaEvent_t e);
 static void releasePeerWindow(css_ctx* c);
 
+namespace css {
+bool pdlEnabled()
+{
+    static const bool on = [] {
+        const char* v = getenv("CSS_PDL");
+        return !v || atoi(v) != 0;
+    }();
+    return on;
+}
+} // namespace css
+
 static int fail(css_ctx* c, int code, const char* fmt, ...)
 {
     char buf[512];

@@ -108,6 +108,7 @@ __global__ void k_euclid_cell(MeshDev m, CellGrid g, int n, const int* __restric
                               double* __restrict__ eucl, int* __restrict__ cellOf, int* __restrict__ cellCount, int* __restrict__ cellSlot,
                               int* __restrict__ coarse)
 {
+    PDL_ENTRY();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     Tri t = ldtri(m, face[i]);
@@ -132,6 +133,7 @@ __global__ void k_euclid_cell(MeshDev m, CellGrid g, int n, const int* __restric
 __global__ void k_cell_place(int n, const int* __restrict__ cellOf, const int* __restrict__ cellSlot, const int* __restrict__ cellCount,
                              int* __restrict__ cellStart, int* __restrict__ bump)
 {
+    PDL_ENTRY();
     const int i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
     const bool first = i < n && cellSlot[i] == 0;
     const int c = first ? cellOf[i] : 0;
@@ -151,6 +153,7 @@ __global__ void k_cell_place(int n, const int* __restrict__ cellOf, const int* _
 __global__ void k_cell_fill(int n, const int* __restrict__ cellOf, const int* __restrict__ cellSlot, const int* __restrict__ cellStart,
                             int* __restrict__ tmpItems)
 {
+    PDL_ENTRY();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     tmpItems[cellStart[cellOf[i]] + cellSlot[i]] = i;
@@ -164,6 +167,7 @@ __global__ void k_cell_rank(int n, const int* __restrict__ cellOf, const int* __
                             const int* __restrict__ tmpItems, int* __restrict__ items, const int* __restrict__ coarse, int nx, int ny, int nz,
                             int kmax, unsigned long long* __restrict__ counters)
 {
+    PDL_ENTRY();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int occ = 0;
     if (i < n) {
@@ -593,6 +597,7 @@ __global__ void __launch_bounds__(64, CSS_WALK_MINB) k_walk(MeshDev m, int n, in
                        double* __restrict__ vel, double* __restrict__ frc, int transportForce, int transportVelocity, int mode,
                        double dt, int* __restrict__ flagsOut, unsigned long long* __restrict__ counters, PeerWin pw)
 {
+    PDL_ENTRY();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int fl = 0, nc = 0;
     if (strideGuardUp(counters)) return; // a step upstream is waiting for a larger neighbour stride: nothing moves (common.cuh)
@@ -993,23 +998,23 @@ static inline int gridFor(int n, int b) { return (n + b - 1) / b; }
 void launchEuclidCell(cudaStream_t st, const MeshDev& m, const CellGrid& g, int n, const int* face, const double* bary, double* eucl,
                       int* cellOf, int* cellCount, int* cellSlot, int* coarse)
 {
-    if (n > 0) k_euclid_cell<<<gridFor(n, 256), 256, 0, st>>>(m, g, n, face, bary, eucl, cellOf, cellCount, cellSlot, coarse);
+    if (n > 0) launchStep(k_euclid_cell, gridFor(n, 256), 256, 0, st, m, g, n, face, bary, eucl, cellOf, cellCount, cellSlot, coarse);
 }
 // cellCount[nCells] is the bump counter (cleared with the counts)
 void launchCellBuild(cudaStream_t st, int n, int nCells, const int* cellOf, const int* cellSlot, int* cellCount, int* cellStart, int* tmpItems,
                      int* items, const int* coarse, const CellGrid& g, int kmax, unsigned long long* counters)
 {
     if (n <= 0) return;
-    k_cell_place<<<gridFor(n, 256), 256, 0, st>>>(n, cellOf, cellSlot, cellCount, cellStart, cellCount + nCells);
-    k_cell_fill<<<gridFor(n, 256), 256, 0, st>>>(n, cellOf, cellSlot, cellStart, tmpItems);
-    k_cell_rank<<<gridFor(n, 256), 256, 0, st>>>(n, cellOf, cellStart, cellCount, tmpItems, items, coarse, g.n[0], g.n[1], g.n[2], kmax, counters);
+    launchStep(k_cell_place, gridFor(n, 256), 256, 0, st, n, cellOf, cellSlot, cellCount, cellStart, cellCount + nCells);
+    launchStep(k_cell_fill, gridFor(n, 256), 256, 0, st, n, cellOf, cellSlot, cellStart, tmpItems);
+    launchStep(k_cell_rank, gridFor(n, 256), 256, 0, st, n, cellOf, cellStart, cellCount, tmpItems, items, coarse, g.n[0], g.n[1], g.n[2], kmax, counters);
 }
 void launchWalk(cudaStream_t st, const MeshDev& m, int n, int minIdx, int* face, double* bary, double* disp, double* vel, double* frc,
                 int transportForce, int transportVelocity, int mode, double dt, int* flags, unsigned long long* counters, const PeerWin& pw)
 {
     if (n > 0)
-        k_walk<<<gridFor(n, 64), 64, 0, st>>>(m, n, minIdx, face, bary, disp, vel, frc, transportForce, transportVelocity, mode, dt,
-                                                flags, counters, pw);
+        launchStep(k_walk, gridFor(n, 64), 64, 0, st, m, n, minIdx, face, bary, disp, vel, frc, transportForce, transportVelocity, mode, dt, flags,
+                   counters, pw);
 }
 
 // ---------------------------------------------------------------------------------- peer-memory exchange

@@ -951,6 +951,7 @@ __global__ void __launch_bounds__(128, 3) k_geodesic(GeoArgs a, size_t wsBytes)
     WS w;
     wsLayout(a.caps, base, &w);
     unsigned long long* cnt = w.wcnt;
+    PDL_ENTRY();
     if (a.xK < 0 && strideGuardUp(a.counters)) return; // neighbour phase waiting for a larger stride (common.cuh); explicit queries are not affected
     if (lane < 16) cnt[lane] = 0;
     __syncwarp();
@@ -990,13 +991,12 @@ cudaError_t launchGeodesic(cudaStream_t st, const GeoArgs& a, int warpsPerBlock,
     if (warpsPerBlock * 32 > 128) return cudaErrorInvalidConfiguration; // __launch_bounds__(128, 3)
     size_t wsBytes = geoWorkspaceBytes(a.caps);
     if (a.gws) {
-        k_geodesic<true><<<blocks, warpsPerBlock * 32, 0, st>>>(a, wsBytes);
+        return launchStep(k_geodesic<true>, blocks, warpsPerBlock * 32, 0, st, a, wsBytes);
     } else {
         size_t smem = wsBytes * warpsPerBlock;
         cudaFuncSetAttribute(k_geodesic<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)geodesicMaxSmemPerBlock());
-        k_geodesic<false><<<blocks, warpsPerBlock * 32, smem, st>>>(a, wsBytes);
+        return launchStep(k_geodesic<false>, blocks, warpsPerBlock * 32, smem, st, a, wsBytes);
     }
-    return cudaGetLastError();
 }
 
 } // namespace css

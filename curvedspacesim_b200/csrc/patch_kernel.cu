@@ -353,6 +353,7 @@ template <class T> __global__ void __launch_bounds__(PATCH_THREADS) k_patch(Patc
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     PatchWs<T>& s = reinterpret_cast<PatchWs<T>*>(smemRaw)[wib];
     unsigned long long nRetry = 0;
+    PDL_ENTRY();
     if (strideGuardUp(a.counters)) return; // the cell-list build found a stencil fuller than the neighbour stride (common.cuh)
     const int nWork = a.srcList ? *a.srcCount : a.nLocal;
     for (;;) {
@@ -418,8 +419,7 @@ template <class T> cudaError_t launchPatch(cudaStream_t st, const PatchArgs& a, 
     // persistent warps pulling sources from a work counter: one wave of resident blocks (a retry tier whose list
     // length is only known on the device gets one block per SM)
     int blocks = a.srcList ? numSMs : min(numSMs * perSM, max(1, (a.nLocal + PATCH_THREADS / 32 - 1) / (PATCH_THREADS / 32)));
-    k_patch<T><<<blocks, PATCH_THREADS, smem, st>>>(a);
-    return cudaGetLastError();
+    return launchStep(k_patch<T>, blocks, PATCH_THREADS, smem, st, a);
 }
 template cudaError_t launchPatch<TierSmall>(cudaStream_t, const PatchArgs&, int);
 template cudaError_t launchPatch<TierLarge>(cudaStream_t, const PatchArgs&, int);

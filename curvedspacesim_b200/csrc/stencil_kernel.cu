@@ -268,6 +268,7 @@ template <class T> __global__ void __launch_bounds__(128, CSS_STENCIL_MINB) k_pa
     __shared__ RestrictSmem<T> smAll[4];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     RestrictSmem<T>& sm = smAll[wib];
+    PDL_ENTRY();
     if (strideGuardUp(a.counters)) return; // the cell-list build found a stencil fuller than the neighbour stride (common.cuh)
     const unsigned ltMask = (1u << lane) - 1u;
     unsigned long long nRetry = 0;
@@ -643,8 +644,7 @@ template <class T> cudaError_t launchPatchStencil(cudaStream_t st, const PatchAr
     if (!perSM)
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_patch_stencil<T>, 128, 0) != cudaSuccess || perSM < 1) perSM = 1;
     const int blocks = std::min(numSMs * perSM, std::max(1, (a.nLocal + 3) / 4));
-    k_patch_stencil<T><<<blocks, 128, 0, st>>>(a);
-    return cudaGetLastError();
+    return launchStep(k_patch_stencil<T>, blocks, 128, 0, st, a);
 }
 template cudaError_t launchPatchStencil<TierSmall>(cudaStream_t, const PatchArgs&, int);
 

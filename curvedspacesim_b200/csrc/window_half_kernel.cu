@@ -122,6 +122,7 @@ template <class T> __global__ void __launch_bounds__(32 * CSS_HALF_WPB, CSS_HALF
     const unsigned hmask = 0xFFFFu << hbase;
     W* const wpair = reinterpret_cast<W*>(smemRaw) + 2 * wib;
     W& w = wpair[half];
+    PDL_ENTRY();
     if (strideGuardUp(a.counters)) return; // stage 1 did not run: the host regrows the neighbour stride and repeats the phase
     // spill stacks of this warp's two sources (global memory, L2-resident; see the push in the pass loop)
     double* const spillPair = a.spill + (size_t)(blockIdx.x * (blockDim.x >> 5) + wib) * 2 * SPILL_CAP * SPILL_DOUBLES;
@@ -686,8 +687,7 @@ template <class T> cudaError_t launchWindowsHalf(cudaStream_t st, const WinArgs&
     }
     int blocks = numSMs * min(perSM, CSS_HALF_MINBLOCKS); // the spill scratch is sized for this many blocks
     if (!a.srcList) blocks = min(blocks, max(1, (a.nLocal + 2 * wpb - 1) / (2 * wpb)));
-    k_windows_half<T><<<blocks, wpb * 32, smem, st>>>(a);
-    return cudaGetLastError();
+    return launchStep(k_windows_half<T>, blocks, wpb * 32, smem, st, a);
 }
 template cudaError_t launchWindowsHalf<TierHalf>(cudaStream_t, const WinArgs&, int);
 size_t windowsHalfSpillBytes(int numSMs)

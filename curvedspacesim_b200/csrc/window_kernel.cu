@@ -542,6 +542,7 @@ template <class T, bool LEAN> __global__ void __launch_bounds__(128, LEAN ? CSS_
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     WinSmem<T, LEAN>& w = reinterpret_cast<WinSmem<T, LEAN>*>(smemRaw)[wib];
     unsigned long long* cnt = w.wcnt;
+    PDL_ENTRY();
     if (strideGuardUp(a.counters)) return; // stage 1 did not run (common.cuh)
     if (lane < 16) cnt[lane] = 0;
     __syncwarp();
@@ -584,8 +585,7 @@ template <class T, bool LEAN> static cudaError_t launchWindowsImpl(cudaStream_t 
     }
     int blocks = numSMs * perSM[warpsPerBlock];
     if (!a.srcList) blocks = min(blocks, max(1, (a.nLocal + warpsPerBlock - 1) / warpsPerBlock));
-    k_windows<T, LEAN><<<blocks, warpsPerBlock * 32, smem, st>>>(a);
-    return cudaGetLastError();
+    return launchStep(k_windows<T, LEAN>, blocks, warpsPerBlock * 32, smem, st, a);
 }
 template <class T> cudaError_t launchWindows(cudaStream_t st, const WinArgs& a, int warpsPerBlock, int numSMs, bool lean)
 {
