@@ -44,6 +44,8 @@ def _off(name):
 
 WORKLOADS = {
     # name: mesh builder, N, potential, integrator
+    # the reference's default executable (curvedSpaceSimulation.cpp:25-29): range 2.6, ~830-face patches -> whole-mesh tier
+    "default_exe_torus_isotropic_N20": dict(mesh=_off("torus_isotropic_remesh.off"), N=20, potential="harmonic", integrator="nve"),
     "cfg1_sphere_radius1_N100": dict(mesh=_off("sphere_radius1.off"), N=100, potential="harmonic", integrator="nve"),
     "cfg2_torusrb20_N2000_gaussian": dict(mesh=_off("torusrb20.off"), N=2000, potential="gaussian", integrator="nve"),
     "cfg3_elephant_N5000_nvt": dict(mesh=_off("triangulatedElephant.off"), N=5000, potential="harmonic", integrator="nvt"),
@@ -212,7 +214,12 @@ def main():
         run_reference(args, rank, world)
         return
     if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"  # the version banner goes to stdout; rank 0 must print exactly one JSON line
+        os.environ["NCCL_DEBUG"] = "WARN"
+    # rank 0 must print exactly ONE line on stdout: native libraries (NCCL's version banner, ...) write to file descriptor 1
+    # directly, so everything but the final JSON line is sent to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
 
     import torch
     import torch.distributed as dist
@@ -518,7 +525,8 @@ def main():
             "cpu_baseline": cpu,
             "cpu_baseline_single_rank": cpu1,
         }
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

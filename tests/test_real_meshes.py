@@ -33,6 +33,7 @@ TOL_TRAJ = 1e-6     # positions / velocities after 1000 steps
 MESHDIR = os.path.join(GOLDEN, "meshes")
 CONFIGS = {
     # name: (file, N, potential)
+    "default_exe": ("torus_isotropic_remesh.off", 20, "harmonic"),   # curvedSpaceSimulation.cpp:25,28 defaults: range 2.6, ~830-face patches
     "cfg1": ("sphere_radius1.off", 100, "harmonic"),
     "cfg2": ("torusrb20.off", 2000, "gaussian"),
     "cfg3": ("triangulatedElephant.off", 5000, "harmonic"),
@@ -370,6 +371,33 @@ def test_config3_elephant_fire_then_nose_hoover(gpu_ctx_factory):
                                                     c["pseudo_sources"], c["disconnected"], c["tier_retry"]))
     assert c["overflow"] == 0 and c["walk_nohit"] == 0 and c["walk_nan"] == 0 and c["walk_itercap"] == 0
     assert flagged.sum() <= 50
+
+
+@pytest.mark.gpu
+def test_default_executable_shape_long_range(gpu_ctx_factory):
+    """The reference's default executable (curvedSpaceSimulation.cpp:25-29: N = 20 on torus_isotropic_remesh.off, area fraction
+    0.9 -> range 2.6): patches of ~830 faces / 440 vertices and ~9 400 windows per source overflow both record tiers and run on
+    the whole-mesh tier (one warp per source on a global-memory workspace).  Same bars as everywhere else."""
+    orc, V, F, corners, face, bary, vel, N, rc, kind, params = setup_oracle("default_exe")
+    ctx = setup_gpu(gpu_ctx_factory, V, corners, face, bary, vel, rc)
+    ctx.counters(reset=True)
+    o_off, o_idx, o_d, o_ts, o_te = orc.find_neighbors(rc)
+    g_off, g_idx, g_d, g_ts, g_te = ctx.find_neighbors(rc, want_end=True)
+    assert np.array_equal(o_off, g_off) and np.array_equal(o_idx, g_idx)
+    c, oc = ctx.counters(), orc.counters()
+    assert c["patch_faces"] == oc["patch_faces"] and c["patch_verts"] == oc["patch_verts"] and c["patch_faces"] > 500 * N
+    assert c["overflow"] == 0 and c["tier_retry"] >= N
+    assert _rel(g_d, o_d) < TOL_DIST and np.max(np.abs(g_ts - o_ts)) < TOL_TAN and np.max(np.abs(g_te - o_te)) < TOL_TAN
+    f0 = orc.compute_forces(kind, params)
+    ctx.compute_forces(kind, params)
+    assert np.max(np.abs(f0 - ctx.get_state()[3])) < TOL_FORCE * np.abs(f0).max()
+    orc.run_nve(kind, params, 0.01, 50)
+    ctx.step_nve(kind, params, 0.01, 50)
+    of, ob, ov, _ = orc.get_state()
+    gf, gb, gv, _ = ctx.get_state()
+    assert np.array_equal(of, gf) and np.max(np.abs(ob - gb)) < 1e-9 and np.max(np.abs(ov - gv)) < 1e-9
+    print("default exe shape: %.0f faces / %.0f vertices per patch, %.0f windows per source, retries %d" % (
+        c["patch_faces"] / N, c["patch_verts"] / N, c["windows"] / N, c["tier_retry"]))
 
 
 @pytest.mark.gpu
