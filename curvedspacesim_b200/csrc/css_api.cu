@@ -69,6 +69,9 @@ struct css_ctx {
     char* d_gws = nullptr;
     size_t gwsBytes = 0;
     GeoCaps capsT0{96, 64, 64, 16, 256, 256}, capsT1{768, 448, 1024, 128, 2048, 1024}, capsT2{0, 0, 0, 0, 0, 0};
+    // one warp per SM on a shared-memory workspace (~195 kB): long-range patches of up to 1408 faces / 768 vertices (the reference's
+    // default executable: N = 20, range 2.6 on torus_isotropic_remesh.off) stay out of the global-memory tier
+    GeoCaps capsHuge{1408, 768, 1024, 32, 4096, 2048};
     int t2Warps = 32;
     int wpb0 = 4, wpb1 = 1;
     // two-stage tier 0: patch records (stage 1) -> window propagation (stage 2)
@@ -783,13 +786,17 @@ static int runGeodesicTiers(css_ctx* ctx, GeoArgs a, int nSrc)
         if (ctx->timing) recordEvent(ctx, ctx->evS[0]);
         p.stencil = ctx->d_stencil, p.stencilLen = ctx->d_stencilLen;
         if (ctx->useStencil && ctx->stencilUsable && a.submeshing) {
-            p.fallbackList = ctx->d_retry[3], p.fallbackCount = ctx->d_work + 9;
+            // sources whose face has no stencil are flood-filled into the same records by a second launch; when every face has
+            // one, the launch is skipped and the (very rare) source with a target outside its stencil goes to the large tier
+            const bool fallback = ctx->stencilMissing > 0;
+            p.fallbackList = fallback ? ctx->d_retry[3] : nullptr, p.fallbackCount = ctx->d_work + 9;
             CU(launchPatchStencil<TierSmall>(ctx->st, p, ctx->numSMs));
-            // the few sources whose face has no stencil: flood fill into the same records
-            PatchArgs q = p;
-            q.srcList = ctx->d_retry[3], q.srcCount = ctx->d_work + 9, q.workCounter = ctx->d_work + 10, q.recordByParticle = 1;
-            CU(launchPatch<TierSmall>(ctx->st, q, ctx->numSMs));
-            ctx->hostKernels++;
+            if (fallback) {
+                PatchArgs q = p;
+                q.srcList = ctx->d_retry[3], q.srcCount = ctx->d_work + 9, q.workCounter = ctx->d_work + 10, q.recordByParticle = 1;
+                CU(launchPatch<TierSmall>(ctx->st, q, ctx->numSMs));
+                ctx->hostKernels++;
+            }
         } else
             CU(launchPatch<TierSmall>(ctx->st, p, ctx->numSMs));
         if (ctx->timing) recordEvent(ctx, ctx->evS[1]);
@@ -829,6 +836,18 @@ static int runGeodesicTiers(css_ctx* ctx, GeoArgs a, int nSrc)
         CU(launchGeodesic(ctx->st, a, wpb, blocks));
         ctx->hostKernels++;
     }
+    // long-range tier: the fused kernel, ONE WARP PER SM with its whole workspace in shared memory (the global-memory tier below
+    // pays an L2 round trip for every ring / vertex access: 9.4 -> 1.x ms per step on the reference's default executable shape)
+    const bool hugeTier = a.xK < 0 && ctx->useCellList && geoWorkspaceBytes(ctx->capsHuge) <= (size_t)geodesicMaxSmemPerBlock();
+    if (hugeTier) {
+        a.caps = ctx->capsHuge;
+        a.srcList = ctx->d_retry[1], a.srcCount = ctx->d_work + 5;
+        a.workCounter = ctx->d_work + 11;
+        a.retryList = ctx->d_retry[2], a.retryCount = ctx->d_work + 6;
+        a.gws = nullptr, a.lastTier = 0;
+        CU(launchGeodesic(ctx->st, a, 1, ctx->numSMs));
+        ctx->hostKernels++;
+    }
     // last tier: the fused kernel with capacities sized for the whole mesh, global-memory workspace
     {
         a.caps = ctx->capsT2;
@@ -838,9 +857,9 @@ static int runGeodesicTiers(css_ctx* ctx, GeoArgs a, int nSrc)
         size_t ws = geoWorkspaceBytes(a.caps);
         int warps = ctx->t2Warps;
         if (int rc2 = ensureWorkspace(ws * warps)) return rc2;
-        a.srcList = ctx->d_retry[1], a.srcCount = ctx->d_work + 5;
+        a.srcList = hugeTier ? ctx->d_retry[2] : ctx->d_retry[1], a.srcCount = ctx->d_work + (hugeTier ? 6 : 5);
         a.workCounter = ctx->d_work + 2;
-        a.retryList = ctx->d_retry[2], a.retryCount = ctx->d_work + 6;
+        a.retryList = hugeTier ? ctx->d_retry[1] : ctx->d_retry[2], a.retryCount = ctx->d_work + 12; // (the last tier retries nothing)
         a.gws = ctx->d_gws, a.lastTier = 1;
         CU(launchGeodesic(ctx->st, a, 1, warps));
         ctx->hostKernels++;
@@ -1323,7 +1342,7 @@ static uint64_t nveGraphKey(css_ctx* ctx, const ForceParams& fp, double range, d
 #define MIX(x) mix(&(x), sizeof(x))
     MIX(fp.kind), MIX(fp.a), MIX(fp.sigma), MIX(range), MIX(dt);
     MIX(ctx->nLocal), MIX(ctx->nTotal), MIX(ctx->minIdx), MIX(ctx->kmax), MIX(ctx->nranks), MIX(ctx->timing), MIX(ctx->submeshing),
-        MIX(ctx->maxDist), MIX(ctx->boundaryMode), MIX(ctx->useCellList), MIX(ctx->wantEnd), MIX(ctx->twoStage), MIX(ctx->winWpb), MIX(ctx->winLean), MIX(ctx->winHalf), MIX(ctx->useStencil), MIX(ctx->stencilUsable), MIX(ctx->grid), MIX(ctx->nCells);
+        MIX(ctx->maxDist), MIX(ctx->boundaryMode), MIX(ctx->useCellList), MIX(ctx->wantEnd), MIX(ctx->twoStage), MIX(ctx->winWpb), MIX(ctx->winLean), MIX(ctx->winHalf), MIX(ctx->useStencil), MIX(ctx->stencilUsable), MIX(ctx->stencilMissing), MIX(ctx->grid), MIX(ctx->nCells);
     void* ptrs[] = {ctx->d_vert, ctx->d_corner, ctx->d_adj, ctx->d_adjopp, ctx->d_geo, ctx->d_saddle, ctx->d_face, ctx->d_bary, ctx->d_eucl, ctx->d_vel, ctx->d_frc,
                     ctx->d_disp, ctx->d_walkFlags, ctx->d_cellOf, ctx->d_cellCount, ctx->d_cellStart, ctx->d_cellSlot, ctx->d_tmpItems,
                     ctx->d_items, ctx->d_nbrCount, ctx->d_nbrIdx, ctx->d_nbrDist, ctx->d_nbrTs, ctx->d_nbrTe, ctx->d_retry[0], ctx->d_retry[1],

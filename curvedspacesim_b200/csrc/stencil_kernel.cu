@@ -601,7 +601,7 @@ template <class T> __global__ void __launch_bounds__(128, CSS_STENCIL_MINB) k_pa
             }
         }
         // ---------------- header, candidate ids, retry list ----------------
-        if (retry == 3) { // no stencil here: the flood fill (patch_kernel.cu) writes this record
+        if (retry == 3 && a.fallbackList) { // no stencil here: the flood fill (patch_kernel.cu) writes this record
             if (lane == 0) a.fallbackList[atomicAdd(a.fallbackCount, 1)] = w;
         } else if (retry) {
             if (lane == 0) {
@@ -609,7 +609,7 @@ template <class T> __global__ void __launch_bounds__(128, CSS_STENCIL_MINB) k_pa
                 int r = atomicAdd(a.retryCount, 1);
                 a.retryList[r] = w;
                 nRetry++;
-                if (retry >= 2) atomicAdd(a.counters + C_OVF_REASON + (retry == 2 ? 0 : (retry == 4 ? 1 : 2)), 1ull); // candidates, faces, vertices
+                if (retry >= 2) atomicAdd(a.counters + C_OVF_REASON + (retry == 2 ? 0 : (retry == 5 ? 2 : 1)), 1ull); // candidates, faces, vertices
             }
         } else {
             if (lane == 0) *reinterpret_cast<int4*>(rec) = make_int4(nF, nV, K, 0);

@@ -7,6 +7,7 @@
 //            1 = gpuSimulation (device-resident fused step)
 //   CSS_EXAMPLE_DB=<dir> in the environment: the initial and final states are also written as two records of a
 //   simpleModelDatabase (host/css_database.hpp), as the reference's mains do with their HDF5 trajectory file.
+//   CSS_EXAMPLE_USERFORCE=1: the pair potential is a user-written force subclass (host callback path) instead of the stock one.
 //   CSS_EXAMPLE_R3=<file>: the final R^3 coordinates are written to <file> and imported again (setMeshPositionsFromR3File).
 // The dump holds N, then the initial (face, bary, velocity) and the final (face, bary, velocity, force) arrays in raw
 // little-endian form; tests/test_gpu_parity.py replays the same initial state through the ctypes binding and the oracle.
@@ -14,6 +15,26 @@
 
 #include <chrono>
 #include <cstdlib>
+
+// A potential written by a USER of the plugin surface (src/forces/baseForce.h:30-57): only pairwiseForce / pairwiseEnergy, no
+// device functor.  With a gpuModel the base class downloads the neighbour lists and calls these virtuals on the host.
+// Selected with CSS_EXAMPLE_USERFORCE=1; it states the harmonic law, so the run must reproduce the stock potential's.
+class userWrittenRepulsion : public force
+    {
+public:
+    userWrittenRepulsion(double stiffness, double range) : k(stiffness), sigma(range) { maximumInteractionRange = range; }
+    virtual string reportSelfName() { return "user-written repulsion"; }
+    virtual double pairwiseEnergy(vector3 separation, double distance)
+        {
+        (void)separation;
+        return distance < sigma ? 0.5 * k * (sigma - distance) * (sigma - distance) : 0.0;
+        }
+    virtual vector3 pairwiseForce(vector3 separation, double distance)
+        {
+        return distance <= sigma ? (-k * (sigma - distance)) * separation : vector3(0, 0, 0);
+        }
+    double k, sigma;
+    };
 
 static void dumpState(FILE* f, simpleModel& m, bool withForces)
 {
@@ -53,7 +74,9 @@ int main(int argc, char** argv)
         configuration->setRandomParticlePositions(noise);
         configuration->setMaxwellBoltzmannVelocities(noise, temperature);
 
-        shared_ptr<harmonicRepulsion> pairwiseForce = make_shared<harmonicRepulsion>(1.0, maximumInteractionRange);
+        shared_ptr<force> pairwiseForce;
+        if (getenv("CSS_EXAMPLE_USERFORCE")) pairwiseForce = make_shared<userWrittenRepulsion>(1.0, maximumInteractionRange);
+        else pairwiseForce = make_shared<harmonicRepulsion>(1.0, maximumInteractionRange);
         pairwiseForce->setModel(configuration);
 
         shared_ptr<simulation> simulator = fused ? make_shared<gpuSimulation>() : make_shared<simulation>();

@@ -52,9 +52,31 @@ def main(out_dir):
     ctx.step_nvt(kind, params, 3)
     ctx.step_nve(kind, params, 0.01, 5)
     f2, b2, v2, fr2 = ctx.get_state()
+    # dense neighbourhoods (K ~ 55 > the initial stride of 32) met for the first time inside a fused call: on one rank the exact
+    # candidate count raises the stride guard, on several ranks the replicated coarse-block bound does (every rank in the same
+    # step, without talking); either way the library regrows, finishes the step and goes on
+    Vd, Fd = meshes.torus(60, 24, R=3.0, r=1.0, jitter=0.2, seed=13377)
+    Nd = 601
+    cd, fd, bd, vd = make_state(Vd, Fd, Nd)
+    rcd = interaction_range(float(meshes.face_areas(Vd, Fd).sum()), Nd, 12.0)
+    kd, pd = binding.force_params("harmonic", k=1.0, sigma=rcd)
+    lod, hid = sharding.index_bounds(Nd, rank, world)
+    dense = binding.Context(local)
+    dense.set_mesh(Vd, cd)
+    dense.set_submeshing(True, rcd)
+    if world > 1:
+        uid = [binding.Context.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        dense.comm_init(rank, world, uid[0])
+    dense.set_state(fd, bd, vd[lod:hid], None, n_local=hid - lod, min_idx=lod)
+    dense.step_nve(kd, pd, 0.01, 4)
+    f3, b3, v3, fr3 = dense.get_state()
+    dcnt = dense.counters()
+    dense.close()
     tag = os.environ.get("CSS_TAG", "")
     np.savez(os.path.join(out_dir, "world%d_rank%d%s.npz" % (world, rank, tag)), face=f, bary=b, vel=v, frc=fr, lo=lo, hi=hi, ke=ke,
-             face2=f2, bary2=b2, vel2=v2, frc2=fr2, peer=ctx.comm_info()[2], timeouts=ctx.counters()["peer_timeout"])
+             face2=f2, bary2=b2, vel2=v2, frc2=fr2, peer=ctx.comm_info()[2], timeouts=ctx.counters()["peer_timeout"],
+             face3=f3, bary3=b3, vel3=v3, frc3=fr3, lo3=lod, hi3=hid, ovf3=dcnt["overflow"] + dcnt["kmax_overflow"])
     ctx.close()
     if world > 1:
         dist.barrier()

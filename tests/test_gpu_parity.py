@@ -863,6 +863,33 @@ def test_cpp_host_layer_matches_the_oracle(branch, fused, tmp_path):
 
 
 # ------------------------------------------------------------------------------ multi-GPU
+@pytest.mark.parametrize("branch", [2, 0])
+def test_cpp_host_layer_user_written_force(branch, tmp_path):
+    """A user-written `force` subclass (only pairwiseForce / pairwiseEnergy, src/forces/baseForce.h:30-57) on a gpuModel: the
+    base class downloads the neighbour lists and calls the virtuals on the host (host/css_host.hpp force::computeForces).  The
+    subclass states the harmonic law, so the run must reproduce the stock device functor's: same faces, state to 1e-9."""
+    from curvedspacesim_b200 import build
+
+    exe = build.build_host_example()
+    V, F = _mesh("icosphere16")
+    off = str(tmp_path / "m.off")
+    meshes.save_off(off, V, F)
+    res = []
+    for user in (False, True):
+        dump = str(tmp_path / ("d%d.bin" % user))
+        env = dict(os.environ)
+        if user:
+            env["CSS_EXAMPLE_USERFORCE"] = "1"
+        out = subprocess.run([exe, off, "150", "25", str(branch), "0", dump, "0.01", "0.2"], capture_output=True, text=True, env=env)
+        assert out.returncode == 0, out.stderr
+        res.append(_read_dump(dump))
+    (n0, ini0, fin0), (n1, ini1, fin1) = res
+    assert n0 == n1 and all(np.array_equal(a, b) for a, b in zip(ini0, ini1))
+    assert np.array_equal(fin0[0], fin1[0])
+    for a, b in zip(fin0[1:], fin1[1:]):
+        assert np.max(np.abs(a - b)) < 1e-9
+
+
 def test_cpp_host_layer_imports_r3_positions(tmp_path):
     """simpleModel::setMeshPositionsFromR3File / R3PositionsToMeshPositions of the C++ host layer (css_locate underneath): the final
     R^3 coordinates of a short run, written as a text file, come back as the mesh positions they were computed from."""
@@ -903,6 +930,11 @@ def test_two_gpus_bitwise_equal_to_one(tmp_path):
             assert np.array_equal(two["face"], one["face"]) and np.array_equal(two["bary"], one["bary"])
             lo, hi = int(two["lo"]), int(two["hi"])
             assert np.array_equal(two["vel"], one["vel"][lo:hi]) and np.array_equal(two["frc"], one["frc"][lo:hi])
+            # the dense run whose first neighbour phase overflows the stride inside the fused call (stride guard, both flavours)
+            assert int(two["ovf3"]) == 0 and int(one["ovf3"]) == 0
+            assert np.array_equal(two["face3"], one["face3"]) and np.array_equal(two["bary3"], one["bary3"])
+            lo, hi = int(two["lo3"]), int(two["hi3"])
+            assert np.array_equal(two["vel3"], one["vel3"][lo:hi]) and np.array_equal(two["frc3"], one["frc3"][lo:hi])
     for r in range(world):  # NVT + NVE continuation: the two transports agree bit for bit
         a = np.load(os.path.join(out, "world%d_rank%d_p2p.npz" % (world, r)))
         b = np.load(os.path.join(out, "world%d_rank%d_nccl.npz" % (world, r)))
