@@ -445,7 +445,7 @@ def main():
                 "traffic": km.get("dram_bytes_per_launch"),
                 "peak_source": pk_kind + " (MEASURED_PEAKS.json hbm_gbs, burst copy)" if pk_kind == "measured" else "fallback 6650 GB/s",
                 "kernel": dom + {"k_windows_half": " (stage 2, two sources per warp: window propagation + queries + pair forces + half kick)",
-                                 "k_patch": " (stage 1: ordered candidates + patch flood fill + local indexing)",
+                                 "k_patch": " (stage 1: ordered candidates + patch = the static stencil of the source's face restricted to the cut-off; flood fill where a face has no stencil)",
                                  "retry_tiers": " (large-capacity tier: k_patch<Large> + k_windows<Large>, one warp per source; patches above 96 faces)"}[dom],
                 "formula": "SURVEY 8(d): B_step = 152 + 60 + 24 P_f + 24 P_v + 64 K" + (" + 152 (second NVT move)" if nvt else ""),
                 "algorithmic_bytes_per_source": b_step, "builder_bytes_per_source": builder_bytes,

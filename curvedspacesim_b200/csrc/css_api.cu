@@ -1893,7 +1893,7 @@ int css_last_stage_ms(css_ctx* ctx, float* patch_ms, float* window_ms, float* re
     if (gather_ms) { // walker end -> start of the neighbour phase: the position all-gather (0 on one rank)
         float g = 0;
         if (cudaEventElapsedTime(&g, ctx->ev[4], ctx->ev[0]) != cudaSuccess) g = 0, (void)cudaGetLastError();
-        *gather_ms = g;
+        *gather_ms = g > 0 ? g : 0; // (an NVT step ends with a move: its last walker event follows the neighbour phase)
     }
     return CSS_OK;
 }
