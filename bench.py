@@ -150,7 +150,7 @@ def oracle_arm(wl, threads, steps, warmup, budget_s=None):
     `threads` host threads sharded like mpiModel::determineIndexBounds.  With `budget_s` the step count is chosen from one
     calibration step so that the sample takes about that long (2..500 steps).
     Returns (particle-timesteps/s, seconds, counters, steps)."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))  # the CPU arm is the one place bench.py may use the oracle
     from oracle_binding import Oracle, force_params
 
     orc = Oracle(wl.V, wl.corners)

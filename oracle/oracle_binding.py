@@ -1,6 +1,6 @@
 """ctypes binding of the CPU oracle (oracle/liboracle.so).  TEST INFRASTRUCTURE ONLY: imported by
-tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs, never by the
-product package."""
+tests/ (tests/conftest.py puts this directory on sys.path), __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs, never by the product package."""
 from __future__ import annotations
 
 import ctypes as C
@@ -9,7 +9,7 @@ import subprocess
 
 import numpy as np
 
-_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # repository root (this file lives in oracle/)
 _LIB = None
 
 c_dp = C.POINTER(C.c_double)

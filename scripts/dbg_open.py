@@ -3,6 +3,7 @@ import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
 from curvedspacesim_b200 import binding, meshes
 from helpers import interaction_range, make_state
 from oracle_binding import Oracle, force_params
