@@ -75,7 +75,7 @@ struct css_ctx {
     int t2Warps = 32;
     int wpb0 = 4, wpb1 = 1;
     // two-stage tier 0: patch records (stage 1) -> window propagation (stage 2)
-    bool twoStage = true, winLean = true, winHalf = true;
+    bool twoStage = true, winLean = true, winHalf = true, ctaTiers = true;
     int winWpb = 2;
     unsigned char *d_records = nullptr, *d_recordsL = nullptr;
     double* d_spill = nullptr; // window spill stacks of the two-sources-per-warp kernel (allocated once)
@@ -327,6 +327,7 @@ int css_create(css_ctx** out, int device)
     if (const char* v = getenv("CSS_NO_GRAPH")) ctx->useGraph = atoi(v) == 0;
     if (const char* v = getenv("CSS_WIN_LEAN")) ctx->winLean = atoi(v) != 0;
     if (const char* v = getenv("CSS_WIN_HALF")) ctx->winHalf = atoi(v) != 0; // 0: one warp per source in tier 0 (window_kernel.cu)
+    if (const char* v = getenv("CSS_CTA")) ctx->ctaTiers = atoi(v) != 0;   // 0: long-range tiers on one warp per source (k_geodesic)
     if (const char* v = getenv("CSS_STENCIL")) ctx->useStencil = atoi(v) != 0; // 0: stage 1 of tier 0 flood-fills every patch (patch_kernel.cu)
     if (const char* v = getenv("CSS_WIN_WPB")) ctx->winWpb = std::max(1, std::min(4, atoi(v)));
     if (const char* v = getenv("CSS_P2P")) ctx->p2pEnabled = atoi(v) != 0;
@@ -836,8 +837,8 @@ static int runGeodesicTiers(css_ctx* ctx, GeoArgs a, int nSrc)
         CU(launchGeodesic(ctx->st, a, wpb, blocks));
         ctx->hostKernels++;
     }
-    // long-range tier: the fused kernel, ONE WARP PER SM with its whole workspace in shared memory (the global-memory tier below
-    // pays an L2 round trip for every ring / vertex access: 9.4 -> 1.x ms per step on the reference's default executable shape)
+    // long-range tier: the fused kernel, ONE CTA PER SOURCE AND SM with its whole workspace in shared memory (256 windows per pass;
+    // the global-memory tier below pays an L2 round trip for every ring / vertex access)
     const bool hugeTier = a.xK < 0 && ctx->useCellList && geoWorkspaceBytes(ctx->capsHuge) <= (size_t)geodesicMaxSmemPerBlock();
     if (hugeTier) {
         a.caps = ctx->capsHuge;
@@ -845,7 +846,8 @@ static int runGeodesicTiers(css_ctx* ctx, GeoArgs a, int nSrc)
         a.workCounter = ctx->d_work + 11;
         a.retryList = ctx->d_retry[2], a.retryCount = ctx->d_work + 6;
         a.gws = nullptr, a.lastTier = 0;
-        CU(launchGeodesic(ctx->st, a, 1, ctx->numSMs));
+        if (ctx->ctaTiers) CU(launchGeodesicCta(ctx->st, a, ctx->numSMs));
+        else CU(launchGeodesic(ctx->st, a, 1, ctx->numSMs));
         ctx->hostKernels++;
     }
     // last tier: the fused kernel with capacities sized for the whole mesh, global-memory workspace
@@ -861,7 +863,8 @@ static int runGeodesicTiers(css_ctx* ctx, GeoArgs a, int nSrc)
         a.workCounter = ctx->d_work + 2;
         a.retryList = hugeTier ? ctx->d_retry[1] : ctx->d_retry[2], a.retryCount = ctx->d_work + 12; // (the last tier retries nothing)
         a.gws = ctx->d_gws, a.lastTier = 1;
-        CU(launchGeodesic(ctx->st, a, 1, warps));
+        if (ctx->ctaTiers) CU(launchGeodesicCta(ctx->st, a, warps)); // one workspace per block
+        else CU(launchGeodesic(ctx->st, a, 1, warps));
         ctx->hostKernels++;
     }
     return CSS_OK;

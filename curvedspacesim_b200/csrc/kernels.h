@@ -58,6 +58,7 @@ struct GeoArgs {
 };
 
 cudaError_t launchGeodesic(cudaStream_t st, const GeoArgs& a, int warpsPerBlock, int blocks);
+cudaError_t launchGeodesicCta(cudaStream_t st, const GeoArgs& a, int blocks); // one CTA per source (long-range tiers)
 
 // ---- two-stage tier-0 path: patch records (patch_kernel.cu) -> window propagation (window_kernel.cu) ----
 // Fixed-capacity patch record, one per local source particle, REC_BYTES apart (all offsets 16-byte aligned):
