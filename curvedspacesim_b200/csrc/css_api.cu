@@ -837,7 +837,7 @@ static int runGeodesicTiers(css_ctx* ctx, GeoArgs a, int nSrc)
         CU(launchGeodesic(ctx->st, a, wpb, blocks));
         ctx->hostKernels++;
     }
-    // long-range tier: the fused kernel, ONE CTA PER SOURCE AND SM with its whole workspace in shared memory (256 windows per pass;
+    // long-range tier: the fused kernel, ONE CTA PER SOURCE AND SM with its whole workspace in shared memory (384 windows per pass;
     // the global-memory tier below pays an L2 round trip for every ring / vertex access)
     const bool hugeTier = a.xK < 0 && ctx->useCellList && geoWorkspaceBytes(ctx->capsHuge) <= (size_t)geodesicMaxSmemPerBlock();
     if (hugeTier) {
@@ -1469,9 +1469,6 @@ int css_step_nve_host(css_ctx* ctx, int kind, const double* params, double dt, i
     if (!ctx->nTotal) return fail(ctx, CSS_ESTATE, "state not set (css_set_state fixes the sharding)");
     BIND();
     const int nT = ctx->nTotal, nL = ctx->nLocal;
-    int bad = 0;
-    for (int i = 0; i < nT; ++i) bad |= (face[i] < 0) | (face[i] >= ctx->nF);
-    if (bad) return fail(ctx, CSS_EINVAL, "css_step_nve_host: face index out of range");
     if (!ctx->stCopy) {
         CU(cudaStreamCreateWithFlags(&ctx->stCopy, cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming));
@@ -1479,10 +1476,17 @@ int css_step_nve_host(css_ctx* ctx, int kind, const double* params, double dt, i
     }
     double range;
     ForceParams fp = mkForce(kind, params, &range);
-    CU(cudaMemcpyAsync(ctx->d_face, face, sizeof(int) * nT, cudaMemcpyHostToDevice, ctx->st));
     CU(cudaMemcpyAsync(ctx->d_bary, bary, sizeof(double) * 3 * nT, cudaMemcpyHostToDevice, ctx->st));
     CU(cudaMemcpyAsync(ctx->d_vel, vel, sizeof(double) * 3 * nL, cudaMemcpyHostToDevice, ctx->st));
     CU(cudaMemcpyAsync(ctx->d_frc, frc, sizeof(double) * 3 * nL, cudaMemcpyHostToDevice, ctx->st));
+    int bad = 0; // the face indices are validated while the other uploads fly, and uploaded last: a rejected call leaves the old faces in place
+    for (int i = 0; i < nT; ++i) bad |= (face[i] < 0) | (face[i] >= ctx->nF);
+    if (bad) {
+        CU(cudaStreamSynchronize(ctx->st));
+        ctx->nbrValid = false;
+        return fail(ctx, CSS_EINVAL, "css_step_nve_host: face index out of range");
+    }
+    CU(cudaMemcpyAsync(ctx->d_face, face, sizeof(int) * nT, cudaMemcpyHostToDevice, ctx->st));
     ctx->ioFace = face, ctx->ioBary = bary;
     CU(cudaMemsetAsync(ctx->d_counters + C_STEP_GUARD, 0, sizeof(unsigned long long), ctx->st));
     int rc = nveSteps(ctx, fp, range, dt, 1);

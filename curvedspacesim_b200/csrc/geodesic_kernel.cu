@@ -945,12 +945,15 @@ __device__ int processSource(const GeoArgs& a, const WS& w, int li, int lane)
 // Block-cooperative variant for long-range sources: ONE CTA (CTA_NT threads) PER SOURCE on the same workspace layout.
 // The reference's default executable (N = 20 on torus_isotropic_remesh.off, range 2.6: patches of ~900 faces, ~7 000 windows
 // per source, triangulatedMeshSpace.cpp:212-238) leaves one warp alone on an SM with nothing to hide its latencies behind;
-// here CTA_NT windows are popped per pass (one per thread, both children), children are compacted into the ring by a
+// here CTA_NT (384) windows are popped per pass (one per thread, both children), children are compacted into the ring by a
 // two-level block scan (deterministic order), target and vertex improvements go through 64-bit atomic minima whose unique
 // last writer stores the start / end directions after a barrier, and all pseudo-source fans of a round are spawned in ONE
 // sweep over the (face, corner) pairs of the patch.  Same path set, same arithmetic per window as processSource above.
 // =====================================================================================================================
-constexpr int CTA_NT = 256, CTA_NW = CTA_NT / 32;
+#ifndef CSS_CTA_NT
+#define CSS_CTA_NT 384 // threads per source (build parameter; default-executable shape: 128 -> 0.87, 256 -> 0.67, 384 -> 0.63, 512 -> 0.65 ms)
+#endif
+constexpr int CTA_NT = CSS_CTA_NT, CTA_NW = CTA_NT / 32;
 struct CtaScratch {
     int scan[2][CTA_NW];
     int src;

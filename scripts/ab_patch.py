@@ -31,7 +31,8 @@ h = hashlib.sha256(f.tobytes() + b.tobytes() + v.tobytes() + fr.tobytes()).hexdi
 hn = hashlib.sha256(off.tobytes() + idx.tobytes() + d.tobytes() + ts.tobytes()).hexdigest()[:16]
 print(json.dumps({"lib": os.environ.get("CSS_LIB_PATH", "default").split("/")[-1] + " stencil=" + os.environ.get("CSS_STENCIL", "1"), "step_ms": float(np.median(T)), "patch_ms": float(np.median(P)), "window_ms": float(np.median(W)),
                   "retry_ms": float(np.median(R)), "walk_ms": float(np.median(Wk)), "cell_ms": float(np.median(Ce)), "state_hash": h, "nbr_hash": hn,
-                  "patch_faces": c["patch_faces"], "patch_verts": c["patch_verts"], "queries": c["queries"], "retry": c["tier_retry"], "overflow": c["overflow"]}))
+                  "patch_faces": c["patch_faces"], "patch_verts": c["patch_verts"], "queries": c["queries"], "retry": c["tier_retry"], "overflow": c["overflow"],
+                  "windows": c["windows"], "pseudo": c.get("pseudo_sources", -1), "clk": [c["clk_patch"], c["clk_batch"], c["clk_fan"], c["clk_prop"], c["clk_total"]]}))
 ''' % ROOT
 wl = sys.argv[1]
 for spec in sys.argv[2:]:  # "<lib or default>[:ENV=VALUE[:ENV=VALUE...]]"

@@ -376,8 +376,8 @@ def test_config3_elephant_fire_then_nose_hoover(gpu_ctx_factory):
 @pytest.mark.gpu
 def test_default_executable_shape_long_range(gpu_ctx_factory):
     """The reference's default executable (curvedSpaceSimulation.cpp:25-29: N = 20 on torus_isotropic_remesh.off, area fraction
-    0.9 -> range 2.6): patches of ~830 faces / 440 vertices and ~9 400 windows per source overflow both record tiers and run on
-    the whole-mesh tier (one warp per source on a global-memory workspace).  Same bars as everywhere else."""
+    0.9 -> range 2.6): patches of ~830 faces / 440 vertices and ~7 000 windows per source overflow both record tiers and run on
+    the long-range tier (one CTA per source, workspace in shared memory).  Same bars as everywhere else."""
     orc, V, F, corners, face, bary, vel, N, rc, kind, params = setup_oracle("default_exe")
     ctx = setup_gpu(gpu_ctx_factory, V, corners, face, bary, vel, rc)
     ctx.counters(reset=True)
