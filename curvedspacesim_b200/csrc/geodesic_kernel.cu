@@ -1502,11 +1502,15 @@ __device__ int processSourceCta(const GeoArgs& a, const WS& w, int li, int tid, 
                 }
             }
             const int mine = c0.valid + c1.valid;
+            double sdx = 0, sdy = 0, sdz = 0; // start direction of the window's family, read before anybody may rewrite it
+            if (improved) {
+                if (psv == NONE16) liftRoot(C - S, sdx, sdy, sdz);
+                else sdx = w.dirx()[psv], sdy = w.diry()[psv], sdz = w.dirz()[psv];
+            }
             int tot;
             int pos = tail + blockExclusiveScan(mine, tid, sc, parity, tot); // (barrier: every atomic minimum of the pass is done)
             if (improved && dC == w.D()[vC]) { // the standing minimum writes the start direction carried to this vertex
-                if (psv == NONE16) liftRoot(C - S, w.dirx()[vC], w.diry()[vC], w.dirz()[vC]);
-                else w.dirx()[vC] = w.dirx()[psv], w.diry()[vC] = w.diry()[psv], w.dirz()[vC] = w.dirz()[psv];
+                w.dirx()[vC] = sdx, w.diry()[vC] = sdy, w.dirz()[vC] = sdz;
                 w.vdirty[vC] = 1;
             }
             if (tail + tot - head > cp.ring) return ST_OVF_RING;

@@ -254,6 +254,7 @@ template <class T> __device__ int buildPatch2(const PatchArgs& a, PatchSmem2<T>&
             const int id = nF + __popc(bal & ltMask);
             int vs = -1;
             bool vnew = false;
+            __syncwarp(); // the frontier slots read at the top of the pass may be the ones reused below (ring of FR entries)
             if (win) {
                 s.fhVal[slot] = (unsigned char)id;
                 gface[id] = g;
