@@ -752,7 +752,8 @@ static int runGeodesicTiers(css_ctx* ctx, GeoArgs a, int nSrc)
     if (staged) {
         // Two-stage tiers: patch records (integer / latency-bound, high occupancy), then window propagation (fp64).
         // Tier 0 = TierSmall over every local source; tier 1 = TierLarge over the sources tier 0 handed on.
-        const int maxLarge = std::min(std::max(nSrc, 1), 65536);
+        static const int maxLargeEnv = getenv("CSS_MAX_LARGE") ? atoi(getenv("CSS_MAX_LARGE")) : -1; // developer switch: 0 hands tier 1's sources straight on
+        const int maxLarge = maxLargeEnv >= 0 ? maxLargeEnv : std::min(std::max(nSrc, 1), 65536);
         size_t needS = (size_t)std::max(nSrc, 1) * TierSmall::BYTES, needL = (size_t)maxLarge * TierLarge::BYTES;
         if (needS > ctx->capRecords || needL > ctx->capRecordsL || (ctx->winHalf && !ctx->d_spill)) {
             CU(cudaStreamSynchronize(ctx->st));
