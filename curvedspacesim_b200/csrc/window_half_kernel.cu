@@ -305,7 +305,7 @@ template <class T> __global__ void __launch_bounds__(32 * CSS_HALF_WPB, CSS_HALF
             // so a pass is full whenever the two rings together hold 16 windows (a BFS level of one patch rarely does).
             for (;;) {
                 // a source whose ring ran dry takes spilled windows back (see the push below); each half moves its own
-                if (spillN > 0 && head == tail) {
+                if (__builtin_expect(spillN > 0 && head == tail, 0)) { // (rare paths carry branch hints: the compiler moves them out of the loop body, which is instruction-fetch sensitive)
                     const int n = min(spillN, 16);
                     if (hl < n) {
                         const double* e = spill + (size_t)(spillN - 1 - hl) * SPILL_DOUBLES;
@@ -386,7 +386,7 @@ template <class T> __global__ void __launch_bounds__(32 * CSS_HALF_WPB, CSS_HALF
                         const double c = sg + fsqrt(d.x * d.x + d.y * d.y);
                         if (den != 0 && mu >= t0 - 1e-12 && mu <= t1 + 1e-12 && atomicMinD(&wp.tbest[t], c)) improvedT = true, myT = t, cand = c, dT = d;
                     }
-                    if (__any_sync(FULL, improvedT)) { // the winner (lowest lane among equal candidates) records how its path starts and ends
+                    if (__builtin_expect(__any_sync(FULL, improvedT), 0)) { // the winner (lowest lane among equal candidates) records how its path starts and ends
                         __syncwarp();
                         bool win = improvedT && wp.tbest[myT] == cand;
                         if (win) atomicMin(&wp.towner[myT], lane);
@@ -464,7 +464,7 @@ template <class T> __global__ void __launch_bounds__(32 * CSS_HALF_WPB, CSS_HALF
                     const bool ovf0 = tail0 + tot0 - (head0 + nb0) > T::RING, ovf1 = tail1 + tot1 - (head1 + nb1) > T::RING;
                     const int rank = __popc(bal & (src ? ~lanes0 : lanes0) & ((1u << lane) - 1u));
                     const int toth = half ? tot1 : tot0;
-                    if (!(ovf0 | ovf1)) { // the common case: everything fits
+                    if (__builtin_expect(!(ovf0 | ovf1), 1)) { // the common case: everything fits
                         if (valid) {
                             const int q = ((src ? tail1 : tail0) + rank) & MASKR;
                             wp.rax[q] = X.x, wp.ray[q] = X.y, wp.rbx[q] = Y.x, wp.rby[q] = Y.y;
