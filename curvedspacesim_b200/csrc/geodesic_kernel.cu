@@ -1155,24 +1155,23 @@ __device__ int processSourceCta(const GeoArgs& a, const WS& w, int li, int tid, 
                     __syncthreads();
                     if (ovf) return ST_OVF_F;
                     if (head >= tail) break;
-                    for (int idx = head + tid; idx < tail; idx += CTA_NT) {
-                        int f = w.gface[idx];
-                        int4 ad = __ldg(a.m.adj + f);
-#pragma unroll
-                        for (int k = 0; k < 3; ++k) {
-                            int g = k == 0 ? ad.x : (k == 1 ? ad.y : ad.z);
-                            if (g < 0) continue;
-                            if (hashFind(w.fhKey, maskF, g) >= 0) continue;
-                            int4 c = __ldg(a.m.corner + g);
-                            bool far = xsqlen(xsub3(sp, ldvert(a.m, c.x))) > thr2 && xsqlen(xsub3(sp, ldvert(a.m, c.y))) > thr2
-                                       && xsqlen(xsub3(sp, ldvert(a.m, c.z))) > thr2;
-                            if (far) continue;
-                            if (w.misc[0] >= cp.maxF) {
-                                w.misc[2] = 1;
-                                continue;
-                            }
-                            addFace(g);
+                    // one thread per (frontier face, edge): the three dependent L2 round trips of a candidate (adjacency, corners,
+                    // vertices) run side by side for the whole ring instead of edge after edge
+                    for (int item = 3 * head + tid; item < 3 * tail; item += CTA_NT) {
+                        const int idx = item / 3, k = item - 3 * idx;
+                        const int4 ad = __ldg(a.m.adj + w.gface[idx]);
+                        const int g = k == 0 ? ad.x : (k == 1 ? ad.y : ad.z);
+                        if (g < 0) continue;
+                        if (hashFind(w.fhKey, maskF, g) >= 0) continue;
+                        const int4 c = __ldg(a.m.corner + g);
+                        const d3 q0 = ldvert(a.m, c.x), q1 = ldvert(a.m, c.y), q2 = ldvert(a.m, c.z);
+                        const bool far = xsqlen(xsub3(sp, q0)) > thr2 && xsqlen(xsub3(sp, q1)) > thr2 && xsqlen(xsub3(sp, q2)) > thr2;
+                        if (far) continue;
+                        if (w.misc[0] >= cp.maxF) {
+                            w.misc[2] = 1;
+                            continue;
                         }
+                        addFace(g);
                     }
                     head = tail;
                 }

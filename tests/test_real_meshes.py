@@ -401,6 +401,40 @@ def test_default_executable_shape_long_range(gpu_ctx_factory):
 
 
 @pytest.mark.gpu
+def test_range_beyond_the_shared_memory_tier_runs_on_the_whole_mesh_workspace(gpu_ctx_factory):
+    """torus_isotropic_remesh.off with a range of 4.2 (N = 12): patches of ~2 500 faces outgrow the shared-memory long-range tier
+    (1 408 faces) and are served by the same block-cooperative kernel on the global-memory workspace sized for the whole mesh
+    (k_geodesic_cta<global>), neighbour lists, forces and fused steps included.  Same bars as everywhere else."""
+    V, F, _, _ = load("default_exe")
+    N, rc = 12, 4.2
+    corners, face, bary, vel = make_state(V, F, N, seed=4242)
+    kind, params = force_params("harmonic", k=1.0, sigma=rc)
+    orc = Oracle(V, corners)
+    orc.set_submeshing(True, rc)
+    orc.set_options(True, False, 8)
+    orc.set_state(face, bary, vel)
+    ctx = setup_gpu(gpu_ctx_factory, V, corners, face, bary, vel, rc)
+    ctx.counters(reset=True)
+    o_off, o_idx, o_d, o_ts, o_te = orc.find_neighbors(rc)
+    g_off, g_idx, g_d, g_ts, g_te = ctx.find_neighbors(rc, want_end=True)
+    assert np.array_equal(o_off, g_off) and np.array_equal(o_idx, g_idx) and len(o_idx) > 3 * N
+    c, oc = ctx.counters(), orc.counters()
+    assert c["patch_faces"] == oc["patch_faces"] and c["patch_verts"] == oc["patch_verts"] and c["patch_faces"] > 1500 * N
+    assert c["overflow"] == 0 and c["tier_retry"] >= 2 * N + N // 2       # most sources went through all three hand-overs
+    assert _rel(g_d, o_d) < TOL_DIST and np.max(np.abs(g_ts - o_ts)) < TOL_TAN and np.max(np.abs(g_te - o_te)) < TOL_TAN
+    f0 = orc.compute_forces(kind, params)
+    ctx.compute_forces(kind, params)
+    assert np.max(np.abs(f0 - ctx.get_state()[3])) < TOL_FORCE * np.abs(f0).max()
+    orc.run_nve(kind, params, 0.01, 20)
+    ctx.step_nve(kind, params, 0.01, 20)
+    of, ob, ov, _ = orc.get_state()
+    gf, gb, gv, _ = ctx.get_state()
+    assert np.array_equal(of, gf) and np.max(np.abs(ob - gb)) < 1e-9 and np.max(np.abs(ov - gv)) < 1e-9
+    print("whole-mesh workspace: %.0f faces / %.0f vertices per patch, %.0f windows per source, retries %d" % (
+        c["patch_faces"] / N, c["patch_verts"] / N, c["windows"] / N, c["tier_retry"]))
+
+
+@pytest.mark.gpu
 def test_vertex_aimed_displacements_are_flagged_and_bit_equal(gpu_ctx_factory):
     """meshTesting.cpp:206-241 (branch -1): face 1 of torus_isotropic_remesh.off, from (0.4,0.3,0.3) along twice the chord to
     (0.7,0.3,0) -- as coded it crosses the edge opposite corner 2, not a vertex -- and the same source aimed exactly at each
