@@ -431,7 +431,7 @@ def main():
     b_step = 152 + 60 + 24 * pf + 24 * pv + 28 * kq + 36 * kq + (152 if nvt else 0)
     builder_bytes = (16 + 5 * kq + 5 * pv + 12 * pf) + 48 * pf + 24 * pv + 48 * kq + 52 + 36 * kq + 24 + 48
     stage = {"k_patch": float(np.mean(patch_ms)), "k_windows_half": float(np.mean(win_ms)), "retry_tiers": float(np.mean(retry_ms))}
-    dom = max(stage, key=stage.get)  # retry_tiers = k_patch<Large> + k_windows<Large> + last tier: dominant only on coarse meshes (config 1)
+    dom = max(stage, key=stage.get)  # retry_tiers = k_patch<Large> + k_windows<Large> + the long-range CTA tiers: dominant on config 1 and the default exe
     dom_ms = stage[dom]
     achieved = (b_step * nloc) / (dom_ms * 1e-3) / 1e9
     pk, pk_kind = peaks()
@@ -446,7 +446,8 @@ def main():
                 "peak_source": pk_kind + " (MEASURED_PEAKS.json hbm_gbs, burst copy)" if pk_kind == "measured" else "fallback 6650 GB/s",
                 "kernel": dom + {"k_windows_half": " (stage 2, two sources per warp: window propagation + queries + pair forces + half kick)",
                                  "k_patch": " (stage 1: ordered candidates + patch = the static stencil of the source's face restricted to the cut-off; flood fill where a face has no stencil)",
-                                 "retry_tiers": " (large-capacity tier: k_patch<Large> + k_windows<Large>, one warp per source; patches above 96 faces)"}[dom],
+                                 "retry_tiers": " (patches above 96 faces: k_patch<Large> + k_windows<Large>, one warp per source, up to 240 faces; beyond that "
+                                                "k_geodesic_cta, one CTA per source)"}[dom],
                 "formula": "SURVEY 8(d): B_step = 152 + 60 + 24 P_f + 24 P_v + 64 K" + (" + 152 (second NVT move)" if nvt else ""),
                 "algorithmic_bytes_per_source": b_step, "builder_bytes_per_source": builder_bytes,
                 "frac_builder_bytes": (builder_bytes * nloc) / (dom_ms * 1e-3) / 1e9 / pk["hbm_gbs"],

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, final evidence run (1 GPU): parity suite, bench lines of every workload and of the reference arm, launch list,
-# full ncu captures of the three kernels that make up the step
+# full ncu captures of the kernels that make up the step (+ the long-range CTA kernel on the default-executable shape)
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -q -s --maxfail=10 2>&1 | grep -v "^$" | tail -40 > gpurun_out/r2_pytest_gpu.log
 tail -3 gpurun_out/r2_pytest_gpu.log
@@ -14,5 +14,9 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 bash scripts/ncu_kernel.sh k_windows_half cfg5_torus_1Mfaces_N100k gpurun_out/r2_k_windows_half 4
 bash scripts/ncu_kernel.sh k_patch_stencil cfg5_torus_1Mfaces_N100k gpurun_out/r2_k_patch_stencil 4
 bash scripts/ncu_kernel.sh k_walk cfg5_torus_1Mfaces_N100k gpurun_out/r2_k_walk 4
+bash scripts/ncu_kernel.sh k_geodesic_cta default_exe_torus_isotropic_N20 gpurun_out/r2_k_geodesic_cta 4
+bash scripts/ncu_stalls.sh k_windows_half > gpurun_out/r2_k_windows_half_stalls.txt 2>&1
+timeout 900 compute-sanitizer --tool initcheck python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "test_neighbours_distances_tangents_forces and torus60x24" > gpurun_out/r2_sanitizer_initcheck.log 2>&1
+grep -E "ERROR SUMMARY|passed|failed" gpurun_out/r2_sanitizer_initcheck.log | tail -2
 tail -3 gpurun_out/r2_bench.err
 nproc; lscpu | grep "Model name"
