@@ -948,6 +948,11 @@ static int ensureNeighbors(css_ctx* ctx)
         CU(regrow(ctx->d_nbrDist, need));
         CU(regrow(ctx->d_nbrTs, 3 * need));
         if (ctx->wantEnd) CU(regrow(ctx->d_nbrTe, 3 * need));
+        // the rows have a fixed stride and are downloaded whole (css_get_neighbors compacts them by the counts): define the unused tails once
+        CU(cudaMemsetAsync(ctx->d_nbrIdx, 0, sizeof(int) * need, ctx->st));
+        CU(cudaMemsetAsync(ctx->d_nbrDist, 0, sizeof(double) * need, ctx->st));
+        CU(cudaMemsetAsync(ctx->d_nbrTs, 0, sizeof(double) * 3 * need, ctx->st));
+        if (ctx->wantEnd) CU(cudaMemsetAsync(ctx->d_nbrTe, 0, sizeof(double) * 3 * need, ctx->st));
         ctx->nbrHasEnd = ctx->wantEnd;
         ctx->capNbr = (int)need;
     }
@@ -1027,6 +1032,9 @@ static int setupGrid(css_ctx* ctx, double range)
         // counts | bump counter | occupancy of the 2x2x2 coarse blocks (sharded runs: replicated stride bound), cleared together
         CU(regrow(ctx->d_cellCount, 2 * (size_t)ctx->nCells + 2)); // (a coarse grid never has more blocks than the grid has cells)
         CU(regrow(ctx->d_cellStart, (size_t)ctx->nCells + 1));
+        // only occupied cells get a start written each step; readers fetch start and count together and ignore the start of an
+        // empty cell, so the array is defined once here (compute-sanitizer initcheck)
+        CU(cudaMemsetAsync(ctx->d_cellStart, 0, sizeof(int) * ((size_t)ctx->nCells + 1), ctx->st));
         ctx->capCells = ctx->nCells;
     }
     return CSS_OK;

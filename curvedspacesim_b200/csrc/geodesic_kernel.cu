@@ -413,8 +413,8 @@ __device__ int processSource(const GeoArgs& a, const WS& w, int li, int lane)
                         bool far = xsqlen(xsub3(sp, ldvert(a.m, c.x))) > thr2 && xsqlen(xsub3(sp, ldvert(a.m, c.y))) > thr2
                                    && xsqlen(xsub3(sp, ldvert(a.m, c.z))) > thr2;
                         if (far) continue;
-                        if (w.misc[0] >= cp.maxF) {
-                            w.misc[2] = 1;
+                        if (w.misc[0] >= cp.maxF) { // full: a second look tells whether g is really missing (another lane may have added it)
+                            if (hashFind(w.fhKey, maskF, g) < 0) w.misc[2] = 1;
                             continue;
                         }
                         addFace(g);
@@ -1167,9 +1167,9 @@ __device__ int processSourceCta(const GeoArgs& a, const WS& w, int li, int tid, 
                         const d3 q0 = ldvert(a.m, c.x), q1 = ldvert(a.m, c.y), q2 = ldvert(a.m, c.z);
                         const bool far = xsqlen(xsub3(sp, q0)) > thr2 && xsqlen(xsub3(sp, q1)) > thr2 && xsqlen(xsub3(sp, q2)) > thr2;
                         if (far) continue;
-                        if (w.misc[0] >= cp.maxF) {
-                            w.misc[2] = 1;
-                            continue;
+                        if (w.misc[0] >= cp.maxF) { // full: nobody inserts any more, so a second look tells whether g is really missing
+                            if (hashFind(w.fhKey, maskF, g) < 0) w.misc[2] = 1; // (another thread may have added g since the first look:
+                            continue;                                           //  the whole-mesh tier fills up to exactly maxF faces)
                         }
                         addFace(g);
                     }
@@ -1177,8 +1177,10 @@ __device__ int processSourceCta(const GeoArgs& a, const WS& w, int li, int tid, 
                 }
                 for (int t = tid; t < K; t += CTA_NT) // leftover goal faces (:143-144)
                     if (hashFind(w.fhKey, maskF, w.tGFace[t]) < 0) {
-                        if (w.misc[0] >= cp.maxF) w.misc[2] = 1;
-                        else addFace(w.tGFace[t]);
+                        if (w.misc[0] >= cp.maxF) {
+                            if (hashFind(w.fhKey, maskF, w.tGFace[t]) < 0) w.misc[2] = 1;
+                        } else
+                            addFace(w.tGFace[t]);
                     }
             }
         }

@@ -599,6 +599,11 @@ template <class T> __global__ void __launch_bounds__(128, CSS_STENCIL_MINB) k_pa
                     }
                 }
             }
+            if (!retry) { // stage 2 stages the face sections in 16-byte and the eligibility flags in 4-byte pieces: define the tail of the last piece
+                const int padF = (4 - (nF & 3)) & 3, padV = (4 - (nV & 3)) & 3;
+                if (lane < padF) ofvert[nF + lane] = 0u, ofadj[nF + lane] = 0u;
+                if (lane < padV) rec[T::OFF_VELIG + nV + lane] = 0;
+            }
         }
         // ---------------- header, candidate ids, retry list ----------------
         if (retry == 3 && a.fallbackList) { // no stencil here: the flood fill (patch_kernel.cu) writes this record

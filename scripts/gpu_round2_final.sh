@@ -16,7 +16,8 @@ bash scripts/ncu_kernel.sh k_patch_stencil cfg5_torus_1Mfaces_N100k gpurun_out/r
 bash scripts/ncu_kernel.sh k_walk cfg5_torus_1Mfaces_N100k gpurun_out/r2_k_walk 4
 bash scripts/ncu_kernel.sh k_geodesic_cta default_exe_torus_isotropic_N20 gpurun_out/r2_k_geodesic_cta 4
 bash scripts/ncu_stalls.sh k_windows_half > gpurun_out/r2_k_windows_half_stalls.txt 2>&1
-timeout 900 compute-sanitizer --tool initcheck python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "test_neighbours_distances_tangents_forces and torus60x24" > gpurun_out/r2_sanitizer_initcheck.log 2>&1
+SEL='(test_neighbours_distances_tangents_forces and (icosphere16 or torus60x24)) or test_open_mesh_boundary_rules or test_edge_cases or test_stride_guard or test_gpu_vertex_crossings or test_gpu_boundary_vertex or default_executable'
+timeout 1500 compute-sanitizer --tool initcheck python -m pytest tests/test_gpu_parity.py tests/test_vertex_crossings.py tests/test_real_meshes.py -m gpu -q -x -k "$SEL" > gpurun_out/r2_sanitizer_initcheck.log 2>&1
 grep -E "ERROR SUMMARY|passed|failed" gpurun_out/r2_sanitizer_initcheck.log | tail -2
 tail -3 gpurun_out/r2_bench.err
 nproc; lscpu | grep "Model name"
