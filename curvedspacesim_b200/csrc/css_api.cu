@@ -68,14 +68,13 @@ struct css_ctx {
     int capRetry = 0;
     char* d_gws = nullptr;
     size_t gwsBytes = 0;
-    GeoCaps capsT0{96, 64, 64, 16, 256, 256}, capsT1{768, 448, 1024, 128, 2048, 1024}, capsT2{0, 0, 0, 0, 0, 0};
+    GeoCaps capsT2{0, 0, 0, 0, 0, 0}; // whole-mesh capacities of the last tier (set with the mesh)
     // one warp per SM on a shared-memory workspace (~195 kB): long-range patches of up to 1408 faces / 768 vertices (the reference's
     // default executable: N = 20, range 2.6 on torus_isotropic_remesh.off) stay out of the global-memory tier
-    GeoCaps capsHuge{1408, 768, 1024, 32, 4096, 2048};
+    GeoCaps capsHuge{1408, 768, 1024, 128, 4096, 2048}; // long-range tier: one CTA per source, workspace in shared memory
     int t2Warps = 32;
-    int wpb0 = 4, wpb1 = 1;
     // two-stage tier 0: patch records (stage 1) -> window propagation (stage 2)
-    bool twoStage = true, winLean = true, winHalf = true, ctaTiers = true;
+    bool winLean = true, winHalf = true;
     int winWpb = 2;
     unsigned char *d_records = nullptr, *d_recordsL = nullptr;
     double* d_spill = nullptr; // window spill stacks of the two-sources-per-warp kernel (allocated once)
@@ -311,23 +310,10 @@ int css_create(css_ctx** out, int device)
     cudaMalloc(&ctx->d_red, 24 * sizeof(double));
     for (auto& e : ctx->ev) cudaEventCreate(&e);
     for (auto& e : ctx->evS) cudaEventCreate(&e);
-    if (const char* tune = getenv("CSS_TUNE")) { // developer tuning: t0 maxF,maxV,ring,kt,warpsPerBlock, t1 ...
-        int v[10];
-        int n = sscanf(tune, "%d,%d,%d,%d,%d,%d,%d,%d,%d,%d", v, v + 1, v + 2, v + 3, v + 4, v + 5, v + 6, v + 7, v + 8, v + 9);
-        auto p2 = [](int x) {
-            int p = 1;
-            while (p < x) p <<= 1;
-            return p;
-        };
-        if (n >= 5) ctx->capsT0 = GeoCaps{v[0], v[1], p2(v[2]), v[3], p2(2 * v[0] + 64), p2(2 * v[1] + 128)}, ctx->wpb0 = v[4];
-        if (n >= 10) ctx->capsT1 = GeoCaps{v[5], v[6], p2(v[7]), v[8], p2(2 * v[5] + 64), p2(2 * v[6] + 128)}, ctx->wpb1 = v[9];
-    }
     for (auto& e : ctx->tev) cudaEventCreate(&e);
-    if (const char* v = getenv("CSS_LEGACY_TIER0")) ctx->twoStage = atoi(v) == 0; // developer switch: fused one-kernel tier 0
     if (const char* v = getenv("CSS_NO_GRAPH")) ctx->useGraph = atoi(v) == 0;
     if (const char* v = getenv("CSS_WIN_LEAN")) ctx->winLean = atoi(v) != 0;
     if (const char* v = getenv("CSS_WIN_HALF")) ctx->winHalf = atoi(v) != 0; // 0: one warp per source in tier 0 (window_kernel.cu)
-    if (const char* v = getenv("CSS_CTA")) ctx->ctaTiers = atoi(v) != 0;   // 0: long-range tiers on one warp per source (k_geodesic)
     if (const char* v = getenv("CSS_STENCIL")) ctx->useStencil = atoi(v) != 0; // 0: stage 1 of tier 0 flood-fills every patch (patch_kernel.cu)
     if (const char* v = getenv("CSS_WIN_WPB")) ctx->winWpb = std::max(1, std::min(4, atoi(v)));
     if (const char* v = getenv("CSS_P2P")) ctx->p2pEnabled = atoi(v) != 0;
@@ -747,7 +733,7 @@ static int runGeodesicTiers(css_ctx* ctx, GeoArgs a, int nSrc)
         }
         return CSS_OK;
     };
-    const bool staged = ctx->twoStage && a.xK < 0 && a.cellStart != nullptr;
+    const bool staged = a.xK < 0 && a.cellStart != nullptr; // neighbour phase with a cell list: record tiers first
     if (staged && (rc = ensureStencils(ctx))) return rc;
     if (staged) {
         // Two-stage tiers: patch records (integer / latency-bound, high occupancy), then window propagation (fp64).
@@ -813,59 +799,33 @@ static int runGeodesicTiers(css_ctx* ctx, GeoArgs a, int nSrc)
         CU(launchPatch<TierLarge>(ctx->st, p, ctx->numSMs));
         CU(launchWindows<TierLarge>(ctx->st, w, 1, ctx->numSMs, false));
         ctx->hostKernels += 4;
-    } else {
-        // fused tier 0 (explicit css_distance queries, all-to-all candidates, developer switch): shared memory
-        a.caps = ctx->capsT0;
-        a.srcList = nullptr, a.srcCount = nullptr;
-        a.workCounter = ctx->d_work + 0;
-        a.retryList = ctx->d_retry[0], a.retryCount = ctx->d_work + 4;
-        a.gws = nullptr, a.lastTier = 0;
-        size_t ws = geoWorkspaceBytes(a.caps);
-        int wpb = ctx->wpb0;
-        int bps = std::max(1, std::min(12 / wpb, (int)(geodesicMaxSmemPerBlock() / (ws * wpb))));
-        int blocks = std::min(ctx->numSMs * bps, std::max(1, (nSrc + wpb - 1) / wpb));
-        CU(launchGeodesic(ctx->st, a, wpb, blocks));
-        ctx->hostKernels++;
-        // fused tier 1: large capacities on a global-memory workspace
-        a.caps = ctx->capsT1;
-        ws = geoWorkspaceBytes(a.caps);
-        wpb = 2, blocks = std::min(ctx->numSMs * 2, std::max(1, nSrc));
-        if (int rc2 = ensureWorkspace(ws * wpb * blocks)) return rc2;
-        a.srcList = ctx->d_retry[0], a.srcCount = ctx->d_work + 4;
-        a.workCounter = ctx->d_work + 8;
-        a.retryList = ctx->d_retry[1], a.retryCount = ctx->d_work + 5;
-        a.gws = ctx->d_gws, a.lastTier = 0;
-        CU(launchGeodesic(ctx->st, a, wpb, blocks));
-        ctx->hostKernels++;
     }
-    // long-range tier: the fused kernel, ONE CTA PER SOURCE AND SM with its whole workspace in shared memory (384 windows per pass;
-    // the global-memory tier below pays an L2 round trip for every ring / vertex access)
-    const bool hugeTier = a.xK < 0 && ctx->useCellList && geoWorkspaceBytes(ctx->capsHuge) <= (size_t)geodesicMaxSmemPerBlock();
-    if (hugeTier) {
+    // Long-range tier: the fused kernel, ONE CTA PER SOURCE AND SM with its whole workspace in shared memory (384 windows per pass;
+    // the global-memory tier below pays an L2 round trip for every ring / vertex access).  It serves what the record tiers handed
+    // on and, directly, explicit css_distance queries and the all-to-all (no cell list) mode.
+    {
         a.caps = ctx->capsHuge;
-        a.srcList = ctx->d_retry[1], a.srcCount = ctx->d_work + 5;
+        a.srcList = staged ? ctx->d_retry[1] : nullptr, a.srcCount = staged ? ctx->d_work + 5 : nullptr;
         a.workCounter = ctx->d_work + 11;
         a.retryList = ctx->d_retry[2], a.retryCount = ctx->d_work + 6;
         a.gws = nullptr, a.lastTier = 0;
-        if (ctx->ctaTiers) CU(launchGeodesicCta(ctx->st, a, ctx->numSMs));
-        else CU(launchGeodesic(ctx->st, a, 1, ctx->numSMs));
+        CU(launchGeodesicCta(ctx->st, a, std::min(ctx->numSMs, staged ? ctx->numSMs : std::max(nSrc, 1))));
         ctx->hostKernels++;
     }
-    // last tier: the fused kernel with capacities sized for the whole mesh, global-memory workspace
+    // last tier: the same kernel with capacities sized for the whole mesh, global-memory workspace (one per block)
     {
         a.caps = ctx->capsT2;
         if (a.xK >= 0) a.caps.kt = std::max(a.caps.kt, a.xK);
         else if (!ctx->useCellList) a.caps.kt = std::max(a.caps.kt, a.nTotal);
         else a.caps.kt = std::max(a.caps.kt, a.kmax);
         size_t ws = geoWorkspaceBytes(a.caps);
-        int warps = ctx->t2Warps;
-        if (int rc2 = ensureWorkspace(ws * warps)) return rc2;
-        a.srcList = hugeTier ? ctx->d_retry[2] : ctx->d_retry[1], a.srcCount = ctx->d_work + (hugeTier ? 6 : 5);
+        int blocks = ctx->t2Warps;
+        if (int rc2 = ensureWorkspace(ws * blocks)) return rc2;
+        a.srcList = ctx->d_retry[2], a.srcCount = ctx->d_work + 6;
         a.workCounter = ctx->d_work + 2;
-        a.retryList = hugeTier ? ctx->d_retry[1] : ctx->d_retry[2], a.retryCount = ctx->d_work + 12; // (the last tier retries nothing)
+        a.retryList = ctx->d_retry[1], a.retryCount = ctx->d_work + 12; // (the last tier retries nothing)
         a.gws = ctx->d_gws, a.lastTier = 1;
-        if (ctx->ctaTiers) CU(launchGeodesicCta(ctx->st, a, warps)); // one workspace per block
-        else CU(launchGeodesic(ctx->st, a, 1, warps));
+        CU(launchGeodesicCta(ctx->st, a, blocks));
         ctx->hostKernels++;
     }
     return CSS_OK;
@@ -1354,7 +1314,7 @@ static uint64_t nveGraphKey(css_ctx* ctx, const ForceParams& fp, double range, d
 #define MIX(x) mix(&(x), sizeof(x))
     MIX(fp.kind), MIX(fp.a), MIX(fp.sigma), MIX(range), MIX(dt);
     MIX(ctx->nLocal), MIX(ctx->nTotal), MIX(ctx->minIdx), MIX(ctx->kmax), MIX(ctx->nranks), MIX(ctx->timing), MIX(ctx->submeshing),
-        MIX(ctx->maxDist), MIX(ctx->boundaryMode), MIX(ctx->useCellList), MIX(ctx->wantEnd), MIX(ctx->twoStage), MIX(ctx->winWpb), MIX(ctx->winLean), MIX(ctx->winHalf), MIX(ctx->useStencil), MIX(ctx->stencilUsable), MIX(ctx->stencilMissing), MIX(ctx->grid), MIX(ctx->nCells);
+        MIX(ctx->maxDist), MIX(ctx->boundaryMode), MIX(ctx->useCellList), MIX(ctx->wantEnd), MIX(ctx->winWpb), MIX(ctx->winLean), MIX(ctx->winHalf), MIX(ctx->useStencil), MIX(ctx->stencilUsable), MIX(ctx->stencilMissing), MIX(ctx->grid), MIX(ctx->nCells);
     void* ptrs[] = {ctx->d_vert, ctx->d_corner, ctx->d_adj, ctx->d_adjopp, ctx->d_geo, ctx->d_saddle, ctx->d_face, ctx->d_bary, ctx->d_eucl, ctx->d_vel, ctx->d_frc,
                     ctx->d_disp, ctx->d_walkFlags, ctx->d_cellOf, ctx->d_cellCount, ctx->d_cellStart, ctx->d_cellSlot, ctx->d_tmpItems,
                     ctx->d_items, ctx->d_nbrCount, ctx->d_nbrIdx, ctx->d_nbrDist, ctx->d_nbrTs, ctx->d_nbrTe, ctx->d_retry[0], ctx->d_retry[1],
@@ -1896,7 +1856,7 @@ int css_last_kernel_ms(css_ctx* ctx, float* geodesic_ms, float* walk_ms, float* 
 int css_last_stage_ms(css_ctx* ctx, float* patch_ms, float* window_ms, float* retry_ms, float* gather_ms)
 {
     if (!ctx) return CSS_EINVAL;
-    if (!ctx->timing || !ctx->twoStage) return fail(ctx, CSS_ESTATE, "stage timing needs css_set_timing(1) and the two-stage path");
+    if (!ctx->timing) return fail(ctx, CSS_ESTATE, "stage timing needs css_set_timing(1)");
     BIND();
     CU(cudaEventSynchronize(ctx->ev[2]));
     float a = 0, b = 0, c = 0;

@@ -1,18 +1,17 @@
-// Many-source exact geodesic kernel: ONE WARP PER SOURCE PARTICLE.
+// Fused exact geodesic kernel for long ranges: ONE CTA PER SOURCE PARTICLE (k_geodesic_cta).
 //
-// For its source the warp (1) gathers the ordered Euclidean candidate list from the cell list
-// (cellListNeighborStructure::constructCandidateNeighborList, src/utility/cellListNeighborStructure.cpp:45-84),
-// (2) flood-fills the local patch with the rule of submesher::constructSubmeshFromSourceAndTargets
-// (src/utility/submesher.cpp:55-147) into its private workspace (shared memory; global memory for the
-// large-capacity fallback tiers), (3) runs exact window propagation (Chen-Han unfolding with the
-// Xin-Wang vertex-distance filter; saddle and patch-boundary vertices are pseudo-sources) over a FIFO
-// ring of windows, 32 windows per step, one per lane, with ballot/shuffle compaction of the children,
-// (4) answers the K target queries (distance, start tangent, end tangent), which replaces
-// CGAL::Surface_mesh_shortest_path as used at src/models/triangulatedMeshSpace.cpp:189-203 and
-// src/utility/meshUtilities.cpp:360-380, and (5) optionally accumulates the pair force of
-// force::computeForces (src/forces/baseForce.cpp:12-28) in neighbour order and applies the velocity
-// half-kick (src/updaters/velocityVerletNVE.cpp:27-28), so tangents never round-trip through HBM
-// unless the caller asks for the lists.
+// For its source the CTA (1) gathers the ordered Euclidean candidate list from the cell list
+// (cellListNeighborStructure::constructCandidateNeighborList, src/utility/cellListNeighborStructure.cpp:45-84) -- or takes the
+// explicit targets of a css_distance query, or everybody else in the all-to-all mode --, (2) flood-fills the local patch with the
+// rule of submesher::constructSubmeshFromSourceAndTargets (src/utility/submesher.cpp:55-147) into its workspace (shared memory
+// for the long-range tier, global memory for the whole-mesh tier), (3) runs exact window propagation (Chen-Han unfolding with the
+// Xin-Wang vertex-distance filter; saddle and patch-boundary vertices are pseudo-sources) over a FIFO ring of windows, one window
+// per thread and pass, (4) answers the K target queries (distance, start tangent, end tangent), which replaces
+// CGAL::Surface_mesh_shortest_path as used at src/models/triangulatedMeshSpace.cpp:189-203, :212-238 and
+// src/utility/meshUtilities.cpp:360-380, and (5) optionally accumulates the pair force of force::computeForces
+// (src/forces/baseForce.cpp:12-28) in neighbour order and applies the velocity half-kick (src/updaters/velocityVerletNVE.cpp:27-28).
+// The short-range work of a step never comes here: it runs on the two-stage record kernels (stencil_kernel.cu / patch_kernel.cu,
+// window_half_kernel.cu / window_kernel.cu); this kernel takes what outgrows their records, explicit queries and the all-to-all mode.
 //
 // Decisions that fix topology (candidate membership/order, patch membership) use exactly-rounded
 // arithmetic (common.cuh x* helpers) and are bit-identical to the CPU oracle; the window geometry is
@@ -28,9 +27,9 @@ static __device__ __forceinline__ double dinf() { return __longlong_as_double(0x
 
 enum { ST_OK = 0, ST_OVERFLOW = 1, ST_OVF_K = 1, ST_OVF_F = 2, ST_OVF_V = 3, ST_OVF_RING = 4 };
 
-struct WS { // per-warp workspace, carved from one contiguous block; arrays addressed as base + k*capacity
+struct WS { // per-source workspace (one per CTA), carved from one contiguous block; arrays addressed as base + k*capacity
     double *dv, *dt, *dr, *root;     // per-vertex [7*maxV], per-target [13*kt], ring [9*ring], root frame [16]
-    unsigned long long* wcnt;        // [16] per-warp counters
+    unsigned long long* wcnt;        // [16] per-CTA counters
     int *gface, *gvert, *fhKey, *vhKey, *tIdx, *tGFace, *rmeta, *misc;
     unsigned short *fvert /*4*maxF*/, *fadj /*4*maxF*/, *fhVal, *vhVal, *tFace, *tCorner /*4*kt*/, *rpsv;
     unsigned char *velig, *vdirty;
@@ -136,12 +135,6 @@ __device__ __forceinline__ double warpMax(double v)
     for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
     return v;
 }
-__device__ __forceinline__ double warpMin(double v)
-{
-#pragma unroll
-    for (int o = 16; o; o >>= 1) v = fmin(v, __shfl_xor_sync(FULL, v, o));
-    return v;
-}
 
 __device__ __forceinline__ bool atomicMinD(double* addr, double v)
 { // non-negative doubles order like their bit patterns
@@ -158,14 +151,6 @@ __device__ __forceinline__ double hitParam(const v2& S, const v2& P, const v2& X
     double mu = cross2(S - X, d) * frcp(den);
     if (!(mu == mu)) mu = 0.5;
     return fmin(1.0, fmax(0.0, mu));
-}
-__device__ __forceinline__ double segDist(const v2& S, const v2& X0, const v2& X1)
-{
-    v2 e = X1 - X0;
-    double L2 = e.x * e.x + e.y * e.y;
-    double s = L2 > 0 ? ((S.x - X0.x) * e.x + (S.y - X0.y) * e.y) / L2 : 0.0;
-    s = fmin(1.0, fmax(0.0, s));
-    return dist2(S, v2{X0.x + s * e.x, X0.y + s * e.y});
 }
 
 // fast (not correctly rounded, ~1 ulp) reciprocal / square root: hardware seed + Newton steps.  Used for the
@@ -226,729 +211,13 @@ __device__ __forceinline__ d3 pairForce(const ForceParams& fp, const d3& sep, do
     return d3{-pre * sep.x, -pre * sep.y, -pre * sep.z};
 }
 
-// ---------------------------------------------------------------------------------------------------
-template <bool GLOBAL_WS>
-__device__ int processSource(const GeoArgs& a, const WS& w, int li, int lane)
-{
-    const GeoCaps& cp = a.caps;
-    unsigned long long* cnt = w.wcnt;
-    const long long tp0 = clock64();
-    const bool explicitQ = a.xK >= 0;
-    const int gi = a.minIdx + li;
-    const int maskF = cp.hashF - 1, maskV = cp.hashV - 1, maskR = cp.ring - 1;
-
-    // ---------------- source ----------------
-    int sf;
-    double sb0, sb1, sb2;
-    d3 sp;
-    if (explicitQ) {
-        sf = a.xSrcFace;
-        sb0 = a.xSrcBary[0], sb1 = a.xSrcBary[1], sb2 = a.xSrcBary[2];
-        int4 c = __ldg(a.m.corner + sf);
-        sp = xpoint(ldvert(a.m, c.x), ldvert(a.m, c.y), ldvert(a.m, c.z), sb0, sb1, sb2);
-    } else {
-        sf = a.face[gi];
-        sb0 = a.bary[3 * gi], sb1 = a.bary[3 * gi + 1], sb2 = a.bary[3 * gi + 2];
-        sp = d3{a.eucl[3 * gi], a.eucl[3 * gi + 1], a.eucl[3 * gi + 2]};
-    }
-
-    // ---------------- 1. ordered candidates ----------------
-    int K = 0;
-    double R;
-    if (explicitQ) {
-        K = a.xK;
-        R = a.xThreshold;
-        if (K > cp.kt) return ST_OVF_K;
-        for (int t = lane; t < K; t += 32) w.tIdx[t] = t;
-    } else if (a.cellStart) {
-        const CellGrid& g = a.grid;
-        int ix = cellCoord(g, sp.x, 0), iy = cellCoord(g, sp.y, 1), iz = cellCoord(g, sp.z, 2);
-        int x0 = max(0, ix - 1), x1 = min(g.n[0] - 1, ix + 1);
-        int y0 = max(0, iy - 1), y1 = min(g.n[1] - 1, iy + 1);
-        int z0 = max(0, iz - 1), z1 = min(g.n[2] - 1, iz + 1);
-        int ny = y1 - y0 + 1, nz = z1 - z0 + 1, ncell = (x1 - x0 + 1) * ny * nz;
-        int s0 = 0, s1 = 0;
-        if (lane < ncell) { // stencil order: xx outer, yy, zz inner (hyperRectangularCellList.cpp:141-144)
-            int xx = x0 + lane / (ny * nz), rem = lane % (ny * nz);
-            int yy = y0 + rem / nz, zz = z0 + rem % nz;
-            int c = xx + yy * g.n[0] + zz * g.n[0] * g.n[1];
-            s0 = a.cellStart[c];
-            s1 = s0 + a.cellCount[c];
-        }
-        int mine = 0;
-        double maxd2 = 0;
-        for (int s = s0; s < s1; ++s) {
-            int j = a.cellItems[s];
-            if (j == gi) continue;
-            d3 q{a.eucl[3 * j], a.eucl[3 * j + 1], a.eucl[3 * j + 2]};
-            double d2 = xsqlen(xsub3(sp, q));
-            if (d2 < g.range2) {
-                mine++;
-                maxd2 = d2 > maxd2 ? d2 : maxd2;
-            }
-        }
-        int incl = warpInclusiveScan(mine, lane);
-        K = __shfl_sync(FULL, incl, 31);
-        maxd2 = warpMax(maxd2);
-        R = xsqrt(maxd2);
-        if (K > cp.kt) return ST_OVF_K;
-        int pos = incl - mine;
-        for (int s = s0; s < s1; ++s) {
-            int j = a.cellItems[s];
-            if (j == gi) continue;
-            d3 q{a.eucl[3 * j], a.eucl[3 * j + 1], a.eucl[3 * j + 2]};
-            double d2 = xsqlen(xsub3(sp, q));
-            if (d2 < g.range2) w.tIdx[pos++] = j;
-        }
-    } else { // baseNeighborStructure::constructCandidateNeighborList: everybody else, VERYLARGEDOUBLE
-        K = a.nTotal - 1;
-        R = 1e20;
-        if (K > cp.kt) return ST_OVF_K;
-        for (int t = lane; t < K; t += 32) w.tIdx[t] = t < gi ? t : t + 1;
-    }
-    if (!explicitQ && K > a.kmax) {
-        if (lane == 0) atomicMax(a.counters + C_KMAX_NEED, (unsigned long long)K), atomicAdd(a.counters + C_KMAX_OVERFLOW, 1ull);
-        K = a.kmax; // truncated; the host grows kmax and reruns
-    }
-    __syncwarp();
-    if (K == 0) {
-        if (lane == 0) cnt[C_SOURCES]++;
-        if (!explicitQ && lane == 0) {
-            a.nbrCount[li] = 0;
-            if (a.forceMode) {
-                d3 f = a.zero ? d3{0, 0, 0} : d3{a.frc[3 * li], a.frc[3 * li + 1], a.frc[3 * li + 2]};
-                a.frc[3 * li] = f.x, a.frc[3 * li + 1] = f.y, a.frc[3 * li + 2] = f.z;
-            }
-        }
-        return ST_OK;
-    }
-    // triangulatedMeshSpace::distanceWithSubmeshing :167-169
-    double thr2 = dinf();
-    if (a.submeshing) {
-        double thr = a.maxDist;
-        if (R < a.maxDist) thr = R;
-        thr2 = xmul(thr, thr);
-    }
-
-    // ---------------- 2. targets ----------------
-    for (int t = lane; t < K; t += 32) {
-        int tf;
-        double b0, b1, b2;
-        d3 tp;
-        if (explicitQ) {
-            tf = a.xTgtFace[t];
-            b0 = a.xTgtBary[3 * t], b1 = a.xTgtBary[3 * t + 1], b2 = a.xTgtBary[3 * t + 2];
-            int4 c = __ldg(a.m.corner + tf);
-            tp = xpoint(ldvert(a.m, c.x), ldvert(a.m, c.y), ldvert(a.m, c.z), b0, b1, b2);
-        } else {
-            int j = w.tIdx[t];
-            tf = a.face[j];
-            b0 = a.bary[3 * j], b1 = a.bary[3 * j + 1], b2 = a.bary[3 * j + 2];
-            tp = d3{a.eucl[3 * j], a.eucl[3 * j + 1], a.eucl[3 * j + 2]};
-        }
-        w.tGFace[t] = tf;
-        w.tb0()[t] = b0, w.tb1()[t] = b1, w.tb2()[t] = b2;
-        w.tpx()[t] = tp.x, w.tpy()[t] = tp.y, w.tpz()[t] = tp.z;
-        w.tbest()[t] = dinf();
-        w.tsx()[t] = 0, w.tsy()[t] = 0, w.tsz()[t] = 0;
-        w.tex()[t] = 0, w.tey()[t] = 0, w.tez()[t] = 0;
-    }
-    for (int h = lane; h < cp.hashF; h += 32) w.fhKey[h] = -1;
-    for (int h = lane; h < cp.hashV; h += 32) w.vhKey[h] = -1;
-    if (lane == 0) {
-        w.misc[0] = 0; // nF
-        w.misc[1] = 0; // nV
-        w.misc[2] = 0; // overflow
-    }
-    __syncwarp();
-
-    // ---------------- 3. patch flood fill (submesher.cpp:55-147) ----------------
-    auto addFace = [&](int g) {
-        bool isNew;
-        int slot = hashInsert(w.fhKey, maskF, g, isNew);
-        if (isNew) {
-            int id = atomicAdd(&w.misc[0], 1);
-            if (id < cp.maxF) {
-                w.gface[id] = g;
-                w.fhVal[slot] = (unsigned short)id;
-            } else
-                w.misc[2] = 1;
-        }
-    };
-    // hash tables are sized >= 2*maxF, so they cannot fill up before misc[2] trips; a tripped overflow
-    // is detected at the next warp-uniform check and the source is retried on a larger tier
-    if (lane == 0) addFace(sf);
-    __syncwarp();
-    bool anyGoal = false;
-    for (int t = lane; t < K; t += 32) anyGoal |= (w.tGFace[t] != sf);
-    anyGoal = __any_sync(FULL, anyGoal);
-    if (anyGoal) {
-        int4 sadj = __ldg(a.m.adj + sf);
-        if (lane < 3) {
-            int g = lane == 0 ? sadj.x : (lane == 1 ? sadj.y : sadj.z);
-            if (g >= 0) addFace(g);
-        }
-        __syncwarp();
-        bool missing = false;
-        for (int t = lane; t < K; t += 32) missing |= (hashFind(w.fhKey, maskF, w.tGFace[t]) < 0);
-        missing = __any_sync(FULL, missing);
-        if (missing) {
-            int head = 1;
-            for (;;) {
-                __syncwarp();
-                // one lane's view of the queue for the whole warp (see patch_kernel.cu)
-                int tail = min(__shfl_sync(FULL, w.misc[0], 0), cp.maxF);
-                if (__shfl_sync(FULL, w.misc[2], 0)) return ST_OVF_F;
-                if (head >= tail) break;
-                int idx = head + lane;
-                if (idx < tail) {
-                    int f = w.gface[idx];
-                    int4 ad = __ldg(a.m.adj + f);
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        int g = k == 0 ? ad.x : (k == 1 ? ad.y : ad.z);
-                        if (g < 0) continue;
-                        if (hashFind(w.fhKey, maskF, g) >= 0) continue;
-                        int4 c = __ldg(a.m.corner + g);
-                        bool far = xsqlen(xsub3(sp, ldvert(a.m, c.x))) > thr2 && xsqlen(xsub3(sp, ldvert(a.m, c.y))) > thr2
-                                   && xsqlen(xsub3(sp, ldvert(a.m, c.z))) > thr2;
-                        if (far) continue;
-                        if (w.misc[0] >= cp.maxF) { // full: a second look tells whether g is really missing (another lane may have added it)
-                            if (hashFind(w.fhKey, maskF, g) < 0) w.misc[2] = 1;
-                            continue;
-                        }
-                        addFace(g);
-                    }
-                }
-                head = min(head + 32, tail);
-            }
-            for (int t = lane; t < K; t += 32) // leftover goal faces (:143-144)
-                if (hashFind(w.fhKey, maskF, w.tGFace[t]) < 0) {
-                    if (w.misc[0] >= cp.maxF) w.misc[2] = 1;
-                    else addFace(w.tGFace[t]);
-                }
-        }
-    }
-    __syncwarp();
-    if (w.misc[2] || w.misc[0] > cp.maxF) return ST_OVF_F;
-    const int nF = w.misc[0];
-
-    // ---------------- 4. local indexing ----------------
-    for (int f = lane; f < nF; f += 32) { // pass 1: create vertex keys
-        int4 c = __ldg(a.m.corner + w.gface[f]);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            int gv = k == 0 ? c.x : (k == 1 ? c.y : c.z);
-            bool isNew;
-            int slot = hashInsert(w.vhKey, maskV, gv, isNew);
-            if (isNew) {
-                int id = atomicAdd(&w.misc[1], 1);
-                if (id < cp.maxV) {
-                    w.gvert[id] = gv;
-                    w.vhVal[slot] = (unsigned short)id;
-                } else
-                    w.misc[2] = 1;
-            }
-        }
-        if (w.misc[2]) break; // hash table might be full next: stop inserting
-    }
-    __syncwarp();
-    if (w.misc[2] || w.misc[1] > cp.maxV) return ST_OVF_V;
-    const int nV = w.misc[1];
-    for (int v = lane; v < nV; v += 32) {
-        int gv = w.gvert[v];
-        d3 p = ldvert(a.m, gv);
-        w.vx()[v] = p.x, w.vy()[v] = p.y, w.vz()[v] = p.z;
-        w.D()[v] = dinf();
-        w.velig[v] = a.m.saddle[gv];
-        w.vdirty[v] = 0;
-    }
-    __syncwarp();
-    for (int f = lane; f < nF; f += 32) { // pass 2: local corners + local adjacency + border eligibility
-        int gf = w.gface[f];
-        int4 c = __ldg(a.m.corner + gf);
-        int4 ad = __ldg(a.m.adj + gf);
-        unsigned short lv[3], la[3];
-        lv[0] = w.vhVal[hashFind(w.vhKey, maskV, c.x)];
-        lv[1] = w.vhVal[hashFind(w.vhKey, maskV, c.y)];
-        lv[2] = w.vhVal[hashFind(w.vhKey, maskV, c.z)];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            int g = k == 0 ? ad.x : (k == 1 ? ad.y : ad.z);
-            int s = g < 0 ? -1 : hashFind(w.fhKey, maskF, g);
-            la[k] = s < 0 ? (unsigned short)NONE16 : w.fhVal[s];
-        }
-#pragma unroll
-        for (int k = 0; k < 3; ++k)
-            if (la[k] == NONE16) {
-                w.velig[lv[(k + 1) % 3]] = 1;
-                w.velig[lv[(k + 2) % 3]] = 1;
-            }
-        w.fvert[4 * f] = lv[0], w.fvert[4 * f + 1] = lv[1], w.fvert[4 * f + 2] = lv[2], w.fvert[4 * f + 3] = (unsigned short)(ad.w & 63);
-        w.fadj[4 * f] = la[0], w.fadj[4 * f + 1] = la[1], w.fadj[4 * f + 2] = la[2], w.fadj[4 * f + 3] = 0;
-    }
-    for (int t = lane; t < K; t += 32) {
-        int s = hashFind(w.fhKey, maskF, w.tGFace[t]);
-        unsigned short lf = w.fhVal[s];
-        w.tFace[t] = lf;
-    }
-    __syncwarp();
-    for (int t = lane; t < K; t += 32) {
-        unsigned short lf = w.tFace[t];
-        w.tCorner[4 * t] = w.fvert[4 * lf], w.tCorner[4 * t + 1] = w.fvert[4 * lf + 1], w.tCorner[4 * t + 2] = w.fvert[4 * lf + 2];
-    }
-
-    // ---------------- 5. window propagation ----------------
-    // root frame (source face = local face 0): corner 0 at the origin, corner 1 on +x, corner 2 above
-    v2 rq0{0, 0}, rq1, rq2, S2;
-    {
-        unsigned short c0 = w.fvert[0], c1 = w.fvert[1], c2 = w.fvert[2];
-        d3 P0{w.vx()[c0], w.vy()[c0], w.vz()[c0]}, P1{w.vx()[c1], w.vy()[c1], w.vz()[c1]}, P2{w.vx()[c2], w.vy()[c2], w.vz()[c2]};
-        d3 e01{P1.x - P0.x, P1.y - P0.y, P1.z - P0.z}, e02{P2.x - P0.x, P2.y - P0.y, P2.z - P0.z};
-        double L01 = sqrt(e01.x * e01.x + e01.y * e01.y + e01.z * e01.z);
-        d3 ex{e01.x / L01, e01.y / L01, e01.z / L01};
-        double x2 = e02.x * ex.x + e02.y * ex.y + e02.z * ex.z;
-        d3 ey{e02.x - x2 * ex.x, e02.y - x2 * ex.y, e02.z - x2 * ex.z};
-        double y2 = sqrt(ey.x * ey.x + ey.y * ey.y + ey.z * ey.z);
-        ey = d3{ey.x / y2, ey.y / y2, ey.z / y2};
-        rq1 = v2{L01, 0};
-        rq2 = v2{x2, y2};
-        double bs = sb0 + sb1 + sb2;
-        S2 = v2{(sb1 * rq1.x + sb2 * rq2.x) / bs, (sb2 * rq2.y) / bs};
-        if (lane == 0) {
-            w.root[0] = ex.x, w.root[1] = ex.y, w.root[2] = ex.z, w.root[3] = ey.x, w.root[4] = ey.y, w.root[5] = ey.z;
-        }
-        // direct distances to the three corners of the source face
-        if (lane < 3) {
-            unsigned short cv = lane == 0 ? c0 : (lane == 1 ? c1 : c2);
-            d3 P = lane == 0 ? P0 : (lane == 1 ? P1 : P2);
-            d3 d{P.x - sp.x, P.y - sp.y, P.z - sp.z};
-            double L = sqrt(d.x * d.x + d.y * d.y + d.z * d.z);
-            w.D()[cv] = L;
-            w.dirx()[cv] = d.x / L, w.diry()[cv] = d.y / L, w.dirz()[cv] = d.z / L;
-            w.vdirty[cv] = 1;
-        }
-    }
-    __syncwarp();
-    auto liftRoot = [&](const v2& d, double& ox, double& oy, double& oz) {
-        double rx = d.x * w.root[0] + d.y * w.root[3], ry = d.x * w.root[1] + d.y * w.root[4], rz = d.x * w.root[2] + d.y * w.root[5];
-        double L = sqrt(rx * rx + ry * ry + rz * rz);
-        ox = rx / L, oy = ry / L, oz = rz / L;
-    };
-    // targets lying in the source face: the chord
-    for (int t = lane; t < K; t += 32)
-        if (w.tFace[t] == 0) {
-            d3 d{w.tpx()[t] - sp.x, w.tpy()[t] - sp.y, w.tpz()[t] - sp.z};
-            double L = sqrt(d.x * d.x + d.y * d.y + d.z * d.z);
-            w.tbest()[t] = L;
-            w.tsx()[t] = d.x / L, w.tsy()[t] = d.y / L, w.tsz()[t] = d.z / L;
-            w.tex()[t] = d.x / L, w.tey()[t] = d.y / L, w.tez()[t] = d.z / L;
-        }
-
-    int head = 0, tail = 0; // ring positions (monotone; index = pos & maskR)
-    bool overflow = false;
-    // root windows
-    {
-        Child ch;
-        ch.valid = 0;
-        if (lane < 3) {
-            int k = lane;
-            unsigned short g = w.fadj[k];
-            if (g != NONE16) {
-                int kk = (w.fvert[3] >> (2 * k)) & 3;
-                v2 q[3] = {rq0, rq1, rq2};
-                ch.valid = 1;
-                ch.meta = (int)g | (kk << 16);
-                ch.A = q[(k + 2) % 3];
-                ch.B = q[(k + 1) % 3];
-                ch.t0 = 0, ch.t1 = 1;
-            }
-        }
-        int incl = warpInclusiveScan(ch.valid, lane);
-        int tot = __shfl_sync(FULL, incl, 31);
-        if (ch.valid) {
-            int p = (tail + incl - 1) & maskR;
-            w.rax()[p] = ch.A.x, w.ray()[p] = ch.A.y, w.rbx()[p] = ch.B.x, w.rby()[p] = ch.B.y, w.rsx()[p] = S2.x, w.rsy()[p] = S2.y;
-            w.rt0()[p] = 0, w.rt1()[p] = 1, w.rsg()[p] = 0, w.rmeta[p] = ch.meta, w.rpsv[p] = NONE16;
-        }
-        tail += tot;
-    }
-    __syncwarp();
-
-    double U = dinf();
-    unsigned long long nWin = 0, nPs = 0;
-    long long tk0 = clock64(), clkFan = 0, clkBatch = 0;
-    if (lane == 0) atomicAdd(a.counters + C_CLK_PATCH, (unsigned long long)(tk0 - tp0));
-    for (;;) {
-        // ================= windows first: drain the ring =================
-        while (head != tail) {
-            long long tb0 = clock64();
-            // ---- bound U = max_t best[t] (window candidates so far)
-            {
-                double myMax = 0;
-                for (int t = lane; t < K; t += 32) myMax = fmax(myMax, w.tbest()[t]);
-                U = warpMax(myMax);
-            }
-            const double Ub = U * (1 + 1e-12);
-            int nb = min(32, tail - head);
-            bool active = lane < nb;
-            int p = (head + lane) & maskR;
-            head += nb;
-            v2 A{0, 0}, B{1, 0}, S{0, -1};
-            double t0 = 0, t1 = 1, sg = 0;
-            int meta = 0;
-            unsigned short psv = NONE16;
-            if (active) {
-                A = v2{w.rax()[p], w.ray()[p]}, B = v2{w.rbx()[p], w.rby()[p]}, S = v2{w.rsx()[p], w.rsy()[p]};
-                t0 = w.rt0()[p], t1 = w.rt1()[p], sg = w.rsg()[p], meta = w.rmeta[p], psv = w.rpsv[p];
-            }
-            __syncwarp(); // all reads of the ring slots done before anybody pushes
-            int g = meta & 0xFFFF, e = (meta >> 16) & 3;
-            v2 AB = B - A;
-            v2 P0 = lerp2(A, B, t0), P1 = lerp2(A, B, t1);
-            if (active && sg + asegDist(S, P0, P1) * (1 - 1e-5) > Ub) active = false; // bound may have tightened since the push
-            if (active) nWin++;
-            int iA = e == 2 ? 0 : e + 1, iB = e == 0 ? 2 : e - 1, iC = e;
-            unsigned short vA = 0, vB = 0, vC = 0;
-            v2 C{0, 1};
-            int kkbits = 0;
-            if (active) {
-                vA = w.fvert[4 * g + iA], vB = w.fvert[4 * g + iB], vC = w.fvert[4 * g + iC];
-                kkbits = w.fvert[4 * g + 3];
-                double PAx = w.vx()[vA], PAy = w.vy()[vA], PAz = w.vz()[vA];
-                double abx = w.vx()[vB] - PAx, aby = w.vy()[vB] - PAy, abz = w.vz()[vB] - PAz;
-                double acx = w.vx()[vC] - PAx, acy = w.vy()[vC] - PAy, acz = w.vz()[vC] - PAz;
-                double r = frcp(abx * abx + aby * aby + abz * abz);
-                double crx = aby * acz - abz * acy, cry = abz * acx - abx * acz, crz = abx * acy - aby * acx;
-                double cxn = (acx * abx + acy * aby + acz * abz) * r;
-                double cyn = fsqrt(crx * crx + cry * cry + crz * crz) * r;
-                C = v2{A.x + cxn * AB.x - cyn * AB.y, A.y + cxn * AB.y + cyn * AB.x};
-            }
-            // ---- queries: targets inside the entered face
-            for (int t = 0; t < K; ++t) {
-                bool has = active && w.tFace[t] == g;
-                if (!__any_sync(FULL, has)) continue;
-                double cand = dinf();
-                v2 dT{0, 0};
-                if (has) {
-                    double bA = iA == 0 ? w.tb0()[t] : (iA == 1 ? w.tb1()[t] : w.tb2()[t]);
-                    double bB = iB == 0 ? w.tb0()[t] : (iB == 1 ? w.tb1()[t] : w.tb2()[t]);
-                    double bC = iC == 0 ? w.tb0()[t] : (iC == 1 ? w.tb1()[t] : w.tb2()[t]);
-                    double bs = bA + bB + bC;
-                    v2 T{(bA * A.x + bB * B.x + bC * C.x) / bs, (bA * A.y + bB * B.y + bC * C.y) / bs};
-                    dT = T - S;
-                    double den = cross2(AB, dT);
-                    if (den != 0) {
-                        double mu = cross2(S - A, dT) / den;
-                        if (mu >= t0 - 1e-12 && mu <= t1 + 1e-12) cand = sg + len2(dT);
-                    }
-                }
-                double mn = warpMin(cand);
-                if (mn < w.tbest()[t]) {
-                    unsigned bal = __ballot_sync(FULL, cand == mn);
-                    if (lane == __ffs(bal) - 1) {
-                        w.tbest()[t] = cand;
-                        if (psv == NONE16) liftRoot(dT, w.tsx()[t], w.tsy()[t], w.tsz()[t]);
-                        else w.tsx()[t] = w.dirx()[psv], w.tsy()[t] = w.diry()[psv], w.tsz()[t] = w.dirz()[psv];
-                        if (a.nbrTe) { // end tangent: dT in the face's (u, u_perp) frame, lifted with the face's 3-D frame
-                            double PAx = w.vx()[vA], PAy = w.vy()[vA], PAz = w.vz()[vA];
-                            double abx = w.vx()[vB] - PAx, aby = w.vy()[vB] - PAy, abz = w.vz()[vB] - PAz;
-                            double acx = w.vx()[vC] - PAx, acy = w.vy()[vC] - PAy, acz = w.vz()[vC] - PAz;
-                            double L3 = sqrt(abx * abx + aby * aby + abz * abz);
-                            double U3x = abx / L3, U3y = aby / L3, U3z = abz / L3;
-                            double cx = acx * U3x + acy * U3y + acz * U3z;
-                            double wx = acx - cx * U3x, wy = acy - cx * U3y, wz = acz - cx * U3z;
-                            double cy = sqrt(wx * wx + wy * wy + wz * wz);
-                            double L2d = len2(AB);
-                            double ux = AB.x / L2d, uy = AB.y / L2d;
-                            double du = dT.x * ux + dT.y * uy, dw = (-dT.x * uy + dT.y * ux) / cy;
-                            double rx = du * U3x + dw * wx, ry = du * U3y + dw * wy, rz = du * U3z + dw * wz;
-                            double L = sqrt(rx * rx + ry * ry + rz * rz);
-                            w.tex()[t] = rx / L, w.tey()[t] = ry / L, w.tez()[t] = rz / L;
-                        }
-                    }
-                }
-                __syncwarp();
-            }
-            // ---- children
-            Child c0, c1;
-            c0.valid = c1.valid = 0;
-            bool improved = false;
-            double dC = 0;
-            if (active) {
-                v2 dL = P0 - S, dR = P1 - S, dCv = C - S;
-                double sideL = cross2(dL, dCv), sideR = cross2(dR, dCv);
-                double lc2 = dCv.x * dCv.x + dCv.y * dCv.y;
-                float lcf = sqrtf((float)lc2);
-                double epsL = 1e-12 * (double)(alen2(dL) * lcf), epsR = 1e-12 * (double)(alen2(dR) * lcf);
-                bool inside = !(sideL > epsL) && !(sideR < -epsR);
-                double DA = w.D()[vA], DB = w.D()[vB], DC = w.D()[vC];
-                if (inside) {
-                    dC = sg + fsqrt(lc2);
-                    if (dC < DC) {
-                        improved = atomicMinD(&w.D()[vC], dC);
-                        DC = fmin(DC, dC);
-                    }
-                }
-                // Xin-Wang filter and bound test in float with a conservative margin: a window is dropped only
-                // when it is dominated by clearly more than the rounding of the approximation
-                const float keep = 1.f - 2e-5f;
-                float fsg = (float)sg, fDA = (float)DA, fDB = (float)DB, fDC = (float)DC;
-                float fUb = Ub < 1e30 ? (float)Ub * (1.f + 2e-5f) : 3e38f;
-                if (!(sideL > epsL)) { // edge C->A of this face (opposite corner B), seen from the neighbour as A->C
-                    unsigned short g2 = w.fadj[4 * g + iB];
-                    if (g2 != NONE16) {
-                        double m0 = hitParam(S, P0, A, C);
-                        double m1 = inside ? 1.0 : hitParam(S, P1, A, C);
-                        if (m1 - m0 > 1e-13) {
-                            v2 XA = lerp2(A, C, m0), XC = lerp2(A, C, m1);
-                            float sXA = fsg + adist2(S, XA), sXC = fsg + adist2(S, XC);
-                            bool dom = (fDA + adist2(A, XC) < sXC * keep) || (fDC + adist2(C, XA) < sXA * keep) || (fDB + adist2(B, XA) < sXA * keep);
-                            if (!dom && fsg + asegDist(S, XA, XC) <= fUb) {
-                                c0.valid = 1;
-                                c0.meta = (int)g2 | (((kkbits >> (2 * iB)) & 3) << 16);
-                                c0.A = A, c0.B = C, c0.t0 = m0, c0.t1 = m1;
-                            }
-                        }
-                    }
-                }
-                if (!(sideR < -epsR)) { // edge B->C of this face (opposite corner A), seen from the neighbour as C->B
-                    unsigned short g2 = w.fadj[4 * g + iA];
-                    if (g2 != NONE16) {
-                        double m0 = inside ? 0.0 : hitParam(S, P0, C, B);
-                        double m1 = hitParam(S, P1, C, B);
-                        if (m1 - m0 > 1e-13) {
-                            v2 XC = lerp2(C, B, m0), XB = lerp2(C, B, m1);
-                            float sXC = fsg + adist2(S, XC), sXB = fsg + adist2(S, XB);
-                            bool dom = (fDB + adist2(B, XC) < sXC * keep) || (fDC + adist2(C, XB) < sXB * keep) || (fDA + adist2(A, XB) < sXB * keep);
-                            if (!dom && fsg + asegDist(S, XC, XB) <= fUb) {
-                                c1.valid = 1;
-                                c1.meta = (int)g2 | (((kkbits >> (2 * iA)) & 3) << 16);
-                                c1.A = C, c1.B = B, c1.t0 = m0, c1.t1 = m1;
-                            }
-                        }
-                    }
-                }
-            }
-            __syncwarp();
-            if (improved && dC == w.D()[vC]) { // winner writes the start direction carried to this vertex
-                if (psv == NONE16) liftRoot(C - S, w.dirx()[vC], w.diry()[vC], w.dirz()[vC]);
-                else w.dirx()[vC] = w.dirx()[psv], w.diry()[vC] = w.diry()[psv], w.dirz()[vC] = w.dirz()[psv];
-                w.vdirty[vC] = 1;
-            }
-            int mine = c0.valid + c1.valid;
-            int incl = warpInclusiveScan(mine, lane);
-            int tot = __shfl_sync(FULL, incl, 31);
-            if (tail + tot - head > cp.ring) return ST_OVF_RING;
-            int pos = tail + incl - mine;
-            if (c0.valid) {
-                int q = pos & maskR;
-                w.rax()[q] = c0.A.x, w.ray()[q] = c0.A.y, w.rbx()[q] = c0.B.x, w.rby()[q] = c0.B.y, w.rsx()[q] = S.x, w.rsy()[q] = S.y;
-                w.rt0()[q] = c0.t0, w.rt1()[q] = c0.t1, w.rsg()[q] = sg, w.rmeta[q] = c0.meta, w.rpsv[q] = psv;
-                pos++;
-            }
-            if (c1.valid) {
-                int q = pos & maskR;
-                w.rax()[q] = c1.A.x, w.ray()[q] = c1.A.y, w.rbx()[q] = c1.B.x, w.rby()[q] = c1.B.y, w.rsx()[q] = S.x, w.rsy()[q] = S.y;
-                w.rt0()[q] = c1.t0, w.rt1()[q] = c1.t1, w.rsg()[q] = sg, w.rmeta[q] = c1.meta, w.rpsv[q] = psv;
-            }
-            tail += tot;
-            __syncwarp();
-            clkBatch += clock64() - tb0;
-        }
-
-        // ================= ring empty: vertex candidates, then pseudo-source fans =================
-        long long tf0 = clock64();
-        // ---- vertex -> target candidates (a path may end with a straight leg from a corner of the target's face)
-        {
-            double myMax = 0;
-            for (int t = lane; t < K; t += 32) {
-                double best = w.tbest()[t];
-                if (w.tFace[t] != 0) {
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        unsigned short cv = w.tCorner[4 * t + k];
-                        double dv = w.D()[cv];
-                        if (dv < best) {
-                            d3 ee{w.tpx()[t] - w.vx()[cv], w.tpy()[t] - w.vy()[cv], w.tpz()[t] - w.vz()[cv]};
-                            double L = sqrt(ee.x * ee.x + ee.y * ee.y + ee.z * ee.z);
-                            if (dv + L < best) {
-                                best = dv + L;
-                                w.tbest()[t] = best;
-                                w.tsx()[t] = w.dirx()[cv], w.tsy()[t] = w.diry()[cv], w.tsz()[t] = w.dirz()[cv];
-                                w.tex()[t] = ee.x / L, w.tey()[t] = ee.y / L, w.tez()[t] = ee.z / L;
-                            }
-                        }
-                    }
-                }
-                myMax = fmax(myMax, best);
-            }
-            U = warpMax(myMax);
-        }
-        const double Ub = U * (1 + 1e-12);
-        __syncwarp();
-        // ---- pseudo-source fans.  A vertex v can lie on a shortest path to target t only if
-        //      D[v] + |x_v - x_t| (Euclidean lower bound of the remaining leg) beats the best path known to t.
-        bool spawned = false;
-        for (int v0 = 0; v0 < nV; v0 += 32) {
-            int v = v0 + lane;
-            bool fl = v < nV && w.vdirty[v] && w.velig[v] && w.D()[v] <= Ub;
-            if (v < nV) w.vdirty[v] = 0;
-            if (fl) {
-                bool useful = false;
-                double Dv = w.D()[v], px = w.vx()[v], py = w.vy()[v], pz = w.vz()[v];
-                for (int t = 0; t < K && !useful; ++t) {
-                    double ex = w.tpx()[t] - px, ey = w.tpy()[t] - py, ez = w.tpz()[t] - pz;
-                    float lb = sqrtf((float)(ex * ex + ey * ey + ez * ez)) * (1.f - 2e-6f);
-                    useful = Dv + (double)lb < w.tbest()[t];
-                }
-                fl = useful;
-            }
-            unsigned bal = __ballot_sync(FULL, fl);
-            while (bal) {
-                int b = __ffs(bal) - 1;
-                bal &= bal - 1;
-                int pv = v0 + b;
-                spawned = true;
-                nPs++;
-                double Dv = w.D()[pv];
-                d3 Pv{w.vx()[pv], w.vy()[pv], w.vz()[pv]};
-                double dvx = w.dirx()[pv], dvy = w.diry()[pv], dvz = w.dirz()[pv];
-                for (int f0 = 0; f0 < nF; f0 += 32) {
-                    int f = f0 + lane;
-                    Child ch;
-                    ch.valid = 0;
-                    if (f < nF) {
-                        int i = -1;
-                        unsigned short c0 = w.fvert[4 * f], c1 = w.fvert[4 * f + 1], c2 = w.fvert[4 * f + 2];
-                        if (c0 == pv) i = 0;
-                        else if (c1 == pv) i = 1;
-                        else if (c2 == pv) i = 2;
-                        if (i >= 0) {
-                            unsigned short vp = i == 0 ? c1 : (i == 1 ? c2 : c0), vq = i == 0 ? c2 : (i == 1 ? c0 : c1);
-                            d3 ep{w.vx()[vp] - Pv.x, w.vy()[vp] - Pv.y, w.vz()[vp] - Pv.z}, eq{w.vx()[vq] - Pv.x, w.vy()[vq] - Pv.y, w.vz()[vq] - Pv.z};
-                            double lp = fsqrt(ep.x * ep.x + ep.y * ep.y + ep.z * ep.z), lq = fsqrt(eq.x * eq.x + eq.y * eq.y + eq.z * eq.z);
-                            // edge paths
-                            if (atomicMinD(&w.D()[vp], Dv + lp)) w.vdirty[vp] = 2;
-                            if (atomicMinD(&w.D()[vq], Dv + lq)) w.vdirty[vq] = 2;
-                            unsigned short g2 = w.fadj[4 * f + i];
-                            if (g2 != NONE16) {
-                                double rlp = frcp(lp);
-                                double qx = (eq.x * ep.x + eq.y * ep.y + eq.z * ep.z) * rlp;
-                                d3 cr{ep.y * eq.z - ep.z * eq.y, ep.z * eq.x - ep.x * eq.z, ep.x * eq.y - ep.y * eq.x};
-                                double qy = fsqrt(cr.x * cr.x + cr.y * cr.y + cr.z * cr.z) * rlp;
-                                int kk = (w.fvert[4 * f + 3] >> (2 * i)) & 3;
-                                ch.valid = 1;
-                                ch.meta = (int)g2 | (kk << 16);
-                                ch.A = v2{qx, qy};
-                                ch.B = v2{lp, 0};
-                                ch.t0 = 0, ch.t1 = 1;
-                                if (Dv + asegDist(v2{0, 0}, ch.A, ch.B) * (1 - 1e-5) > Ub) ch.valid = 0;
-                            }
-                        }
-                    }
-                    __syncwarp();
-                    // vertices improved along an edge inherit the pseudo-source's start direction
-                    if (f < nF) {
-#pragma unroll
-                        for (int k = 0; k < 3; ++k) {
-                            unsigned short cv = w.fvert[4 * f + k];
-                            if (w.vdirty[cv] == 2) {
-                                w.dirx()[cv] = dvx, w.diry()[cv] = dvy, w.dirz()[cv] = dvz;
-                            }
-                        }
-                    }
-                    __syncwarp();
-                    if (f < nF) {
-#pragma unroll
-                        for (int k = 0; k < 3; ++k) {
-                            unsigned short cv = w.fvert[4 * f + k];
-                            if (w.vdirty[cv] == 2) w.vdirty[cv] = 1;
-                        }
-                    }
-                    int incl = warpInclusiveScan(ch.valid, lane);
-                    int tot = __shfl_sync(FULL, incl, 31);
-                    if (tail + tot - head > cp.ring) overflow = true;
-                    else if (ch.valid) {
-                        int p = (tail + incl - 1) & maskR;
-                        w.rax()[p] = ch.A.x, w.ray()[p] = ch.A.y, w.rbx()[p] = ch.B.x, w.rby()[p] = ch.B.y, w.rsx()[p] = 0, w.rsy()[p] = 0;
-                        w.rt0()[p] = 0, w.rt1()[p] = 1, w.rsg()[p] = Dv, w.rmeta[p] = ch.meta, w.rpsv[p] = (unsigned short)pv;
-                    }
-                    if (!overflow) tail += tot;
-                    __syncwarp();
-                }
-            }
-        }
-        clkFan += clock64() - tf0;
-        if (overflow) return ST_OVF_RING;
-        if (!spawned) break;
-    }
-    if (lane == 0) {
-        cnt[C_PSEUDO] += nPs;
-        atomicAdd(a.counters + C_CLK_BATCH, (unsigned long long)clkBatch);
-        atomicAdd(a.counters + C_CLK_FAN, (unsigned long long)clkFan);
-        atomicAdd(a.counters + C_CLK_PROP, (unsigned long long)(clock64() - tk0));
-    }
-    {
-        unsigned long long w0 = nWin;
-        for (int o = 16; o; o >>= 1) w0 += __shfl_xor_sync(FULL, w0, o);
-        if (lane == 0) cnt[C_WINDOWS] += w0;
-    }
-
-    // ---------------- 6. results ----------------
-    unsigned long long nDis = 0;
-    for (int t = lane; t < K; t += 32) {
-        double d = w.tbest()[t];
-        if (!(d < dinf())) { // unreachable inside the patch
-            nDis++;
-            if (a.submeshing) { // triangulatedMeshSpace.cpp:198-203
-                d = 2.0 * a.maxDist;
-                w.tsx()[t] = 0, w.tsy()[t] = 0, w.tsz()[t] = 1;
-                w.tex()[t] = 0, w.tey()[t] = 0, w.tez()[t] = 1;
-            } else
-                d = -1.0;
-            w.tbest()[t] = d;
-        }
-        size_t o = explicitQ ? (size_t)t : (size_t)li * a.kmax + t;
-        if (a.nbrIdx && !explicitQ) a.nbrIdx[o] = w.tIdx[t];
-        a.nbrDist[o] = d;
-        if (a.nbrTs) a.nbrTs[3 * o] = w.tsx()[t], a.nbrTs[3 * o + 1] = w.tsy()[t], a.nbrTs[3 * o + 2] = w.tsz()[t];
-        if (a.nbrTe) a.nbrTe[3 * o] = w.tex()[t], a.nbrTe[3 * o + 1] = w.tey()[t], a.nbrTe[3 * o + 2] = w.tez()[t];
-    }
-    for (int o = 16; o; o >>= 1) nDis += __shfl_xor_sync(FULL, nDis, o);
-    __syncwarp();
-    if (lane == 0) {
-        cnt[C_DISCONNECTED] += nDis;
-        cnt[C_SOURCES]++;
-        cnt[C_QUERIES] += K;
-        cnt[C_PATCH_FACES] += nF;
-        cnt[C_PATCH_VERTS] += nV;
-        if (!explicitQ) {
-            a.nbrCount[li] = K;
-            if (a.forceMode) { // force::computeForces: accumulate in neighbour order
-                d3 f = a.zero ? d3{0, 0, 0} : d3{a.frc[3 * li], a.frc[3 * li + 1], a.frc[3 * li + 2]};
-                for (int t = 0; t < K; ++t) {
-                    d3 pf = pairForce(a.fp, d3{w.tsx()[t], w.tsy()[t], w.tsz()[t]}, w.tbest()[t]);
-                    f.x += pf.x, f.y += pf.y, f.z += pf.z;
-                }
-                a.frc[3 * li] = f.x, a.frc[3 * li + 1] = f.y, a.frc[3 * li + 2] = f.z;
-                if (a.kick != 0.0) { // velocityVerletNVE.cpp:27-28
-                    a.vel[3 * li] += a.kick * f.x, a.vel[3 * li + 1] += a.kick * f.y, a.vel[3 * li + 2] += a.kick * f.z;
-                }
-            }
-        }
-    }
-    return ST_OK;
-}
-
 // =====================================================================================================================
-// Block-cooperative variant for long-range sources: ONE CTA (CTA_NT threads) PER SOURCE on the same workspace layout.
-// The reference's default executable (N = 20 on torus_isotropic_remesh.off, range 2.6: patches of ~900 faces, ~7 000 windows
-// per source, triangulatedMeshSpace.cpp:212-238) leaves one warp alone on an SM with nothing to hide its latencies behind;
-// here CTA_NT (384) windows are popped per pass (one per thread, both children), children are compacted into the ring by a
-// two-level block scan (deterministic order), target and vertex improvements go through 64-bit atomic minima whose unique
-// last writer stores the start / end directions after a barrier, and all pseudo-source fans of a round are spawned in ONE
-// sweep over the (face, corner) pairs of the patch.  Same path set, same arithmetic per window as processSource above.
+// ONE CTA (CTA_NT threads) PER SOURCE.  The reference's default executable (N = 20 on torus_isotropic_remesh.off, range 2.6:
+// patches of ~830 faces, ~7 000 windows per source, triangulatedMeshSpace.cpp:212-238) would leave one warp alone on an SM with
+// nothing to hide its latencies behind (measured: 6.4 ms per step); here CTA_NT (384) windows are popped per pass (one per thread,
+// both children), children are compacted into the ring by a two-level block scan (deterministic order), target and vertex
+// improvements go through 64-bit atomic minima whose unique last writer stores the start / end directions after a barrier, and
+// all pseudo-source fans of a round are spawned in ONE sweep over the (face, corner) pairs of the patch (0.74 ms per step).
 // =====================================================================================================================
 #ifndef CSS_CTA_NT
 #define CSS_CTA_NT 384 // threads per source (build parameter; default-executable shape: 128 -> 0.87, 256 -> 0.67, 384 -> 0.63, 512 -> 0.65 ms)
@@ -1005,7 +274,7 @@ __device__ int processSourceCta(const GeoArgs& a, const WS& w, int li, int tid, 
         sp = d3{a.eucl[3 * gi], a.eucl[3 * gi + 1], a.eucl[3 * gi + 2]};
     }
 
-    // ---------------- 1. ordered candidates (every warp repeats the gather of processSource; warp 0 stores) ----------------
+    // ---------------- 1. ordered candidates (every warp repeats the gather; warp 0 stores) ----------------
     int K = 0;
     double R;
     if (explicitQ) {
@@ -1751,63 +1020,7 @@ __global__ void __launch_bounds__(CTA_NT, 1) k_geodesic_cta(GeoArgs a, size_t ws
     if (tid < 16 && cnt[tid]) atomicAdd(a.counters + tid, cnt[tid]);
 }
 
-template <bool GLOBAL_WS>
-__global__ void __launch_bounds__(128, 3) k_geodesic(GeoArgs a, size_t wsBytes)
-{
-    extern __shared__ __align__(16) char smem[];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int warpsPerBlock = blockDim.x >> 5;
-    char* base = GLOBAL_WS ? a.gws + ((size_t)blockIdx.x * warpsPerBlock + wib) * wsBytes : smem + (size_t)wib * wsBytes;
-    WS w;
-    wsLayout(a.caps, base, &w);
-    unsigned long long* cnt = w.wcnt;
-    PDL_ENTRY();
-    if (a.xK < 0 && strideGuardUp(a.counters)) return; // neighbour phase waiting for a larger stride (common.cuh); explicit queries are not affected
-    if (lane < 16) cnt[lane] = 0;
-    __syncwarp();
-
-    const int nSrc = a.srcList ? *a.srcCount : (a.xK >= 0 ? 1 : a.nLocal);
-    for (;;) {
-        int s = 0;
-        if (lane == 0) s = atomicAdd(a.workCounter, 1);
-        s = __shfl_sync(FULL, s, 0);
-        if (s >= nSrc) break;
-        int li = a.srcList ? a.srcList[s] : s;
-        long long tc0 = clock64();
-        int st = processSource<GLOBAL_WS>(a, w, li, lane);
-        if (lane == 0) atomicAdd(a.counters + C_CLK_TOTAL, (unsigned long long)(clock64() - tc0));
-        st = __shfl_sync(FULL, st, 0);
-        __syncwarp();
-        if (st != ST_OK && lane == 0) {
-            atomicAdd(a.counters + C_OVF_REASON + st - 1, 1ull);
-            if (a.lastTier) {
-                cnt[C_OVERFLOW]++;
-                if (a.xK < 0) a.nbrCount[li] = 0;
-            } else {
-                int r = atomicAdd(a.retryCount, 1);
-                a.retryList[r] = li;
-                cnt[C_TIER_RETRY]++;
-            }
-        }
-    }
-    __syncwarp();
-    if (lane < 16 && cnt[lane]) atomicAdd(a.counters + lane, cnt[lane]);
-}
-
 int geodesicMaxSmemPerBlock() { return 227 * 1024; }
-
-cudaError_t launchGeodesic(cudaStream_t st, const GeoArgs& a, int warpsPerBlock, int blocks)
-{
-    if (warpsPerBlock * 32 > 128) return cudaErrorInvalidConfiguration; // __launch_bounds__(128, 3)
-    size_t wsBytes = geoWorkspaceBytes(a.caps);
-    if (a.gws) {
-        return launchStep(k_geodesic<true>, blocks, warpsPerBlock * 32, 0, st, a, wsBytes);
-    } else {
-        size_t smem = wsBytes * warpsPerBlock;
-        cudaFuncSetAttribute(k_geodesic<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)geodesicMaxSmemPerBlock());
-        return launchStep(k_geodesic<false>, blocks, warpsPerBlock * 32, smem, st, a, wsBytes);
-    }
-}
 
 // block-cooperative tier: one CTA per source; workspace in shared memory (a.gws == nullptr, one block per SM) or in global memory
 // (block b uses a.gws + b * geoWorkspaceBytes(a.caps))

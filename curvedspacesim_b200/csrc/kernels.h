@@ -57,7 +57,6 @@ struct GeoArgs {
     int lastTier;
 };
 
-cudaError_t launchGeodesic(cudaStream_t st, const GeoArgs& a, int warpsPerBlock, int blocks);
 cudaError_t launchGeodesicCta(cudaStream_t st, const GeoArgs& a, int blocks); // one CTA per source (long-range tiers)
 
 // ---- two-stage tier-0 path: patch records (patch_kernel.cu) -> window propagation (window_kernel.cu) ----

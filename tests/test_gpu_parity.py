@@ -610,39 +610,40 @@ def test_error_convention(gpu_ctx_factory):
         ctx.distance(0, [0.3, 0.3, 0.4], [99], [[0.3, 0.3, 0.4]])
 
 
-def test_small_tiers_fall_back_without_changing_results():
-    """Force every source through the global-memory tier by shrinking the shared-memory tiers."""
+def test_long_range_kernel_agrees_with_the_large_record_tier():
+    """sphere_radius1-like patches (~150 faces) are served by the 240-face record tier (k_patch<Large> + k_windows<Large>, one warp
+    per source); CSS_MAX_LARGE=0 hands them straight on to the block-cooperative fused kernel (k_geodesic_cta).  Two independent
+    implementations of the propagation on the same inputs: same lists, distances and tangents to round-off."""
     code = r"""
 import sys, numpy as np
 sys.path.insert(0, %r); sys.path.insert(0, %r)
 from curvedspacesim_b200 import binding, meshes
 from helpers import make_state, interaction_range
 V, F = meshes.icosphere(16)
-corners, face, bary, vel = make_state(V, F, 200)
-area = float(meshes.face_areas(V, F).sum()); rc = interaction_range(area, 200)
+corners, face, bary, vel = make_state(V, F, 100)
+area = float(meshes.face_areas(V, F).sum()); rc = interaction_range(area, 100)
 ctx = binding.Context(0); ctx.set_mesh(V, corners); ctx.set_submeshing(True, rc); ctx.set_options(True, True); ctx.set_state(face, bary, vel)
 off, idx, d, ts, te = ctx.find_neighbors(rc, want_end=True)
 c = ctx.counters()
-np.savez(sys.argv[1], off=off, idx=idx, d=d, ts=ts, te=te, retry=c["tier_retry"], overflow=c["overflow"])
+np.savez(sys.argv[1], off=off, idx=idx, d=d, ts=ts, te=te, retry=c["tier_retry"], overflow=c["overflow"], faces=c["patch_faces"])
 """ % (ROOT, os.path.join(ROOT, "tests"))
     import tempfile
 
     outs = []
     with tempfile.TemporaryDirectory() as td:
-        for i, tune in enumerate((None, "8,8,16,4,4,24,20,32,8,1")):
+        for i, skip in enumerate((None, "0")):
             env = dict(os.environ)
-            env.pop("CSS_TUNE", None)
-            env.pop("CSS_LEGACY_TIER0", None)
-            if tune:  # fused tier 0 with tiny capacities: (almost) every source overflows into the next tiers
-                env["CSS_TUNE"] = tune
-                env["CSS_LEGACY_TIER0"] = "1"
+            env.pop("CSS_MAX_LARGE", None)
+            if skip is not None:
+                env["CSS_MAX_LARGE"] = skip
             out = os.path.join(td, "o%d.npz" % i)
             subprocess.check_call([sys.executable, "-c", code, out], env=env)
             outs.append(dict(np.load(out)))
     a, b = outs
-    assert int(b["retry"]) > int(a["retry"]) and int(b["overflow"]) == 0
-    assert np.array_equal(a["off"], b["off"]) and np.array_equal(a["idx"], b["idx"])
-    assert _rel(a["d"], b["d"]) < 1e-12 and np.max(np.abs(a["ts"] - b["ts"])) < 1e-10
+    assert int(a["faces"]) > 100 * 100 and int(a["retry"]) >= 80                  # the large tier is where these sources live ...
+    assert int(b["retry"]) >= int(a["retry"]) + 50 and int(b["overflow"]) == 0    # ... and with the switch they move on once more
+    assert np.array_equal(a["off"], b["off"]) and np.array_equal(a["idx"], b["idx"]) and len(a["idx"]) > 100
+    assert _rel(a["d"], b["d"]) < 1e-12 and np.max(np.abs(a["ts"] - b["ts"])) < 1e-10 and np.max(np.abs(a["te"] - b["te"])) < 1e-10
 
 
 def test_half_warp_and_one_warp_tier0_agree():
