@@ -340,7 +340,10 @@ def test_config3_elephant_fire_then_nose_hoover(gpu_ctx_factory):
     of, ob, ov, ofr = orc.get_state()
     gf, gb, gv, gfr = ctx.get_state()
     fl = (orc.walk_flags() != 0) | (ctx.walk_flags() != 0)
-    assert np.array_equal(of[~fl], gf[~fl]) and np.max(np.abs(ob - gb)[~fl]) < 1e-9 and np.max(np.abs(ov - gv)[~fl]) < 1e-9
+    # positions are compared in space: a barycentric coordinate on one of the elephant's smallest faces (edge ratio 13x) magnifies
+    # the same displacement by the inverse face size (measured after the 200 iterations: 7e-10 in barycentrics, 1e-11 in space)
+    assert np.array_equal(of[~fl], gf[~fl]) and np.max(np.abs(ov - gv)[~fl]) < 1e-9
+    assert np.max(np.abs(orc.euclidean(of, ob) - orc.euclidean(gf, gb))[~fl]) < 1e-9 and np.max(np.abs(ob - gb)[~fl]) < 1e-7
     assert np.max(np.abs(ofr - gfr)[~fl]) < TOL_FORCE * np.abs(ofr).max()
     # phase B: Nose-Hoover from the minimised positions with fresh Maxwell-Boltzmann velocities, 2 x 1000 steps
     vel2 = random_velocities(V, corners, of, 0.2, np.random.default_rng(99))
