@@ -75,6 +75,7 @@ struct css_ctx {
     int t2Warps = 32;
     // two-stage tier 0: patch records (stage 1) -> window propagation (stage 2)
     bool winLean = true, winHalf = true;
+    bool nvtOnDevice = true; // single-rank Nose-Hoover steps keep the chain on the device (CSS_NVT_HOST=1: host chain, one sync per step)
     int winWpb = 2;
     unsigned char *d_records = nullptr, *d_recordsL = nullptr;
     double* d_spill = nullptr; // window spill stacks of the two-sources-per-warp kernel (allocated once)
@@ -95,6 +96,11 @@ struct css_ctx {
         int M = 0;
         std::vector<double> bx, by, bz, bw;
         double KE = 0, scale = 1;
+        // single rank: the chain lives on the device (k_nh_chain), so css_step_nvt queues all its steps without a host round trip
+        double* d = nullptr;      // bx | by | bz | bw | KE, scale, T, dt2, dt4, dt8
+        int dM = 0;               // chain length the device block was allocated for
+        bool deviceNewer = false; // the device copy is ahead of the host mirror (css_nvt_state downloads it)
+        bool hostNewer = true;    // the host mirror has to be uploaded before the next device step
     } nh;
     struct FireState {
         double dt = 0.001, alpha = 0.99;
@@ -314,6 +320,7 @@ int css_create(css_ctx** out, int device)
     if (const char* v = getenv("CSS_NO_GRAPH")) ctx->useGraph = atoi(v) == 0;
     if (const char* v = getenv("CSS_WIN_LEAN")) ctx->winLean = atoi(v) != 0;
     if (const char* v = getenv("CSS_WIN_HALF")) ctx->winHalf = atoi(v) != 0; // 0: one warp per source in tier 0 (window_kernel.cu)
+    if (const char* v = getenv("CSS_NVT_HOST")) ctx->nvtOnDevice = atoi(v) == 0;
     if (const char* v = getenv("CSS_STENCIL")) ctx->useStencil = atoi(v) != 0; // 0: stage 1 of tier 0 flood-fills every patch (patch_kernel.cu)
     if (const char* v = getenv("CSS_WIN_WPB")) ctx->winWpb = std::max(1, std::min(4, atoi(v)));
     if (const char* v = getenv("CSS_P2P")) ctx->p2pEnabled = atoi(v) != 0;
@@ -346,6 +353,7 @@ int css_destroy(css_ctx* ctx)
     if (ctx->evFork) cudaEventDestroy(ctx->evFork);
     if (ctx->evJoin) cudaEventDestroy(ctx->evJoin);
     if (ctx->stCopy) cudaStreamDestroy(ctx->stCopy);
+    if (ctx->nh.d) cudaFree(ctx->nh.d);
     cudaStreamDestroy(ctx->st);
     delete ctx;
     return CSS_OK;
@@ -1564,6 +1572,40 @@ int css_nvt_init(css_ctx* ctx, double dt, double T, double tau, int M)
     for (int i = 1; i <= M; ++i) h.bw[i] = T * tau * tau;
     h.KE = h.bw[0];
     h.scale = 1.0;
+    h.hostNewer = true, h.deviceNewer = false;
+    return CSS_OK;
+}
+// host mirror <-> device block of the chain
+static int nhUpload(css_ctx* ctx)
+{
+    auto& h = ctx->nh;
+    const int M = h.M, n = 4 * (M + 1) + 6;
+    if (!h.d || h.dM != M) {
+        if (h.d) cudaFree(h.d);
+        h.d = nullptr;
+        CU(cudaMalloc(&h.d, sizeof(double) * n));
+        h.dM = M;
+    }
+    std::vector<double> buf(n);
+    for (int i = 0; i <= M; ++i) buf[i] = h.bx[i], buf[M + 1 + i] = h.by[i], buf[2 * (M + 1) + i] = h.bz[i], buf[3 * (M + 1) + i] = h.bw[i];
+    double* sc = buf.data() + 4 * (M + 1);
+    sc[0] = h.KE, sc[1] = h.scale, sc[2] = h.T, sc[3] = h.dt2, sc[4] = h.dt4, sc[5] = h.dt8;
+    CU(cudaMemcpyAsync(h.d, buf.data(), sizeof(double) * n, cudaMemcpyHostToDevice, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st)); // (buf is a local)
+    h.hostNewer = false, h.deviceNewer = false;
+    return CSS_OK;
+}
+static int nhDownload(css_ctx* ctx)
+{
+    auto& h = ctx->nh;
+    if (!h.deviceNewer || !h.d) return CSS_OK;
+    const int M = h.M, n = 4 * (M + 1) + 6;
+    std::vector<double> buf(n);
+    CU(cudaMemcpyAsync(buf.data(), h.d, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    for (int i = 0; i <= M; ++i) h.bx[i] = buf[i], h.by[i] = buf[M + 1 + i], h.bz[i] = buf[2 * (M + 1) + i], h.bw[i] = buf[3 * (M + 1) + i];
+    h.KE = buf[4 * (M + 1)], h.scale = buf[4 * (M + 1) + 1];
+    h.deviceNewer = false;
     return CSS_OK;
 }
 static void propagateChain(css_ctx* ctx) // noseHooverNVT.cpp:65-110
@@ -1599,6 +1641,64 @@ static void propagateChain(css_ctx* ctx) // noseHooverNVT.cpp:65-110
         h.by[ii] *= ef;
     }
 }
+// Single rank: every step of the call is queued without a host round trip.  The chain (k_nh_chain) and the velocity scaling read
+// the kinetic energy / the scale factor from device memory.  Like the NVE path the queue freezes behind the stride guard when a
+// particle first exceeds the neighbour stride (cell-list build of some step): the walker, the stage kernels, the chain and the
+// scaling all return at once, the state stays "after the first move of that step", and the host finishes the step and goes on.
+static int stepNvtDevice(css_ctx* ctx, const ForceParams& fp, double range, int nsteps)
+{
+    auto& h = ctx->nh;
+    int rc;
+    if (h.hostNewer && (rc = nhUpload(ctx))) return rc;
+    const int M = h.M;
+    double* scaleDev = h.d + 4 * (M + 1) + 1;
+    auto firstHalf = [&]() -> int { // chain, scale, displacement, move
+        launchNhChain(ctx->st, h.d, M, ctx->d_red, 0, ctx->d_counters);
+        launchScaleDev(ctx->st, ctx->nLocal, scaleDev, ctx->d_vel, ctx->d_counters);
+        launchAxpy(ctx->st, 3, ctx->nLocal, h.dt2, 0, ctx->d_vel, ctx->d_frc, ctx->d_disp);
+        ctx->hostKernels += 3;
+        return moveImpl(ctx, 0, 1, 0, 0.0);
+    };
+    auto secondHalf = [&]() -> int { // forces + kick, displacement, kinetic energy, move, chain, scale
+        int rc2 = findNeighborsImpl(ctx, range, 1, fp, 1, h.dt);
+        if (rc2) return rc2;
+        launchAxpy(ctx->st, 3, ctx->nLocal, h.dt2, 0, ctx->d_vel, ctx->d_frc, ctx->d_disp);
+        launchReduce(ctx->st, ctx->nLocal, ctx->d_vel, ctx->d_frc, ctx->d_partial, ctx->d_red);
+        ctx->hostKernels += 3;
+        if ((rc2 = moveImpl(ctx, 0, 1, 0, 0.0))) return rc2;
+        launchNhChain(ctx->st, h.d, M, ctx->d_red, 1, ctx->d_counters);
+        launchScaleDev(ctx->st, ctx->nLocal, scaleDev, ctx->d_vel, ctx->d_counters);
+        ctx->hostKernels += 2;
+        return CSS_OK;
+    };
+    h.deviceNewer = true;
+    int remaining = nsteps;
+    for (int attempt = 0; remaining > 0; ++attempt) {
+        if (attempt == 16) return fail(ctx, CSS_ECAPACITY, "neighbour stride keeps overflowing");
+        CU(cudaMemsetAsync(ctx->d_counters + C_STEP_GUARD, 0, sizeof(unsigned long long), ctx->st));
+        for (int s = 0; s < remaining; ++s) {
+            if ((rc = firstHalf())) return rc;
+            if ((rc = secondHalf())) return rc;
+        }
+        bool rerun = false;
+        int moves = 0;
+        if ((rc = checkCapacity(ctx, &rerun, &moves))) return rc; // synchronises
+        if (!rerun) break;
+        // the guard went up in the force phase of step (moves - 1) / 2: its first move happened, nothing after it did
+        const int done = (moves - 1) / 2;
+        if (moves < 1 || (moves & 1) == 0 || done >= remaining) return fail(ctx, CSS_ESTATE, "stride guard: inconsistent move count %d of %d steps", moves, remaining);
+        for (int a2 = 0;; ++a2) {
+            if ((rc = secondHalf())) return rc;
+            if ((rc = checkCapacity(ctx, &rerun))) return rc;
+            if (!rerun) break;
+            if (a2 == 8) return fail(ctx, CSS_ECAPACITY, "neighbour stride keeps overflowing");
+        }
+        remaining -= done + 1;
+    }
+    if (nsteps > 0) readPhaseTimes(ctx, true);
+    return CSS_OK;
+}
+
 int css_step_nvt(css_ctx* ctx, int kind, const double* params, int nsteps)
 {
     if (!ctx || !params) return CSS_EINVAL;
@@ -1607,6 +1707,9 @@ int css_step_nvt(css_ctx* ctx, int kind, const double* params, int nsteps)
     double range;
     ForceParams fp = mkForce(kind, params, &range);
     auto& h = ctx->nh;
+    if (ctx->nranks == 1 && ctx->nvtOnDevice) return stepNvtDevice(ctx, fp, range, nsteps);
+    if (int rcd = nhDownload(ctx)) return rcd;
+    h.hostNewer = true;
     for (int s = 0; s < nsteps; ++s) { // noseHooverNVT::performUpdate :42-59 and propagatePositionsVelocities :116-139
         propagateChain(ctx);
         launchAxpy(ctx->st, 2, ctx->nLocal, h.scale, 0, ctx->d_vel, ctx->d_frc, ctx->d_disp);
@@ -1638,6 +1741,8 @@ int css_step_nvt(css_ctx* ctx, int kind, const double* params, int nsteps)
 int css_nvt_state(css_ctx* ctx, double* bath, double* ke, double* scale)
 {
     if (!ctx || !ctx->nh.M) return fail(ctx, CSS_ESTATE, "css_nvt_init not called");
+    BIND();
+    if (int rcd = nhDownload(ctx)) return rcd;
     auto& h = ctx->nh;
     for (int i = 0; i <= h.M && bath; ++i) bath[4 * i] = h.bx[i], bath[4 * i + 1] = h.by[i], bath[4 * i + 2] = h.bz[i], bath[4 * i + 3] = h.bw[i];
     if (ke) *ke = h.KE;

@@ -1111,6 +1111,63 @@ void launchTransportGeneric(cudaStream_t st, const MeshDev& m, int n, int* face,
 {
     if (n > 0) k_transport_generic<<<gridFor(n, 128), 128, 0, st>>>(m, n, face, bary, disp, nVec, vecs, flags);
 }
+// Nose-Hoover chain on the device (noseHooverNVT.cpp:65-110, the same statements in the same order as the host version in css_api.cu;
+// this file is compiled without FMA contraction, so only exp() may differ from the host's libm in the last bit).  One thread.
+// nh = bx[M+1] | by[M+1] | bz[M+1] | bw[M+1] | KE, scale, T, dt2, dt4, dt8.  Frozen behind the stride guard like every step kernel.
+__global__ void k_nh_chain(double* __restrict__ nh, int M, const double* __restrict__ red, int takeKE, const unsigned long long* counters)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    if (strideGuardUp(counters)) return;
+    double *bx = nh, *by = nh + (M + 1), *bz = nh + 2 * (M + 1), *bw = nh + 3 * (M + 1), *sc = nh + 4 * (M + 1);
+    if (takeKE) sc[0] = red[4];
+    double KE = sc[0];
+    const double T = sc[2], dt2 = sc[3], dt4 = sc[4], dt8 = sc[5];
+    double ef = 0;
+    for (int ii = M - 1; ii > 0; --ii) {
+        bz[ii] = (bw[ii - 1] * by[ii - 1] * by[ii - 1] - T) / bw[ii];
+        ef = exp(-dt8 * by[ii + 1]);
+        by[ii] *= ef;
+        by[ii] += bz[ii] * dt4;
+        by[ii] *= ef;
+    }
+    bz[0] = (2.0 * KE / bw[0] - 1.0);
+    ef = exp(-dt8 * by[1]);
+    by[0] *= ef;
+    by[0] += bz[0] * dt4;
+    by[0] *= ef;
+    for (int ii = 0; ii < M; ++ii) bx[ii] += dt2 * by[ii];
+    const double scale = exp(-dt2 * by[0]);
+    KE = scale * scale * KE;
+    bz[0] = (2.0 * KE / bw[0] - 1.0);
+    ef = exp(-dt8 * by[1]);
+    by[0] *= ef;
+    by[0] += bz[0] * dt4;
+    by[0] *= ef;
+    for (int ii = 1; ii < M; ++ii) {
+        bz[ii] = (bw[ii - 1] * by[ii - 1] * by[ii - 1] - T) / bw[ii];
+        ef = exp(-dt8 * by[ii + 1]);
+        by[ii] *= ef;
+        by[ii] += bz[ii] * dt4;
+        by[ii] *= ef;
+    }
+    sc[0] = KE, sc[1] = scale;
+}
+// v *= *s with the factor in device memory (the chain's velocity scale); frozen behind the stride guard
+__global__ void k_scale_dev(int n, const double* __restrict__ s, double* __restrict__ vel, const unsigned long long* counters)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || strideGuardUp(counters)) return;
+    const double a = *s;
+    st3(vel, i, a * ld3(vel, i));
+}
+void launchNhChain(cudaStream_t st, double* nh, int M, const double* red, int takeKE, const unsigned long long* counters)
+{
+    k_nh_chain<<<1, 32, 0, st>>>(nh, M, red, takeKE, counters);
+}
+void launchScaleDev(cudaStream_t st, int n, const double* s, double* vel, const unsigned long long* counters)
+{
+    if (n > 0) k_scale_dev<<<gridFor(n, 256), 256, 0, st>>>(n, s, vel, counters);
+}
 void launchAxpy(cudaStream_t st, int op, int n, double a, double b, double* vel, const double* frc, double* disp)
 {
     if (n > 0) k_axpy<<<gridFor(n, 256), 256, 0, st>>>(op, n, a, b, vel, frc, disp);

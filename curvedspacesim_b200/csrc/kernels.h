@@ -228,6 +228,8 @@ void launchTransportGeneric(cudaStream_t st, const MeshDev& m, int n, int* face,
 void launchLocate(cudaStream_t st, const MeshDev& m, const double gmn[3], double h, const int gn[3], const int* cellStart, const int* cellFaces,
                   int n, const double* xyz, double clampTol, int* face, double* bary);
 void launchAxpy(cudaStream_t st, int op, int n, double a, double b, double* vel, const double* frc, double* disp);
+void launchNhChain(cudaStream_t st, double* nh, int M, const double* red, int takeKE, const unsigned long long* counters); // Nose-Hoover chain, device-resident
+void launchScaleDev(cudaStream_t st, int n, const double* s, double* vel, const unsigned long long* counters);
 void launchReduce(cudaStream_t st, int n, const double* vel, const double* frc, double* partial, double* out);
 void launchEnergy(cudaStream_t st, int nLocal, int kmax, const int* nbrCount, const double* nbrDist, ForceParams fp, double* partial,
                   double* out);
