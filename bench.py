@@ -286,13 +286,20 @@ def main():
             flush_buf.zero_()
             torch.cuda.synchronize()
 
+    def align():
+        """Multi-rank: the ranks leave the host barrier tens of microseconds apart, and a step's first exchange would wait for the
+        latest one inside the timed region.  An (untimed, idempotent) position all-gather queued right before the start event makes
+        every rank's stream wait for the others on the device, so the timed steps start together."""
+        if world > 1:
+            dist.barrier()
+            ctx.gather_positions()
+
     def timed_steps(k):
         """k steps, each timed with CUDA events on the launching stream, L2 flushed (untimed) in between."""
         ms = []
         for _ in range(k):
             flush()
-            if world > 1:
-                dist.barrier()
+            align()
             ctx.timer_record(0)
             step(1)
             ctx.timer_record(1)
@@ -324,8 +331,7 @@ def main():
     inst_ms, geo_ms, walk_ms, cell_ms, patch_ms, win_ms, retry_ms, gather_ms = [], [], [], [], [], [], [], []
     for _ in range(args.steps):
         flush()
-        if world > 1:
-            dist.barrier()
+        align()
         ctx.timer_record(0)
         step(1)
         ctx.timer_record(1)
@@ -371,8 +377,7 @@ def main():
     te_step, te_geo = [], []
     for _ in range(args.steps):
         flush()
-        if world > 1:
-            dist.barrier()
+        align()
         ctx.timer_record(0)
         step(1)
         ctx.timer_record(1)
