@@ -1483,24 +1483,6 @@ int css_step_nve_host(css_ctx* ctx, int kind, const double* params, double dt, i
     return CSS_OK;
 }
 
-// force phase of the host-driven updaters (GD, NVT, FIRE) with the host half of the stride guard: the counters are read after
-// the phase (one small copy + synchronisation; these updaters synchronise every step anyway) and the phase is repeated with a
-// larger stride when the guard went up.  Nothing downstream of the cell list ran in that case, so repeating is exact.
-static int forcesGuarded(css_ctx* ctx, double range, const ForceParams& fp, double kick)
-{
-    for (int attempt = 0; attempt < 10; ++attempt) {
-        int rc = findNeighborsImpl(ctx, range, 1, fp, 1, kick);
-        if (rc) return rc;
-        unsigned long long ovf = 0;
-        CU(cudaMemcpyAsync(&ovf, ctx->d_counters + C_KMAX_OVERFLOW, sizeof ovf, cudaMemcpyDeviceToHost, ctx->st));
-        CU(cudaStreamSynchronize(ctx->st));
-        if (!ovf) return CSS_OK;
-        bool rerun = false;
-        if ((rc = checkCapacity(ctx, &rerun))) return rc;
-    }
-    return fail(ctx, CSS_ECAPACITY, "neighbour stride keeps overflowing");
-}
-
 int css_step_gd(css_ctx* ctx, int kind, const double* params, double dt, int nsteps)
 {
     if (!ctx || !params) return CSS_EINVAL;
@@ -1508,12 +1490,26 @@ int css_step_gd(css_ctx* ctx, int kind, const double* params, double dt, int nst
     BIND();
     double range;
     ForceParams fp = mkForce(kind, params, &range);
-    for (int s = 0; s < nsteps; ++s) {
-        int rc = forcesGuarded(ctx, range, fp, 0.0);
-        if (rc) return rc;
-        launchAxpy(ctx->st, 1, ctx->nLocal, dt, 0, ctx->d_vel, ctx->d_frc, ctx->d_disp);
-        ctx->hostKernels++;
-        if ((rc = moveImpl(ctx, 0, 0, 0, 0.0))) return rc;
+    // All steps are queued without a host round trip.  When a particle first exceeds the neighbour stride, the force phase of that
+    // step and every move after it return at once behind the stride guard (common.cuh); the walker's move counter then tells how
+    // many steps are complete, the stride is regrown and the rest of the call is queued again.
+    int remaining = nsteps;
+    for (int attempt = 0; remaining > 0; ++attempt) {
+        if (attempt == 16) return fail(ctx, CSS_ECAPACITY, "neighbour stride keeps overflowing");
+        CU(cudaMemsetAsync(ctx->d_counters + C_STEP_GUARD, 0, sizeof(unsigned long long), ctx->st));
+        for (int s = 0; s < remaining; ++s) {
+            int rc = findNeighborsImpl(ctx, range, 1, fp, 1, 0.0);
+            if (rc) return rc;
+            launchAxpy(ctx->st, 1, ctx->nLocal, dt, 0, ctx->d_vel, ctx->d_frc, ctx->d_disp);
+            ctx->hostKernels++;
+            if ((rc = moveImpl(ctx, 0, 0, 0, 0.0))) return rc;
+        }
+        bool rerun = false;
+        int moves = 0;
+        if (int rc = checkCapacity(ctx, &rerun, &moves)) return rc; // synchronises
+        if (!rerun) return CSS_OK;
+        if (moves < 0 || moves >= remaining) return fail(ctx, CSS_ESTATE, "stride guard: inconsistent move count %d of %d steps", moves, remaining);
+        remaining -= moves; // the step that raised the guard did nothing: it starts again with its force phase
     }
     return checkCapacity(ctx, nullptr);
 }
